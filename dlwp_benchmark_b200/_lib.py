@@ -1,0 +1,67 @@
+"""ctypes binding of the C-ABI kernel library ``libspectral_b200.so`` (include/spectral_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+caller gets an exception (the product path must never silently run on the CPU / on torch.fft).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspectral_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+_vp, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+
+# name -> (restype, argtypes); mirrors include/spectral_b200.h one to one
+SIGNATURES = {
+    "sb200_version": (_i, []),
+    "sb200_last_error": (ctypes.c_char_p, []),
+    "sb200_device_arch": (_i, []),
+    "sb200_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _d, _d]),
+    "sb200_plan_destroy": (_i, [_vp]),
+    "sb200_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "sb200_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "sb200_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "sb200_modes_gemm": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
+    "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),
+    "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "sb200_gelu_fwd": (_i, [_vp, _vp, _i64, _vp]),
+    "sb200_gelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+}
+
+
+class SpectralB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SpectralB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C dlwp_benchmark_b200/csrc`. There is no CPU / torch.fft fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().sb200_last_error().decode("utf-8", "replace")
+        raise SpectralB200Error(f"{what or 'spectral_b200'} failed (rc={rc}): {msg}")

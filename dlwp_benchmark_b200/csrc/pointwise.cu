@@ -1,0 +1,396 @@
+// Fused row synthesis + pointwise (1x1) channel mix + epilogue, and the pointwise weight
+// gradient.  fp32 CUDA-core versions (exact-fp32 parity path, any shape with W % 4 == 0).
+//
+// Replaces, per FNO block (neuralop FNOBlocks.forward_with_postactivation):
+//   irfftn's W-axis half + `+ bias` + fno_skips[l] (Conv2d 1x1, no bias) + add + F.gelu
+// and in backward: the adjoint row synthesis + skip dgrad + GELU' of the previous layer.
+#include "common.cuh"
+
+constexpr int PW_PX = 128;   // pixels per block tile
+constexpr int PW_N = 64;     // output channels per block tile
+constexpr int PW_MC = 16;    // input-channel chunk
+
+
+__global__ void __launch_bounds__(128)
+rowidft_pointwise_kernel(const PwParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int K2 = 2 * p.Mx;
+    float* As = smem;                               // [PW_MC][PW_PX]
+    float* Ws = As + PW_MC * PW_PX;                 // [PW_MC][PW_N]
+    float* Es = Ws + PW_MC * PW_N;                  // [K2][PW_PX]
+    float* Ps = Es + (size_t)K2 * PW_PX;            // [nrows][K2][PW_N]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, tn = tid >> 4;
+    const int64_t HW = (int64_t)p.H * p.W;
+    const int tiles_per_b = (int)((HW + PW_PX - 1) / PW_PX);
+    const int b = blockIdx.x / tiles_per_b;
+    const int64_t p_base = (int64_t)(blockIdx.x % tiles_per_b) * PW_PX;
+    const int n0 = blockIdx.y * PW_N;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // ---------------- spectral part: K = 2*Mx ----------------
+    if (p.Phi != nullptr) {
+        const int row_lo = (int)(p_base / p.W);
+        int64_t p_last = p_base + PW_PX - 1;
+        if (p_last > HW - 1) p_last = HW - 1;
+        const int nrows = (int)(p_last / p.W) - row_lo + 1;
+        for (int idx = tid; idx < K2 * PW_PX; idx += 128) {
+            const int kk = idx / PW_PX, j = idx % PW_PX;
+            const int64_t pp = p_base + j;
+            float v = 0.f;
+            if (pp < HW) {
+                const float2 t = __ldg(p.RI + (int64_t)(kk >> 1) * p.W + (int)(pp % p.W));
+                v = (kk & 1) ? t.y : t.x;
+            }
+            Es[idx] = v;
+        }
+        for (int idx = tid; idx < nrows * p.Mx * PW_N; idx += 128) {
+            const int nl = idx % PW_N;
+            const int kx = (idx / PW_N) % p.Mx;
+            const int rl = idx / (PW_N * p.Mx);
+            float2 v = make_float2(0.f, 0.f);
+            if (n0 + nl < p.N)
+                v = __ldg(p.Phi + (((int64_t)b * p.N + n0 + nl) * p.H + row_lo + rl) * p.Mx + kx);
+            Ps[((size_t)rl * K2 + 2 * kx) * PW_N + nl] = v.x;
+            Ps[((size_t)rl * K2 + 2 * kx + 1) * PW_N + nl] = v.y;
+        }
+        __syncthreads();
+        int rl0 = (int)((p_base + tx * 4) / p.W) - row_lo;
+        int rl1 = (int)((p_base + 64 + tx * 4) / p.W) - row_lo;
+        if (rl0 >= nrows) rl0 = nrows - 1;      // masked pixels past HW: any valid row
+        if (rl1 >= nrows) rl1 = nrows - 1;
+        const float* P0 = Ps + (size_t)rl0 * K2 * PW_N + tn * 8;
+        const float* P1 = Ps + (size_t)rl1 * K2 * PW_N + tn * 8;
+#pragma unroll 2
+        for (int kk = 0; kk < K2; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(Es + kk * PW_PX + tx * 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(Es + kk * PW_PX + 64 + tx * 4);
+            const float4 b00 = *reinterpret_cast<const float4*>(P0 + kk * PW_N);
+            const float4 b01 = *reinterpret_cast<const float4*>(P0 + kk * PW_N + 4);
+            const float4 b10 = *reinterpret_cast<const float4*>(P1 + kk * PW_N);
+            const float4 b11 = *reinterpret_cast<const float4*>(P1 + kk * PW_N + 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b0[8] = {b00.x, b00.y, b00.z, b00.w, b01.x, b01.y, b01.z, b01.w};
+            const float b1[8] = {b10.x, b10.y, b10.z, b10.w, b11.x, b11.y, b11.z, b11.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[i][j] = fmaf(a[i], b0[j], acc[i][j]);
+                    acc[4 + i][j] = fmaf(a[4 + i], b1[j], acc[4 + i][j]);
+                }
+        }
+    }
+
+    // ---------------- pointwise part: K = M ----------------
+    if (p.Wp != nullptr) {
+        for (int m0 = 0; m0 < p.M; m0 += PW_MC) {
+            __syncthreads();
+            for (int idx = tid; idx < PW_MC * (PW_PX / 4); idx += 128) {
+                const int mm = idx / (PW_PX / 4), j4 = (idx % (PW_PX / 4)) * 4;
+                const int64_t pp = p_base + j4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + mm < p.M && pp < HW)   // HW % 4 == 0
+                    v = __ldg(reinterpret_cast<const float4*>(p.A + ((int64_t)b * p.M + m0 + mm) * HW + pp));
+                *reinterpret_cast<float4*>(As + mm * PW_PX + j4) = v;
+            }
+            for (int idx = tid; idx < PW_MC * PW_N; idx += 128) {
+                const int mm = idx / PW_N, nl = idx % PW_N;
+                float v = 0.f;
+                if (m0 + mm < p.M && n0 + nl < p.N)
+                    v = __ldg(p.Wp + (int64_t)(n0 + nl) * p.w_sn + (int64_t)(m0 + mm) * p.w_sm);
+                Ws[idx] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int mm = 0; mm < PW_MC; ++mm) {
+                const float4 a0 = *reinterpret_cast<const float4*>(As + mm * PW_PX + tx * 4);
+                const float4 a1 = *reinterpret_cast<const float4*>(As + mm * PW_PX + 64 + tx * 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(Ws + mm * PW_N + tn * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(Ws + mm * PW_N + tn * 8 + 4);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+        }
+    }
+
+    // ---------------- epilogue ----------------
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = n0 + tn * 8 + j;
+        if (n >= p.N) continue;
+        const float bv = p.bias ? __ldg(p.bias + n) : 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int64_t pp = p_base + g * 64 + tx * 4;
+            if (pp >= HW) continue;
+            const int64_t off = ((int64_t)b * p.N + n) * HW + pp;
+            float4 v = make_float4(acc[g * 4 + 0][j] + bv, acc[g * 4 + 1][j] + bv, acc[g * 4 + 2][j] + bv,
+                                   acc[g * 4 + 3][j] + bv);
+            if (p.mode == 0) {
+                if (p.z_out) *reinterpret_cast<float4*>(p.z_out + off) = v;
+                if (p.apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+                *reinterpret_cast<float4*>(p.y_out + off) = v;
+            } else {
+                if (p.zprev) {
+                    const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + off));
+                    v.x *= gelu_grad_f(z.x); v.y *= gelu_grad_f(z.y); v.z *= gelu_grad_f(z.z); v.w *= gelu_grad_f(z.w);
+                }
+                *reinterpret_cast<float4*>(p.y_out + off) = v;
+            }
+        }
+    }
+}
+
+int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& p, cudaStream_t st, int* handled);
+
+extern "C" int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float* Phi, const float* A, const float* Wp,
+                                       int64_t w_sn, int64_t w_sm, const float* bias, const float* zprev,
+                                       float* z_out, float* y_out, int B, int M, int N, int mode, int apply_act,
+                                       void* stream) {
+    SB_REQUIRE(plan && y_out, "rowidft_pointwise: NULL plan/output");
+    SB_REQUIRE(pass == 0 || pass == 1, "rowidft_pointwise: pass must be 0 or 1");
+    SB_REQUIRE(mode == 0 || mode == 1, "rowidft_pointwise: mode must be 0 or 1");
+    SB_REQUIRE((Wp == nullptr) == (A == nullptr), "rowidft_pointwise: A and Wp must both be given or both NULL");
+    SB_REQUIRE(Phi || Wp, "rowidft_pointwise: nothing to compute");
+    SB_REQUIRE(plan->W % 4 == 0, "rowidft_pointwise: W=%d must be a multiple of 4", plan->W);
+    if (B <= 0 || N <= 0) return 0;
+    PwParams p;
+    p.Phi = reinterpret_cast<const float2*>(Phi);
+    p.RI = plan->rowI[pass];
+    p.A = A; p.Wp = Wp; p.w_sn = w_sn; p.w_sm = w_sm; p.bias = bias; p.zprev = zprev;
+    p.z_out = z_out; p.y_out = y_out;
+    p.B = B; p.M = M; p.N = N; p.H = plan->H; p.W = plan->W; p.Mx = plan->Mx;
+    p.mode = mode; p.apply_act = apply_act;
+    p.nrows_max = (PW_PX + plan->W - 1) / plan->W + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int handled = 0;
+    if (int rc = sb200_tc_rowidft_pointwise(plan, pass, p, st, &handled)) return rc;
+    if (handled) return 0;
+    const int K2 = 2 * p.Mx;
+    const size_t smem = sizeof(float) * ((size_t)PW_MC * PW_PX + PW_MC * PW_N + (size_t)K2 * PW_PX +
+                                         (size_t)p.nrows_max * K2 * PW_N);
+    SB_REQUIRE(smem <= 200 * 1024, "rowidft_pointwise: shared memory %zu too large (W=%d Mx=%d)", smem, p.W, p.Mx);
+    if (smem > 48 * 1024)
+        SB_CHECK_CUDA(cudaFuncSetAttribute(rowidft_pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t HW = (int64_t)p.H * p.W;
+    const int64_t tiles = (HW + PW_PX - 1) / PW_PX * B;
+    SB_REQUIRE(tiles < (1LL << 31), "rowidft_pointwise: too many tiles");
+    dim3 grid((unsigned)tiles, (unsigned)((N + PW_N - 1) / PW_N));
+    rowidft_pointwise_kernel<<<grid, 128, smem, st>>>(p);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ======================================================================================
+// pointwise weight gradient:  gW[o,i] = sum_{b,p} g[b,o,p] x[b,i,p];  gbias[o] = sum g
+// ======================================================================================
+constexpr int WG_PC = 32;       // pixels per smem step
+constexpr int WG_LD = 68;       // padded leading dim of the transposed tiles
+
+__global__ void __launch_bounds__(256)
+pointwise_wgrad_partial_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ ws,
+                               float* __restrict__ wsb, int B, int Cout, int Cin, int64_t HW, int64_t chunk_px,
+                               int chunks_per_b, int i_tiles) {
+    __shared__ __align__(16) float Gs[WG_PC][WG_LD];
+    __shared__ __align__(16) float Xs[WG_PC][WG_LD];
+    __shared__ float red[64][65];
+    const int tid = threadIdx.x;
+    const int sub = tid >> 6, t64 = tid & 63;
+    const int to = t64 >> 3, ti = t64 & 7;
+    const int chunk = blockIdx.x;
+    const int b = chunk / chunks_per_b;
+    const int64_t pc0 = (int64_t)(chunk % chunks_per_b) * chunk_px;
+    int64_t pc1 = pc0 + chunk_px;
+    if (pc1 > HW) pc1 = HW;
+    const int o0 = (blockIdx.y / i_tiles) * 64, i0 = (blockIdx.y % i_tiles) * 64;
+
+    float acc[8][8];
+    float accb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        accb[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+
+    for (int64_t p0 = pc0; p0 < pc1; p0 += WG_PC) {
+        __syncthreads();
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int c = (tid >> 3) + 32 * rep;      // channel within tile
+            const int p4 = (tid & 7) * 4;
+            const int64_t pp = p0 + p4;
+            float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vx = vg;
+            if (pp < pc1) {                             // HW % 4 == 0 and chunk_px % 4 == 0
+                if (o0 + c < Cout) vg = __ldg(reinterpret_cast<const float4*>(g + ((int64_t)b * Cout + o0 + c) * HW + pp));
+                if (i0 + c < Cin) vx = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)b * Cin + i0 + c) * HW + pp));
+            }
+            Gs[p4 + 0][c] = vg.x; Gs[p4 + 1][c] = vg.y; Gs[p4 + 2][c] = vg.z; Gs[p4 + 3][c] = vg.w;
+            Xs[p4 + 0][c] = vx.x; Xs[p4 + 1][c] = vx.y; Xs[p4 + 2][c] = vx.z; Xs[p4 + 3][c] = vx.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < WG_PC / 4; ++s) {
+            const int pp = sub + 4 * s;
+            const float4 a0 = *reinterpret_cast<const float4*>(&Gs[pp][to * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Gs[pp][to * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Xs[pp][ti * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Xs[pp][ti * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                accb[i] += a[i];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+        }
+    }
+    // reduce the 4 pixel-subsets through shared memory (deterministic order 0+1+2+3)
+    for (int s = 1; s < 4; ++s) {
+        __syncthreads();
+        if (sub == s) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[i * 8 + j][t64] = acc[i][j];
+        }
+        __syncthreads();
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] += red[i * 8 + j][t64];
+        }
+        __syncthreads();
+        if (sub == s) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[i][t64] = accb[i];
+        }
+        __syncthreads();
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) accb[i] += red[i][t64];
+        }
+    }
+    if (sub == 0) {
+        float* wsc = ws + (int64_t)chunk * Cout * Cin;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = o0 + to * 8 + i;
+            if (o >= Cout) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ic = i0 + ti * 8 + j;
+                if (ic < Cin) wsc[(int64_t)o * Cin + ic] = acc[i][j];
+            }
+            if (ti == 0 && i0 == 0) wsb[(int64_t)chunk * Cout + o] = accb[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t E, int nchunks) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= E) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < nchunks; ++c) s += __ldg(ws + (int64_t)c * E + e);
+    out[e] = s;
+}
+
+static void wgrad_chunking(int B, int64_t HW, int64_t* chunk_px, int* chunks_per_b) {
+    // aim for ~2 waves of 148 SMs; chunk is a multiple of WG_PC pixels inside one sample
+    int64_t target = 296;
+    int64_t cpb = (target + B - 1) / B;
+    if (cpb < 1) cpb = 1;
+    int64_t px = (HW + cpb - 1) / cpb;
+    px = (px + WG_PC - 1) / WG_PC * WG_PC;
+    if (px < WG_PC) px = WG_PC;
+    *chunk_px = px;
+    *chunks_per_b = (int)((HW + px - 1) / px);
+}
+
+extern "C" int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
+    int64_t px; int cpb;
+    wgrad_chunking(B, HW, &px, &cpb);
+    return (int64_t)B * cpb * ((int64_t)Cout * Cin + Cout);
+}
+
+extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
+                                     int64_t HW, float* workspace, void* stream) {
+    SB_REQUIRE(g && x && gW && workspace, "pointwise_wgrad: NULL argument");
+    SB_REQUIRE(HW % 4 == 0, "pointwise_wgrad: H*W=%lld must be a multiple of 4", (long long)HW);
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t px; int cpb;
+    wgrad_chunking(B, HW, &px, &cpb);
+    const int nchunks = B * cpb;
+    float* ws = workspace;
+    float* wsb = workspace + (int64_t)nchunks * Cout * Cin;
+    const int o_tiles = (Cout + 63) / 64, i_tiles = (Cin + 63) / 64;
+    dim3 grid(nchunks, o_tiles * i_tiles);
+    pointwise_wgrad_partial_kernel<<<grid, 256, 0, st>>>(g, x, ws, wsb, B, Cout, Cin, HW, px, cpb, i_tiles);
+    SB_LAUNCH_CHECK();
+    const int64_t E = (int64_t)Cout * Cin;
+    wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(ws, gW, E, nchunks);
+    SB_LAUNCH_CHECK();
+    if (gbias) {
+        wgrad_reduce_kernel<<<(unsigned)ceil_div64(Cout, 256), 256, 0, st>>>(wsb, gbias, Cout, nchunks);
+        SB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ======================================================================================
+// element-wise GELU helpers
+// ======================================================================================
+__global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
+        v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+        *reinterpret_cast<float4*>(y + i) = v;
+    } else {
+        for (int64_t k = i; k < n; ++k) y[k] = gelu_f(z[k]);
+    }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z, float* __restrict__ gz,
+                                int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
+        float4 g = __ldg(reinterpret_cast<const float4*>(gy + i));
+        g.x *= gelu_grad_f(v.x); g.y *= gelu_grad_f(v.y); g.z *= gelu_grad_f(v.z); g.w *= gelu_grad_f(v.w);
+        *reinterpret_cast<float4*>(gz + i) = g;
+    } else {
+        for (int64_t k = i; k < n; ++k) gz[k] = gy[k] * gelu_grad_f(z[k]);
+    }
+}
+extern "C" int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream) {
+    SB_REQUIRE(z && y, "gelu_fwd: NULL argument");
+    if (n <= 0) return 0;
+    SB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+               "gelu_fwd: pointers must be 16-byte aligned");
+    gelu_fwd_kernel<<<(unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream>>>(z, y, n);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream) {
+    SB_REQUIRE(gy && z && gz, "gelu_bwd: NULL argument");
+    if (n <= 0) return 0;
+    gelu_bwd_kernel<<<(unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream>>>(gy, z, gz, n);
+    SB_LAUNCH_CHECK();
+    return 0;
+}

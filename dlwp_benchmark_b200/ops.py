@@ -1,0 +1,141 @@
+"""Tensor-level wrappers over the C ABI (one python function per exported stage).
+
+Every function requires CUDA fp32 contiguous tensors and launches on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .plan import Plan
+
+_vp = ctypes.c_void_p
+
+
+def _p(t: Optional[torch.Tensor]):
+    return _vp(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.SpectralB200Error(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise _lib.SpectralB200Error(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.SpectralB200Error(f"{name}: expected a contiguous tensor")
+
+
+def rowdft_fwd(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
+    """x [..., W] -> T [..., Mx, 2]"""
+    _req(x, "x")
+    assert x.shape[-1] == plan.W
+    rows = x.numel() // plan.W
+    T = torch.empty(*x.shape[:-1], plan.Mx, 2, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_rowdft_fwd(plan.handle, pas, _p(x), _p(T), rows, _stream()), "rowdft_fwd")
+    return T
+
+
+def coldft_fwd(plan: Plan, pas: int, T: torch.Tensor) -> torch.Tensor:
+    """T [..., H, Mx, 2] -> Xh [..., My, Mx, 2]"""
+    _req(T, "T")
+    assert T.shape[-3:] == (plan.H, plan.Mx, 2)
+    nimg = T.numel() // (plan.H * plan.Mx * 2)
+    Xh = torch.empty(*T.shape[:-3], plan.My, plan.Mx, 2, device=T.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_coldft_fwd(plan.handle, pas, _p(T), _p(Xh), nimg, _stream()), "coldft_fwd")
+    return Xh
+
+
+def coldft_inv(plan: Plan, pas: int, Yh: torch.Tensor) -> torch.Tensor:
+    """Yh [..., My, Mx, 2] -> Phi [..., H, Mx, 2]"""
+    _req(Yh, "Yh")
+    assert Yh.shape[-3:] == (plan.My, plan.Mx, 2)
+    nimg = Yh.numel() // (plan.My * plan.Mx * 2)
+    Phi = torch.empty(*Yh.shape[:-3], plan.H, plan.Mx, 2, device=Yh.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_coldft_inv(plan.handle, pas, _p(Yh), _p(Phi), nimg, _stream()), "coldft_inv")
+    return Phi
+
+
+def modes_gemm(A, sAr, sAp, B, sBr, sBq, out, sOp, sOq, P, Q, R, K, conj_flags=0):
+    _req(A, "A"); _req(B, "B"); _req(out, "out")
+    _lib.check(_lib.load().sb200_modes_gemm(_p(A), sAr, sAp, _p(B), sBr, sBq, _p(out), sOp, sOq,
+                                            P, Q, R, K, conj_flags, _stream()), "modes_gemm")
+    return out
+
+
+def mix_fwd(Xh: torch.Tensor, Wc: torch.Tensor) -> torch.Tensor:
+    """Yh[b,o,k] = sum_i Xh[b,i,k] W[i,o,k];  Xh [B,Cin,My,Mx,2], Wc [Cin,Cout,My,Mx,2]."""
+    B, Cin = Xh.shape[:2]
+    Cout = Wc.shape[1]
+    M = Xh.shape[2] * Xh.shape[3]
+    out = torch.empty(B, Cout, *Xh.shape[2:], device=Xh.device, dtype=torch.float32)
+    return modes_gemm(Xh, M, Cin * M, Wc, Cout * M, M, out, Cout * M, M, B, Cout, Cin, M, 0)
+
+
+def mix_bwd_input(gYh: torch.Tensor, Wc: torch.Tensor) -> torch.Tensor:
+    """gXh[b,i,k] = sum_o conj(W[i,o,k]) gYh[b,o,k]"""
+    B, Cout = gYh.shape[:2]
+    Cin = Wc.shape[0]
+    M = gYh.shape[2] * gYh.shape[3]
+    out = torch.empty(B, Cin, *gYh.shape[2:], device=gYh.device, dtype=torch.float32)
+    return modes_gemm(gYh, M, Cout * M, Wc, M, Cout * M, out, Cin * M, M, B, Cin, Cout, M, 2)
+
+
+def mix_bwd_weight(Xh: torch.Tensor, gYh: torch.Tensor) -> torch.Tensor:
+    """gW[i,o,k] = sum_b conj(Xh[b,i,k]) gYh[b,o,k]"""
+    B, Cin = Xh.shape[:2]
+    Cout = gYh.shape[1]
+    M = Xh.shape[2] * Xh.shape[3]
+    out = torch.empty(Cin, Cout, *Xh.shape[2:], device=Xh.device, dtype=torch.float32)
+    return modes_gemm(Xh, Cin * M, M, gYh, Cout * M, M, out, Cout * M, M, Cin, Cout, B, M, 1)
+
+
+def rowidft_pointwise(plan: Plan, pas: int, Phi, A, Wp, w_sn, w_sm, bias, zprev, B, M, N, mode, apply_act,
+                      want_z: bool = False):
+    """Fused row synthesis + pointwise mix + epilogue; returns (y, z or None)."""
+    dev = (Phi if Phi is not None else A).device
+    for t, n in ((Phi, "Phi"), (A, "A"), (Wp, "Wp"), (bias, "bias"), (zprev, "zprev")):
+        if t is not None:
+            _req(t, n)
+    y = torch.empty(B, N, plan.H, plan.W, device=dev, dtype=torch.float32)
+    z = torch.empty_like(y) if want_z else None
+    _lib.check(_lib.load().sb200_rowidft_pointwise(plan.handle, pas, _p(Phi), _p(A), _p(Wp), w_sn, w_sm, _p(bias),
+                                                   _p(zprev), _p(z), _p(y), B, M, N, mode, int(apply_act), _stream()),
+               "rowidft_pointwise")
+    return y, z
+
+
+def pointwise_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+    """gW[o,i] = sum g[b,o,p] x[b,i,p]; gbias[o] = sum g[b,o,p].  g [B,Cout,H,W], x [B,Cin,H,W]."""
+    _req(g, "g"); _req(x, "x")
+    B, Cout = g.shape[:2]
+    Cin = x.shape[1]
+    HW = g.shape[2] * g.shape[3]
+    lib = _lib.load()
+    n = lib.sb200_pointwise_wgrad_workspace(B, Cout, Cin, HW)
+    ws = torch.empty(n, device=g.device, dtype=torch.float32)
+    gW = torch.empty(Cout, Cin, device=g.device, dtype=torch.float32)
+    gb = torch.empty(Cout, device=g.device, dtype=torch.float32) if want_bias else None
+    _lib.check(lib.sb200_pointwise_wgrad(_p(g), _p(x), _p(gW), _p(gb), B, Cout, Cin, HW, _p(ws), _stream()),
+               "pointwise_wgrad")
+    return gW, gb
+
+
+def gelu_fwd(z: torch.Tensor) -> torch.Tensor:
+    _req(z, "z")
+    y = torch.empty_like(z)
+    _lib.check(_lib.load().sb200_gelu_fwd(_p(z), _p(y), z.numel(), _stream()), "gelu_fwd")
+    return y
+
+
+def gelu_bwd(gy: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    _req(gy, "gy"); _req(z, "z")
+    gz = torch.empty_like(z)
+    _lib.check(_lib.load().sb200_gelu_bwd(_p(gy), _p(z), _p(gz), z.numel(), _stream()), "gelu_bwd")
+    return gz

@@ -1,0 +1,109 @@
+/*
+ * spectral_b200 -- C ABI of the B200 (sm_100a) spectral-convolution kernel library.
+ *
+ * This is the drop-in boundary for the FNO-family hot path of amazon-science/dlwp-benchmark.
+ * The reference has no FFI of its own (it is pure PyTorch); what it calls on this path are
+ * library primitives.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference root; "neuralop" = neuraloperator @05c01c3 pinned by
+ * README.md:34-35, reached from src/nsbench/models/fno/fno.py:19-27 and
+ * src/dlwpbench/models/fno/fno.py:38-47,136-146).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch: tensor.data_ptr()),
+ *    contiguous, fp32; complex data is interleaved (re,im) exactly like torch.complex64 /
+ *    torch.view_as_real
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *    the library never synchronises, never allocates activation memory and never switches
+ *    device; scratch is passed in by the caller
+ *  - every function returns 0 on success, non-zero on failure; sb200_last_error() returns a
+ *    thread-local message.  There is NO CPU fallback: without a CUDA device every compute
+ *    entry point fails.
+ *  - plans hold only immutable twiddle tables (device memory) for one (H, W, ky0, My, Mx,
+ *    scales) combination and may be shared by concurrent callers.
+ */
+#ifndef SPECTRAL_B200_H
+#define SPECTRAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb200_plan_s* sb200_plan_t;
+
+/* library / build identification: returns 10000*major + 100*minor + patch */
+int sb200_version(void);
+/* thread-local description of the last failure (never NULL) */
+const char* sb200_last_error(void);
+/* compute capability major*10+minor of the current device, or <0 when no device */
+int sb200_device_arch(void);
+
+/* ---- plans ---------------------------------------------------------------------------
+ * Retained block: rows ky = (ky0 + j) mod H, j in [0,My); cols kx in [0,Mx).
+ * FNO (neuralop SpectralConv.forward, fftshift-era slicing): ky0 = lo - H/2, norm "forward"
+ *   => scale_fwd = 1/(H*W), scale_inv = 1.
+ * AFNO2D (src/nsbench/models/fourcastnet/fourcastnet.py:84,92-95,123): ky0 = r0,
+ *   norm "ortho" => scale_fwd = scale_inv = 1/sqrt(h*w).
+ * Tables are built in double precision on the host and uploaded to the current device. */
+int sb200_plan_create(sb200_plan_t* plan, int H, int W, int ky0, int My, int Mx,
+                      double scale_fwd, double scale_inv);
+int sb200_plan_destroy(sb200_plan_t plan);
+
+/* `pass` selects the table set: 0 = the transforms of the forward pass (analysis un-weighted
+ * * scale_fwd, synthesis with Hermitian weights 1/2/1 * scale_inv); 1 = their adjoints used
+ * by the backward pass (analysis of the output gradient WITH Hermitian weights * scale_inv,
+ * synthesis with weights 1 * scale_fwd). */
+
+/* ---- channels-first (FNO) stages -------------------------------------------------------
+ * replaces torch.fft.rfftn + fftshift + slice (neuralop SpectralConv.forward) */
+/* x [rows, W] real  ->  T [rows, Mx] complex   (rows = B*C*H) */
+int sb200_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, void* stream);
+/* T [nimg, H, Mx] complex -> Xh [nimg, My, Mx] complex */
+int sb200_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, int64_t nimg, void* stream);
+/* Yh [nimg, My, Mx] complex -> Phi [nimg, H, Mx] complex
+ * replaces zeros + scatter + fftshift + the H-axis half of torch.fft.irfftn */
+int sb200_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, int64_t nimg, void* stream);
+
+/* Batched-over-modes complex contraction
+ *      out[p,q,k] = sum_r opA(A[r,p,k]) * opB(B[r,q,k]),   k contiguous,
+ * with element strides (in complex elements) for r/p/q.  conj flags: bit0 = conj A, bit1 = conj B.
+ * replaces torch.einsum("bixy,ioxy->boxy") (neuralop _contract_dense) and its two autograd
+ * products (grad wrt input spectrum, grad wrt weight). */
+int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp,
+                     const float* B, int64_t sBr, int64_t sBq,
+                     float* out, int64_t sOp, int64_t sOq,
+                     int P, int Q, int R, int K, int conj_flags, void* stream);
+
+/* Fused row synthesis + pointwise (1x1) channel mix + epilogue.
+ *   acc[b,n,y,x] = sum_kx ( Phi[b,n,y,kx].re * RI[kx][x].x + Phi.im * RI[kx][x].y )
+ *                + sum_m  Wp[n,m] * A[b,m,y,x]            (skipped when Wp == NULL)
+ *                + bias[n]                                  (skipped when bias == NULL)
+ *   mode 0 (forward):  z_out = acc (if non-NULL);  y_out = gelu(acc) if apply_act else acc
+ *   mode 1 (backward): y_out = acc * gelu'(zprev) if zprev != NULL else acc
+ * Wp element (n,m) is read at Wp[n*w_sn + m*w_sm] (so the transpose is a stride swap).
+ * replaces the W-axis half of irfftn + bias add + fno_skips Conv2d(1x1) + add + F.gelu
+ * (neuralop SpectralConv.forward / FNOBlocks.forward_with_postactivation) and, in mode 1,
+ * the corresponding autograd nodes. */
+int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float* Phi,
+                            const float* A, const float* Wp, int64_t w_sn, int64_t w_sm,
+                            const float* bias, const float* zprev,
+                            float* z_out, float* y_out,
+                            int B, int M, int N, int mode, int apply_act, void* stream);
+
+/* Weight / bias gradient of the pointwise (1x1) channel mix:
+ *   gW[o,i] = sum_{b,p} g[b,o,p] * x[b,i,p]      gbias[o] = sum_{b,p} g[b,o,p]   (gbias may be NULL)
+ * `workspace` must hold sb200_pointwise_wgrad_workspace(...) floats.  Deterministic (two-phase).
+ * replaces the Conv2d weight-grad and bias-sum autograd nodes. */
+int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);
+int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias,
+                          int B, int Cout, int Cin, int64_t HW, float* workspace, void* stream);
+
+/* Element-wise helpers used between layers: y = gelu(z);  gz = gy * gelu'(z) */
+int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream);
+int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRAL_B200_H */

@@ -1,0 +1,269 @@
+"""GPU parity tests of the FNO / TFNO path: CUDA kernels (through the C ABI) vs the oracle.
+
+Tolerance (north_star): relative L2 <= 1e-5 for outputs and every gradient in the fp32 path.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dlwp_benchmark_b200 as pkg
+from dlwp_benchmark_b200 import ops
+from dlwp_benchmark_b200.plan import fno_plan
+from dlwp_benchmark_b200.spectral_conv import FNOBlockFn
+from oracle import spectral_oracle as so
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _rand(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*s, generator=g) * scale
+
+
+STAGE_SHAPES = [
+    # B, C, H, W, n_modes
+    (2, 3, 16, 16, (6, 6)),
+    (1, 5, 16, 32, (8, 12)),
+    (2, 4, 8, 8, (8, 8)),        # all modes incl. Nyquist column
+    (3, 7, 64, 64, (12, 12)),    # cfg1 grid
+    (2, 8, 32, 64, (12, 12)),    # dlwpbench grid
+    (1, 2, 64, 128, (32, 32)),
+    (1, 2, 12, 20, (6, 7)),      # W % 8 != 0, odd mode counts
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,nm", STAGE_SHAPES)
+def test_analysis_stages(B, C, H, W, nm):
+    half = so.halve_last_mode(nm)
+    plan = fno_plan(DEV, H, W, half)
+    x = _rand(B, C, H, W)
+    xd = x.double()
+    full = torch.fft.fftshift(torch.fft.rfftn(xd, norm="forward", dim=(-2, -1)), dim=(-2,))
+    lo, My = so.retained_rows(H, half[0])
+    ref = full[:, :, lo:lo + My, :plan.Mx]
+    T = ops.rowdft_fwd(plan, 0, x.to(DEV))
+    refT = torch.fft.rfft(xd, dim=-1)[..., :plan.Mx]
+    assert rel_l2(torch.view_as_complex(T), refT) < TOL
+    Xh = ops.coldft_fwd(plan, 0, T)
+    assert rel_l2(torch.view_as_complex(Xh), ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,nm", STAGE_SHAPES)
+def test_synthesis_stages(B, C, H, W, nm):
+    half = so.halve_last_mode(nm)
+    plan = fno_plan(DEV, H, W, half)
+    lo, My = so.retained_rows(H, half[0])
+    Yh = torch.view_as_complex(_rand(B, C, My, plan.Mx, 2, seed=3).double())
+    full = torch.zeros(B, C, H, W // 2 + 1, dtype=torch.complex128)
+    full[:, :, lo:lo + My, :plan.Mx] = Yh
+    ref = torch.fft.irfftn(torch.fft.fftshift(full, dim=(-2,)), s=(H, W), dim=(-2, -1), norm="forward")
+    Phi = ops.coldft_inv(plan, 0, torch.view_as_real(Yh).float().contiguous().to(DEV))
+    y, _ = ops.rowidft_pointwise(plan, 0, Phi, None, None, 0, 0, None, None, B, C, C, 0, False)
+    assert rel_l2(y, ref) < TOL
+
+
+@pytest.mark.parametrize("P,Q,R,K", [(5, 7, 3, 10), (64, 64, 64, 144), (32, 32, 32, 84), (8, 33, 65, 7)])
+def test_modes_gemm_all_three_uses(P, Q, R, K):
+    A = torch.view_as_complex(_rand(P, R, K, 2, seed=1).double())     # Xh [b,i,k]
+    Wc = torch.view_as_complex(_rand(R, Q, K, 2, seed=2).double())    # W  [i,o,k]
+    G = torch.view_as_complex(_rand(P, Q, K, 2, seed=3).double())     # gYh [b,o,k]
+    f = lambda t: torch.view_as_real(t).float().contiguous().to(DEV).reshape(*t.shape[:2], K, 1, 2)
+    Yh = ops.mix_fwd(f(A), f(Wc))
+    assert rel_l2(torch.view_as_complex(Yh).squeeze(-1), torch.einsum("bik,iok->bok", A, Wc)) < TOL
+    gX = ops.mix_bwd_input(f(G), f(Wc))
+    assert rel_l2(torch.view_as_complex(gX).squeeze(-1), torch.einsum("iok,bok->bik", Wc.conj(), G)) < TOL
+    gW = ops.mix_bwd_weight(f(A), f(G))
+    assert rel_l2(torch.view_as_complex(gW).squeeze(-1), torch.einsum("bik,bok->iok", A.conj(), G)) < TOL
+
+
+@pytest.mark.parametrize("B,Co,Ci,H,W", [(2, 5, 3, 8, 8), (3, 64, 64, 16, 16), (2, 70, 33, 16, 32), (1, 8, 8, 64, 64)])
+def test_pointwise_wgrad(B, Co, Ci, H, W):
+    g = _rand(B, Co, H, W, seed=5)
+    x = _rand(B, Ci, H, W, seed=6)
+    gW, gb = ops.pointwise_wgrad(g.to(DEV), x.to(DEV))
+    assert rel_l2(gW, torch.einsum("bop,bip->oi", g.double().flatten(2), x.double().flatten(2))) < TOL
+    assert rel_l2(gb, g.double().sum(dim=(0, 2, 3))) < TOL
+
+
+def test_gelu_helpers():
+    z = _rand(1000, seed=9, scale=2.0)
+    zd = z.double().requires_grad_(True)
+    yd = torch.nn.functional.gelu(zd)
+    yd.backward(torch.ones_like(yd))
+    assert rel_l2(ops.gelu_fwd(z.to(DEV)), yd) < 1e-6
+    assert rel_l2(ops.gelu_bwd(torch.ones(1000, device=DEV), z.to(DEV)), zd.grad) < 1e-6
+
+
+BLOCK_SHAPES = [
+    # B, Cin, Cout, H, W, n_modes, act, skip
+    (2, 3, 3, 16, 16, (6, 6), True, True),
+    (2, 4, 6, 16, 32, (8, 12), False, False),    # pure SpectralConv, Cin != Cout
+    (1, 8, 8, 64, 64, (12, 12), True, True),
+    (2, 5, 5, 8, 8, (8, 8), True, True),
+    (1, 70, 70, 16, 16, (6, 6), True, True),     # more than one channel tile
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,H,W,nm,act,skip", BLOCK_SHAPES)
+def test_block_forward_backward(B, Ci, Co, H, W, nm, act, skip):
+    half = so.halve_last_mode(nm)
+    lo, My = so.retained_rows(H, half[0])
+    Mx = min(half[1], W // 2 + 1)
+    x = _rand(B, Ci, H, W, seed=1)
+    w = _rand(Ci, Co, My, Mx, 2, seed=2, scale=0.5)
+    ws = _rand(Co, Ci, 1, 1, seed=3, scale=0.4) if skip else None
+    b = _rand(Co, 1, 1, seed=4, scale=0.3)
+    gy = _rand(B, Co, H, W, seed=5)
+    # oracle, fp64
+    xo, wo, bo = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    wso = ws.double().requires_grad_(True) if skip else None
+    yo = so.spectral_conv_dense(xo, torch.view_as_complex(wo), bo, [My, Mx])
+    if skip:
+        yo = yo + torch.nn.functional.conv2d(xo, wso)
+    if act:
+        yo = torch.nn.functional.gelu(yo)
+    yo.backward(gy.double())
+    # CUDA
+    xc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    wsc = ws.to(DEV).requires_grad_(True) if skip else None
+    yc = FNOBlockFn.apply(xc, wc, wsc, bc, tuple(half), act)
+    yc.backward(gy.to(DEV))
+    assert rel_l2(yc, yo) < TOL
+    assert rel_l2(xc.grad, xo.grad) < TOL
+    assert rel_l2(wc.grad, wo.grad) < TOL
+    assert rel_l2(bc.grad, bo.grad) < TOL
+    if skip:
+        assert rel_l2(wsc.grad, wso.grad) < TOL
+
+
+def _load_fixture(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, cin, hid, cout, H, W, n0, n1, L, lp = [int(v) for v in d["meta"]]
+    rank = float(d["rank"])
+    cls = pkg.TFNO if rank > 0 else pkg.FNO
+    m = cls(n_modes=(n0, n1), hidden_channels=hid, in_channels=cin, out_channels=cout, lifting_channels=lp,
+            projection_channels=lp, n_layers=L, rank=rank if rank > 0 else 1.0)
+    sd = {k[2:]: torch.tensor(d[k]).float() for k in d.files if k.startswith("p:")}
+    missing = m.load_state_dict(sd, strict=True)
+    return d, m.to(DEV), (n0, n1), L
+
+
+@pytest.mark.parametrize("name", ["fno_cfg1_small", "fno_rect", "fno_fullmodes", "tfno_small"])
+def test_model_against_golden_fixture(golden_dir, name):
+    """Whole FNO / TFNO fwd+bwd on the committed vectors (state_dict loads with strict=True)."""
+    d, m, nm, L = _load_fixture(golden_dir, name)
+    x = torch.tensor(d["x"]).float().to(DEV).requires_grad_(True)
+    y = m(x)
+    y.backward(torch.tensor(d["gy"]).float().to(DEV))
+    assert rel_l2(y, torch.tensor(d["y"])) < TOL
+    assert rel_l2(x.grad, torch.tensor(d["gx"])) < TOL
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad, torch.tensor(d["g:" + k])) < 2e-5, k
+
+
+def test_per_block_api_equals_fused_stack(golden_dir):
+    d, m, nm, L = _load_fixture(golden_dir, "fno_cfg1_small")
+    x = torch.tensor(d["x"]).float().to(DEV)
+    with torch.no_grad():
+        h = m.lifting(x)
+        a = m.fno_blocks.forward_all(h)
+        b = h
+        for l in range(L):
+            b = m.fno_blocks(b, l)
+    assert rel_l2(a, b) < 1e-6
+
+
+def test_cfg1_full_size_vs_oracle():
+    """BASELINE configs[0]: FNO2D 64x64, in 1, width 32, 12 modes, 4 layers, batch 8, fwd+bwd."""
+    torch.manual_seed(1234)
+    m = pkg.FNO(n_modes=(12, 12), hidden_channels=32, in_channels=1, out_channels=1, lifting_channels=256,
+                projection_channels=256, n_layers=4)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = _rand(8, 1, 64, 64, seed=7)
+    tgt = _rand(8, 1, 64, 64, seed=8)
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    yo = so.fno_forward(leaves, x.double(), (12, 12), 4)
+    lo = torch.nn.functional.mse_loss(yo, tgt.double())
+    lo.backward()
+    m = m.to(DEV)
+    yc = m(x.to(DEV))
+    lc = torch.nn.functional.mse_loss(yc, tgt.to(DEV))
+    lc.backward()
+    assert rel_l2(yc, yo) < TOL
+    assert abs(lc.item() - lo.item()) / abs(lo.item()) < TOL
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad, leaves[k].grad) < 2e-5, k
+
+
+def test_rollout_20_steps_vs_oracle():
+    """north_star: parity checked over a 20-step closed-loop rollout."""
+    torch.manual_seed(5)
+    m = pkg.FNO(n_modes=(12, 12), hidden_channels=16, in_channels=1, out_channels=1, lifting_channels=32,
+                projection_channels=32, n_layers=4)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    x0 = _rand(2, 1, 32, 32, seed=11)
+    ref = so.rollout(sd, x0.double(), (12, 12), 4, 20)
+    m = m.to(DEV)
+    outs, x = [], x0.to(DEV)
+    with torch.no_grad():
+        for _ in range(20):
+            x = m(x)
+            outs.append(x)
+    got = torch.stack(outs, dim=1)
+    assert rel_l2(got, ref) < TOL
+    assert rel_l2(got[:, -1], ref[:, -1]) < 5e-5
+
+
+def test_cfg2_shapes_vs_oracle_on_gpu():
+    """BASELINE configs[1] shapes (64x64, width 64, 16 modes, batch 64): one block fwd+bwd
+    against the oracle evaluated with torch.fft on the same GPU (checker only)."""
+    B, C, H, W, nm = 64, 64, 64, 64, (16, 16)
+    half = so.halve_last_mode(nm)
+    x = _rand(B, C, H, W, seed=1).to(DEV)
+    w = _rand(C, C, 16, 9, 2, seed=2, scale=0.2).to(DEV)
+    ws = _rand(C, C, 1, 1, seed=3, scale=0.1).to(DEV)
+    b = _rand(C, 1, 1, seed=4, scale=0.3).to(DEV)
+    gy = _rand(B, C, H, W, seed=5).to(DEV)
+    xo, wo, wso, bo = (t.clone().requires_grad_(True) for t in (x, w, ws, b))
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        yo = torch.nn.functional.gelu(so.spectral_conv_dense(xo, torch.view_as_complex(wo), bo, half)
+                                      + torch.nn.functional.conv2d(xo, wso))
+        yo.backward(gy)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    xc, wc, wsc, bc = (t.clone().requires_grad_(True) for t in (x, w, ws, b))
+    yc = FNOBlockFn.apply(xc, wc, wsc, bc, tuple(half), True)
+    yc.backward(gy)
+    assert rel_l2(yc, yo) < TOL
+    assert rel_l2(xc.grad, xo.grad) < TOL
+    assert rel_l2(wc.grad, wo.grad) < 2e-5
+    assert rel_l2(wsc.grad, wso.grad) < 2e-5
+    assert rel_l2(bc.grad, bo.grad) < 2e-5
+
+
+def test_linearity_at_cfg3_tile():
+    """Size-independent property at 256x256 / 32 modes: SpectralConv is linear in x."""
+    half = so.halve_last_mode((32, 32))
+    m = pkg.SpectralConv(8, 8, (32, 32), fft_norm="forward", bias=False).to(DEV)
+    a, b = _rand(2, 8, 256, 256, seed=1).to(DEV), _rand(2, 8, 256, 256, seed=2).to(DEV)
+    with torch.no_grad():
+        lhs = m(2.0 * a - 3.0 * b)
+        rhs = 2.0 * m(a) - 3.0 * m(b)
+        ref = so.spectral_conv_dense(a, m.weight[0].to_dense_complex(), None, half)
+        got = m(a)
+    assert rel_l2(lhs, rhs) < 1e-5
+    assert rel_l2(got, ref) < TOL
+
+
+def test_odd_height_is_rejected_loudly():
+    m = pkg.SpectralConv(2, 2, (4, 4), fft_norm="forward").to(DEV)
+    with pytest.raises(pkg._lib.SpectralB200Error):
+        m(torch.randn(1, 2, 15, 16, device=DEV))
