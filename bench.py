@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Headline benchmark: FNO-family train step (fwd + MSE + bwd + Adam) samples/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg3]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+
+Workload at N=1 (BASELINE.json configs[1], the config the metric's target is quoted on):
+TFNO2D (Tucker rank 0.8) on 64x64 synthetic fields, 1 -> 1 channels, width 64, 16 modes, 4 layers,
+lifting/projection 256, batch 64 PER GPU (weak scaling), fp32.
+
+Keys beyond the base contract:
+  roofline      dominant kernel (by device time) of the spectral path, timed alone with CUDA events
+                on the launching stream; algorithmic bytes per launch are stated in DESIGN.md
+  cpu_baseline  the oracle (torch CPU restatement of the reference path) on this box's host cores,
+                on a bounded sample (smaller batch) of the same workload
+  e2e           same metric through the public nn.Module API with pinned-host inputs copied H2D and
+                the loss read back D2H inside the timed region every step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dict(model kwargs, grid, per-gpu batch, tucker)
+    "cfg1": dict(desc="FNO2D 64x64 in1 width32 modes12 L4 batch8 (BASELINE configs[0], CPU-runnable)",
+                 n_modes=(12, 12), hidden=32, cin=1, cout=1, L=4, lift=256, proj=256, H=64, W=64, batch=8, rank=0.0),
+    "cfg2": dict(desc="TFNO2D(Tucker rank 0.8) 64x64 in1 width64 modes16 L4 batch64/GPU (BASELINE configs[1])",
+                 n_modes=(16, 16), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=64, W=64, batch=64, rank=0.8),
+    "cfg2d": dict(desc="FNO2D(dense) 64x64 in1 width64 modes16 L4 batch64/GPU",
+                  n_modes=(16, 16), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=64, W=64, batch=64, rank=0.0),
+    "cfg3": dict(desc="FNO2D 256x256 in1 width64 modes32 L4 batch64/GPU (BASELINE configs[2])",
+                 n_modes=(32, 32), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=256, W=256, batch=64, rank=0.0),
+}
+
+
+def build_model(wl, seed=1234):
+    import torch
+    import dlwp_benchmark_b200 as pkg
+    torch.manual_seed(seed)
+    cls = pkg.TFNO if wl["rank"] > 0 else pkg.FNO
+    return cls(n_modes=wl["n_modes"], hidden_channels=wl["hidden"], in_channels=wl["cin"], out_channels=wl["cout"],
+               lifting_channels=wl["lift"], projection_channels=wl["proj"], n_layers=wl["L"],
+               rank=wl["rank"] if wl["rank"] > 0 else 1.0)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampling (recipe in B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([s.strip() for s in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on host cores, bounded sample
+# ----------------------------------------------------------------------------------------
+def cpu_oracle_rate(wl, sample_batch, steps, warmup):
+    """fwd + MSE + bwd of the oracle restatement (torch CPU, fp32, all host threads)."""
+    import torch
+    from oracle import spectral_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = build_model(wl)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(sample_batch, wl["cin"], wl["H"], wl["W"], generator=g)
+    y = torch.randn(sample_batch, wl["cout"], wl["H"], wl["W"], generator=g)
+    times = []
+    for it in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        out = so.fno_forward(sd, x, wl["n_modes"], wl["L"])
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return sample_batch / med, med, torch.get_num_threads()
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    sample = max(1, min(wl["batch"], 8 if wl["H"] <= 64 else 1))
+    steps = max(1, min(args.steps, 5))
+    rate, med, cores = cpu_oracle_rate(wl, sample, steps, min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": "FNO2D train samples/s (fwd+bwd)", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "note": "reference path = oracle restatement (neuralop is not vendored "
+                   "by the reference; parity unpinned) on host cores, bounded sample"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"batch {sample} of {wl['batch']}, fwd+MSE+bwd, median of {steps}"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# per-kernel roofline of the spectral path (timed alone, CUDA events on the launching stream)
+# ----------------------------------------------------------------------------------------
+def kernel_rooflines(wl, peak_gbs, reps=10):
+    import torch
+    from dlwp_benchmark_b200 import ops
+    from dlwp_benchmark_b200.plan import fno_plan
+    dev = torch.device("cuda")
+    B, C, H, W = wl["batch"], wl["hidden"], wl["H"], wl["W"]
+    half = [wl["n_modes"][0], wl["n_modes"][1] // 2 + 1]
+    plan = fno_plan(dev, H, W, half)
+    My, Mx = plan.My, plan.Mx
+    M = My * Mx
+    P = B * C * H * W
+    x = torch.randn(B, C, H, W, device=dev)
+    g = torch.randn(B, C, H, W, device=dev)
+    z = torch.randn(B, C, H, W, device=dev)
+    Wc = torch.randn(C, C, My, Mx, 2, device=dev) * 0.1
+    ws = torch.randn(C, C, device=dev) * 0.1
+    bv = torch.randn(C, device=dev)
+    T = ops.rowdft_fwd(plan, 0, x)
+    Xh = ops.coldft_fwd(plan, 0, T)
+    Yh = ops.mix_fwd(Xh, Wc)
+    Phi = ops.coldft_inv(plan, 0, Yh)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)     # > 126 MB L2
+    spec = 8 * B * C * M                                         # bytes of one [B,C,My,Mx] complex tensor
+    tb = 8 * B * C * H * Mx                                      # bytes of T / Phi
+    cases = {
+        "rowdft_fwd": (lambda: ops.rowdft_fwd(plan, 0, x), 4 * P + tb),
+        "coldft_fwd": (lambda: ops.coldft_fwd(plan, 0, T), tb + spec),
+        "modes_gemm(mix_fwd)": (lambda: ops.mix_fwd(Xh, Wc), 2 * spec + 8 * C * C * M),
+        "modes_gemm(wgrad)": (lambda: ops.mix_bwd_weight(Xh, Yh), 2 * spec + 8 * C * C * M),
+        "coldft_inv": (lambda: ops.coldft_inv(plan, 0, Yh), spec + tb),
+        "rowidft_pointwise(fwd)": (lambda: ops.rowidft_pointwise(plan, 0, Phi, x, ws, C, 1, bv, None, B, C, C, 0, True,
+                                                                 want_z=True), tb + 4 * P + 8 * P),
+        "rowidft_pointwise(bwd)": (lambda: ops.rowidft_pointwise(plan, 1, Phi, g, ws, 1, C, None, z, B, C, C, 1, False),
+                                   tb + 8 * P + 4 * P),
+        "pointwise_wgrad": (lambda: ops.pointwise_wgrad(g, x), 8 * P),
+    }
+    out = {}
+    for name, (fn, nbytes) in cases.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sum(ts) / len(ts)
+        out[name] = {"ms": t * 1e3, "alg_bytes": nbytes, "achieved_gbs": nbytes / t / 1e9,
+                     "frac": nbytes / t / 1e9 / peak_gbs}
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import dlwp_benchmark_b200 as pkg  # noqa: F401  (fails loudly if the .so is missing)
+    from dlwp_benchmark_b200.ddp import GradSync
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(wl).to(dev)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    sync = GradSync(params, world) if world > 1 else None
+    B = wl["batch"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    hx = torch.randn(B, wl["cin"], wl["H"], wl["W"], generator=g).pin_memory()
+    hy = torch.randn(B, wl["cout"], wl["H"], wl["W"], generator=g).pin_memory()
+    x, y = hx.to(dev), hy.to(dev)
+    loss_buf = torch.zeros((), device=dev)
+    hloss = torch.zeros((), pin_memory=True)
+
+    def fwd_bwd():
+        out = model(x)
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+
+    def step_eager():
+        if sync:
+            sync.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
+        fwd_bwd()
+        if sync:
+            sync.allreduce()
+        opt.step()
+
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if sync is None:
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fwd_bwd()
+                opt.step()
+            step = graph.replay
+        else:
+            # grads live in GradSync's flat buffer (static addresses); NCCL stays outside the graph
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sync.zero()
+                fwd_bwd()
+
+            def step():
+                graph.replay()
+                sync.allreduce()
+                opt.step()
+    else:
+        step = step_eager
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only (inputs resident) ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    clocks = cs.summary()
+
+    # ---- end to end: pinned host -> device every step, loss read back every step ----
+    def step_e2e():
+        x.copy_(hx, non_blocking=True)
+        y.copy_(hy, non_blocking=True)
+        step()
+        hloss.copy_(loss_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(hloss)
+
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        last_loss = step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+
+    tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        roof = None
+        try:
+            kr = kernel_rooflines(wl, peak)
+            # launches per train step of each kernel on the spectral path (4 layers)
+            L = wl["L"]
+            per_step = {"rowdft_fwd": 2 * L, "coldft_fwd": 2 * L, "modes_gemm(mix_fwd)": 2 * L - 0,
+                        "modes_gemm(wgrad)": L, "coldft_inv": 2 * L - 0, "rowidft_pointwise(fwd)": L,
+                        "rowidft_pointwise(bwd)": L - 1, "pointwise_wgrad": L}
+            share = {k: v["ms"] * per_step.get(k, 1) for k, v in kr.items()}
+            top = max(share, key=share.get)
+            roof = {"bound": "hbm", "kernel": top, "achieved": kr[top]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kr[top]["frac"], "traffic": None, "peak_source": peak_src,
+                    "kernel_ms": kr[top]["ms"], "alg_bytes": kr[top]["alg_bytes"],
+                    "all": {k: {"ms": round(v["ms"], 4), "frac": round(v["frac"], 4)} for k, v in kr.items()}}
+        except Exception as ex:  # the roofline block must never take the headline number down
+            roof = {"bound": "hbm", "error": repr(ex)}
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            sample = 8 if wl["H"] <= 64 else 1
+            rate, med, cores = cpu_oracle_rate(wl, sample, 5, 2)
+            cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"batch {sample} of {B}, fwd+MSE+bwd (no optimizer), median of 5, oracle restatement"}
+        n_launch = count_launches(wl)
+        line = {
+            "metric": "FNO2D train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [wl["H"], wl["W"]],
+                       "parallelism": f"dp{world}", "step": "fwd+MSE+bwd+Adam(fused)" + ("+allreduce" if world > 1 else ""),
+                       "cuda_graph": bool(use_graph),
+                       "l2": "per-step working set (activations of 4 layers + 256-ch lifting/projection, >1 GB) exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
+                    "h2d_bytes_per_step": (hx.numel() + hy.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": t_e2e / args.steps * 1e3, "last_loss": last_loss},
+            "gpu_launches": n_launch * args.steps,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def count_launches(wl):
+    """Kernels of libspectral_b200.so launched per train step (counted from the call graph:
+    FNOStackFn forward = 5 per layer; backward = 2 analysis + wgrad_spec + wgrad (partial+2 reduce) +
+    [mix_bwd_input + coldft_inv + rowidft_pointwise] for every layer but the first)."""
+    L = wl["L"]
+    fwd = 5 * L
+    bwd = L * (2 + 1 + 3) + (L - 1) * 3
+    return fwd + bwd
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    run_b200(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
