@@ -31,6 +31,14 @@ SIGNATURES = {
     "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),
     "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "sb200_cl_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp]),
+    "sb200_cl_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "sb200_cl_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
+    "sb200_cl_rowidft_res": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _vp]),
+    "sb200_afno_blocklinear_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _vp]),
+    "sb200_afno_blocklinear_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "sb200_afno_blocklinear_wgrad_workspace": (_i64, [_i64, _i, _i, _i]),
+    "sb200_afno_blocklinear_wgrad": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "sb200_gelu_fwd": (_i, [_vp, _vp, _i64, _vp]),
     "sb200_gelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
 }

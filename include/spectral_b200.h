@@ -99,6 +99,37 @@ int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);
 int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias,
                           int B, int Cout, int Cin, int64_t HW, float* workspace, void* stream);
 
+/* ---- channels-last (FourCastNet AFNO2D) stages ------------------------------------------
+ * reference: AFNO2D.forward, src/nsbench/models/fourcastnet/fourcastnet.py:77-126
+ * (identical copy src/dlwpbench/models/fourcastnet/fourcastnet.py:78-127).
+ * x is [B,h,w,C]; complex tensors are [...,C,2].  Plans: sb200_plan_create(h, w, r0, r1-r0, kc,
+ * 1/sqrt(hw), 1/sqrt(hw)).                                                                  */
+/* x [rows,W,C] -> T [rows,Mx,C] complex (rows = B*h); replaces the w-axis half of rfft2 (:84) */
+int sb200_cl_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, int C, void* stream);
+/* T [B,H,Mx,C] -> Xh [B,My,Mx,C]; replaces the h-axis half of rfft2 + the row/col slicing (:92-95) */
+int sb200_cl_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, int B, int C, void* stream);
+/* Yh [B,My,Mx,C] -> Phi [B,H,Mx,C]; replaces zeros + scatter (:87-90) + h-axis half of irfft2 (:123) */
+int sb200_cl_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, int B, int C, void* stream);
+/* Phi [rows,Mx,C] (+ resid [rows,W,C] or NULL) -> y [rows,W,C]; replaces the w-axis half of irfft2
+ * and the residual add `x + bias` (:126) */
+int sb200_cl_rowidft_res(sb200_plan_t plan, int pass, const float* Phi, const float* resid, float* y,
+                         int64_t rows, int C, void* stream);
+/* Block-diagonal complex linear layer: out[t,n,o] = act( sum_i in[t,n,i] * W[n,i,o] + b[n,o] ),
+ * w [2,nb,Ni,No] and b [2,nb,No] planar (index 0 = real part, 1 = imaginary part) exactly like the
+ * reference parameters w1/b1/w2/b2 (:72-75); act: 0 none, 1 ReLU on re and im separately (:95-105),
+ * 2 softshrink(lam) on re and im (:121).  replaces the 8 einsums + relu/softshrink. */
+int sb200_afno_blocklinear_fwd(const float* in, const float* w, const float* b, float* out, int64_t ntok,
+                               int nb, int Ni, int No, int act, float lam, void* stream);
+/* gin[t,n,i] = sum_o (gout[t,n,o] * act'(fwd_out[t,n,o])) * conj(W[n,i,o]); mask_kind as `act`;
+ * fwd_out may be NULL (no activation) */
+int sb200_afno_blocklinear_dgrad(const float* gout, const float* fwd_out, int mask_kind, const float* w,
+                                 float* gin, int64_t ntok, int nb, int Ni, int No, void* stream);
+/* gw[.,n,i,o] = sum_t conj(a[t,n,i]) * (gout*act')[t,n,o];  gb[.,n,o] = sum_t (gout*act')[t,n,o] */
+int64_t sb200_afno_blocklinear_wgrad_workspace(int64_t ntok, int nb, int Ni, int No);
+int sb200_afno_blocklinear_wgrad(const float* a, const float* gout, const float* fwd_out, int mask_kind,
+                                 float* gw, float* gb, int64_t ntok, int nb, int Ni, int No,
+                                 float* workspace, void* stream);
+
 /* Element-wise helpers used between layers: y = gelu(z);  gz = gy * gelu'(z) */
 int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream);
 int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream);
