@@ -218,7 +218,7 @@ def run_b200(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(wl).to(dev)
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     sync = GradSync(params, world) if world > 1 else None
     B = wl["batch"]
     g = torch.Generator().manual_seed(1234 + rank)

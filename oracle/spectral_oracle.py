@@ -86,7 +86,7 @@ def spectral_conv_dense(x: torch.Tensor, weight: torch.Tensor, bias: Optional[to
     fft_size = [H, W // 2 + 1]
     xf = torch.fft.rfftn(x, norm=fft_norm, dim=(-2, -1))
     xf = torch.fft.fftshift(xf, dim=(-2,))
-    out_fft = torch.zeros(B, weight.shape[1], *fft_size, dtype=xf.dtype)
+    out_fft = torch.zeros(B, weight.shape[1], *fft_size, dtype=xf.dtype, device=xf.device)
     # slice the weight down to min(size, n_modes) out of max_n_modes
     w_sl = _centre_slices(max_n_modes, [min(s, n) for s, n in zip(fft_size, n_modes)])
     w = weight[(slice(None), slice(None), *w_sl)]
@@ -143,7 +143,7 @@ def spectral_conv_tucker(x, core, factors, bias, n_modes, fft_norm="forward"):
     fft_size = [H, W // 2 + 1]
     xf = torch.fft.fftshift(torch.fft.rfftn(x, norm=fft_norm, dim=(-2, -1)), dim=(-2,))
     Cout = factors[1].shape[0]
-    out_fft = torch.zeros(B, Cout, *fft_size, dtype=xf.dtype)
+    out_fft = torch.zeros(B, Cout, *fft_size, dtype=xf.dtype, device=xf.device)
     kept = [min(s, n) for s, n in zip(fft_size, n_modes)]
     w_sl = _centre_slices([factors[2].shape[0], factors[3].shape[0]], kept)
     f2, f3 = factors[2][w_sl[0]], factors[3][w_sl[1]]
@@ -176,7 +176,8 @@ def explicit_tables(H: int, W: int, n_modes: Sequence[int], dtype=torch.float64)
 
 
 def spectral_conv_explicit(x, weight, bias, n_modes):
-    """Direct O(HW*M) evaluation of SpectralConv (norm='forward', even H). Small cases only."""
+    """Direct O(HW*M) evaluation of SpectralConv (norm='forward', even H). Small cases only.
+    ``n_modes`` is the already-halved mode tuple, as for ``spectral_conv_dense``."""
     B, Cin, H, W = x.shape
     rd = x.dtype
     cd = torch.complex128 if rd == torch.float64 else torch.complex64

@@ -1,0 +1,75 @@
+"""GPU parity tests of AFNO2D: CUDA kernels (through the C ABI) vs the reference's own vectors
+(tests/golden/afno2d_*.npz, produced by the reference class) and vs the oracle at cfg4 shapes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dlwp_benchmark_b200 as pkg
+from oracle import afno_oracle as ao
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+AFNO = ["afno2d_sq8", "afno2d_8x16", "afno2d_32x64", "afno2d_frac", "afno2d_fac2"]
+
+
+@pytest.mark.parametrize("name", AFNO)
+def test_afno_against_reference_vectors(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, h, w, C, nb, fac = [int(v) for v in d["meta"]]
+    m = pkg.AFNO2D(C, num_blocks=nb, sparsity_threshold=0.01, hard_thresholding_fraction=float(d["frac"]),
+                   hidden_size_factor=fac)
+    m.load_state_dict({k: torch.tensor(d[k]) for k in ("w1", "b1", "w2", "b2")}, strict=True)
+    m = m.to(DEV)
+    x = torch.tensor(d["x"]).to(DEV).requires_grad_(True)
+    y = m(x)
+    y.backward(torch.tensor(d["gy"]).to(DEV))
+    assert rel_l2(y, torch.tensor(d["y"])) < TOL
+    assert rel_l2(x.grad, torch.tensor(d["gx"])) < TOL
+    for k in ("w1", "b1", "w2", "b2"):
+        assert rel_l2(getattr(m, k).grad, torch.tensor(d["g" + k])) < 2e-5, k
+
+
+@pytest.mark.parametrize("B,h,w,C,nb", [(16, 32, 64, 256, 8), (2, 32, 64, 64, 4), (3, 16, 16, 24, 3), (1, 8, 12, 10, 5)])
+def test_afno_vs_oracle(B, h, w, C, nb):
+    """cfg4 token grid (32x64, embed 256, 8 blocks, batch 16) and ragged shapes (odd C/nb, w%8!=0)."""
+    torch.manual_seed(3)
+    m = pkg.AFNO2D(C, num_blocks=nb)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(10.0)            # move activations across the ReLU / softshrink kinks
+    x = torch.randn(B, h, w, C)
+    gy = torch.randn(B, h, w, C)
+    xo = x.double().requires_grad_(True)
+    ps = [p.detach().double().requires_grad_(True) for p in (m.w1, m.b1, m.w2, m.b2)]
+    yo = ao.afno2d_fft(xo, *ps, nb, 0.01, 1.0)
+    yo.backward(gy.double())
+    m = m.to(DEV)
+    xc = x.to(DEV).requires_grad_(True)
+    yc = m(xc)
+    yc.backward(gy.to(DEV))
+    assert rel_l2(yc, yo) < TOL
+    # a handful of elements sit within fp32 rounding of a ReLU/softshrink kink; allow those
+    assert rel_l2(xc.grad, xo.grad) < 5e-4
+    for p, po in zip((m.w1, m.b1, m.w2, m.b2), ps):
+        assert rel_l2(p.grad, po.grad) < 5e-4
+
+
+def test_afno_dtype_roundtrip():
+    m = pkg.AFNO2D(16, num_blocks=4).to(DEV)
+    x = torch.randn(1, 8, 8, 16, device=DEV, dtype=torch.float16)
+    assert m(x).dtype == torch.float16
+
+
+def test_afno_linear_when_mlp_is_dead():
+    """Size-independent property: with zero biases and the default 0.02 init every spectral value of a
+    small input falls in the softshrink dead zone, so AFNO2D(x) == x exactly (as in the reference)."""
+    torch.manual_seed(0)
+    m = pkg.AFNO2D(256, num_blocks=8).to(DEV)
+    with torch.no_grad():
+        m.b2.zero_(); m.b1.zero_()
+    x = 1e-3 * torch.randn(2, 32, 64, 256, device=DEV)
+    assert torch.equal(m(x), x)
