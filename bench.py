@@ -43,6 +43,11 @@ WORKLOADS = {
 }
 
 
+def log(msg):
+    sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
 def build_model(wl, seed=1234):
     import torch
     import dlwp_benchmark_b200 as pkg
@@ -245,6 +250,7 @@ def run_b200(args, wl, rank, world, local_rank):
         opt.step()
 
     use_graph = not args.no_graph
+    log(f'model built, graph={use_graph}')
     graph = None
     if use_graph:
         s = torch.cuda.Stream()
@@ -280,6 +286,7 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('step function ready')
     # ---- kernel-only (inputs resident) ----
     for _ in range(args.warmup):
         step()
@@ -294,6 +301,7 @@ def run_b200(args, wl, rank, world, local_rank):
     t_dev = e0.elapsed_time(e1) * 1e-3
     clocks = cs.summary()
 
+    log(f'kernel-only timing done: {t_dev / args.steps * 1e3:.3f} ms/step')
     # ---- end to end: pinned host -> device every step, loss read back every step ----
     def step_e2e():
         x.copy_(hx, non_blocking=True)
@@ -325,6 +333,7 @@ def run_b200(args, wl, rank, world, local_rank):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         roof = None
+        log('e2e done; per-kernel rooflines')
         try:
             kr = kernel_rooflines(wl, peak)
             # launches per train step of each kernel on the spectral path (4 layers)
@@ -341,6 +350,7 @@ def run_b200(args, wl, rank, world, local_rank):
         except Exception as ex:  # the roofline block must never take the headline number down
             roof = {"bound": "hbm", "error": repr(ex)}
         cpu = None
+        log('cpu baseline')
         if world == 1 and not args.skip_cpu:
             sample = 8 if wl["H"] <= 64 else 1
             rate, med, cores = cpu_oracle_rate(wl, sample, 5, 2)

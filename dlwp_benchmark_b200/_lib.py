@@ -31,6 +31,9 @@ SIGNATURES = {
     "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),
     "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "sb200_pointwise_small_n": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp]),
+    "sb200_wgrad_small_workspace": (_i64, [_i, _i, _i, _i64]),
+    "sb200_wgrad_small": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp]),
     "sb200_cl_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp]),
     "sb200_cl_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "sb200_cl_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),

@@ -1,0 +1,122 @@
+"""``FusedChainFn``: the whole FNO (lifting MLP -> L FNO blocks -> projection MLP) as ONE autograd
+node whose forward and backward are sequences of C-ABI kernel launches.
+
+Every layer of an FNO has the same form
+
+    z_l = [ SpectralConv(h_l ; W_l) ] + P_l h_l + b_l ,      h_{l+1} = gelu(z_l)  or  z_l
+
+(the bracket only for the L FNO blocks; P_l is a 1x1 convolution), so one fused kernel
+(``sb200_rowidft_pointwise``: row synthesis + channel mix + bias + GELU) serves all of them:
+
+  forward   per layer: [analysis -> mode mix -> column synthesis] -> fused kernel writing h_{l+1}
+            (and z_l when the layer has a GELU and gradients are needed)
+  backward  per layer, in reverse: the producer of the incoming gradient already multiplied it by
+            GELU'(z_l); weight grads (``pointwise_wgrad`` / ``wgrad_small`` + spectral ``modes_gemm``);
+            data grad through the same fused kernel with transposed weights, adjoint tables and the
+            GELU'(z_{l-1}) epilogue.
+
+Reference call chain replaced: neuralop ``FNO.forward`` (lifting MLP, FNOBlocks x L, projection MLP)
+as constructed at src/nsbench/models/fno/fno.py:19-27 / src/dlwpbench/models/fno/fno.py:38-47.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from .plan import fno_plan
+
+SMALL = 8      # channel counts handled by the small-N forward kernel
+SMALL_W = 16   # channel counts handled by the small weight-gradient kernel
+
+
+class FusedChainFn(torch.autograd.Function):
+    """args: x, n_modes_halved, spec (tuple of bool per layer: has a spectral branch),
+    acts (tuple of bool per layer), then per layer (Wspec_l or None, Wp_l, b_l or None)."""
+
+    @staticmethod
+    def forward(ctx, x, n_modes_halved, spec, acts, *params):
+        if not x.is_cuda:
+            raise _lib.SpectralB200Error("FNO(B200) got a CPU tensor: there is no CPU / torch.fft path")
+        x = x.contiguous().float()
+        B, _, H, Wd = x.shape
+        nl = len(spec)
+        plan = fno_plan(x.device, H, Wd, n_modes_halved)
+        need_grad = any(ctx.needs_input_grad)
+        Ws, Ps, bs = [], [], []
+        for l in range(nl):
+            w, p, b = params[3 * l:3 * l + 3]
+            Ws.append(w.contiguous().float() if w is not None else None)
+            Ps.append(p.reshape(p.shape[0], p.shape[1]).contiguous().float())
+            bs.append(b.reshape(-1).contiguous().float() if b is not None else None)
+        hs, Xhs, zs = [], [], []
+        h = x
+        for l in range(nl):
+            N, M = Ps[l].shape
+            want_z = acts[l] and need_grad
+            Xh = None
+            if spec[l]:
+                Xh = ops.coldft_fwd(plan, 0, ops.rowdft_fwd(plan, 0, h))
+                Phi = ops.coldft_inv(plan, 0, ops.mix_fwd(Xh, Ws[l]))
+                y, z = ops.rowidft_pointwise(plan, 0, Phi, h, Ps[l], M, 1, bs[l], None, B, M, N, 0, acts[l],
+                                             want_z=want_z)
+            elif N <= SMALL:
+                y, z = ops.pointwise_small_n(h, Ps[l], bs[l], acts[l], want_z=want_z)
+            else:
+                y, z = ops.rowidft_pointwise(plan, 0, None, h, Ps[l], M, 1, bs[l], None, B, M, N, 0, acts[l],
+                                             want_z=want_z)
+            hs.append(h); Xhs.append(Xh); zs.append(z)
+            h = y
+        ctx.plan, ctx.nl, ctx.spec, ctx.acts = plan, nl, tuple(spec), tuple(acts)
+        ctx.shapes = [(params[3 * l + 1].shape, params[3 * l + 2].shape if params[3 * l + 2] is not None else None)
+                      for l in range(nl)]
+        saved = list(hs) + [t for t in Xhs if t is not None] + [t for t in zs if t is not None] \
+            + [t for t in Ws if t is not None] + Ps
+        ctx.has_z = [t is not None for t in zs]
+        ctx.save_for_backward(*saved)
+        return h
+
+    @staticmethod
+    def backward(ctx, gy):
+        nl, spec, acts, plan = ctx.nl, ctx.spec, ctx.acts, ctx.plan
+        sv = list(ctx.saved_tensors)
+        it = iter(sv)
+        hs = [next(it) for _ in range(nl)]
+        Xhs = [next(it) if spec[l] else None for l in range(nl)]
+        zs = [next(it) if ctx.has_z[l] else None for l in range(nl)]
+        Ws = [next(it) if spec[l] else None for l in range(nl)]
+        Ps = [next(it) for _ in range(nl)]
+        B = hs[0].shape[0]
+        gz = gy.contiguous().float()
+        if acts[nl - 1]:
+            gz = ops.gelu_bwd(gz, zs[nl - 1])
+        grads: List[Optional[torch.Tensor]] = [None] * (3 * nl)
+        gx = None
+        for l in range(nl - 1, -1, -1):
+            N, M = Ps[l].shape
+            has_b = ctx.shapes[l][1] is not None
+            # ---- weight gradients ----
+            if N <= SMALL_W and N <= M:
+                gP, gb, _ = ops.wgrad_small(gz, hs[l], False, has_b, False)
+            elif M <= SMALL_W:
+                gP, _, gb = ops.wgrad_small(hs[l], gz, True, False, has_b)
+            else:
+                gP, gb = ops.pointwise_wgrad(gz, hs[l], want_bias=has_b)
+            grads[3 * l + 1] = gP.reshape(ctx.shapes[l][0])
+            if has_b:
+                grads[3 * l + 2] = gb.reshape(ctx.shapes[l][1])
+            gYh = None
+            if spec[l]:
+                gYh = ops.coldft_fwd(plan, 1, ops.rowdft_fwd(plan, 1, gz))
+                grads[3 * l] = ops.mix_bwd_weight(Xhs[l], gYh)
+            # ---- data gradient (fused with GELU' of the previous layer) ----
+            if l > 0 or ctx.needs_input_grad[0]:
+                gPhi = ops.coldft_inv(plan, 1, ops.mix_bwd_input(gYh, Ws[l])) if spec[l] else None
+                zprev = zs[l - 1] if (l > 0 and acts[l - 1]) else None
+                gprev, _ = ops.rowidft_pointwise(plan, 1, gPhi, gz, Ps[l], 1, M, None, zprev, B, N, M, 1, False)
+                if l > 0:
+                    gz = gprev
+                else:
+                    gx = gprev
+        return (gx, None, None, None, *grads)

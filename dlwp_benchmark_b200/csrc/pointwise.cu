@@ -108,8 +108,9 @@ rowidft_pointwise_kernel(const PwParams p) {
                 Ws[idx] = v;
             }
             __syncthreads();
-#pragma unroll
-            for (int mm = 0; mm < PW_MC; ++mm) {
+            const int kmax = min(PW_MC, p.M - m0);
+#pragma unroll 4
+            for (int mm = 0; mm < kmax; ++mm) {
                 const float4 a0 = *reinterpret_cast<const float4*>(As + mm * PW_PX + tx * 4);
                 const float4 a1 = *reinterpret_cast<const float4*>(As + mm * PW_PX + 64 + tx * 4);
                 const float4 b0 = *reinterpret_cast<const float4*>(Ws + mm * PW_N + tn * 8);
@@ -350,6 +351,201 @@ extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, 
         wgrad_reduce_kernel<<<(unsigned)ceil_div64(Cout, 256), 256, 0, st>>>(wsb, gbias, Cout, nchunks);
         SB_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+// ======================================================================================
+// pointwise layer with few output channels (N <= 8): out[b,n,p] = sum_m W[n,m] A[b,m,p] + bias[n]
+// (projection fc2 of the FNO: 256 -> out_channels).  Memory-bound: A is read exactly once.
+// ======================================================================================
+template <int NT>
+__global__ void __launch_bounds__(256)
+pointwise_small_n_kernel(const float* __restrict__ A, const float* __restrict__ Wp, const float* __restrict__ bias,
+                         float* __restrict__ z_out, float* __restrict__ y_out, int M, int N, int64_t HW,
+                         int apply_act) {
+    extern __shared__ float wsm[];      // [NT][M]
+    const int b = blockIdx.y;
+    for (int idx = threadIdx.x; idx < NT * M; idx += 256) {
+        const int n = idx / M, m = idx % M;
+        wsm[idx] = n < N ? __ldg(Wp + (int64_t)n * M + m) : 0.f;
+    }
+    __syncthreads();
+    const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p0 >= HW) return;
+    float4 acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* Ab = A + (int64_t)b * M * HW + p0;
+#pragma unroll 4
+    for (int m = 0; m < M; ++m) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(Ab + (int64_t)m * HW));
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float w = wsm[n * M + m];
+            acc[n].x = fmaf(w, a.x, acc[n].x); acc[n].y = fmaf(w, a.y, acc[n].y);
+            acc[n].z = fmaf(w, a.z, acc[n].z); acc[n].w = fmaf(w, a.w, acc[n].w);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        if (n >= N) break;
+        const float bv = bias ? __ldg(bias + n) : 0.f;
+        float4 v = make_float4(acc[n].x + bv, acc[n].y + bv, acc[n].z + bv, acc[n].w + bv);
+        const int64_t off = ((int64_t)b * N + n) * HW + p0;
+        if (z_out) *reinterpret_cast<float4*>(z_out + off) = v;
+        if (apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+        *reinterpret_cast<float4*>(y_out + off) = v;
+    }
+}
+
+extern "C" int sb200_pointwise_small_n(const float* A, const float* Wp, const float* bias, float* z_out, float* y_out,
+                                       int B, int M, int N, int64_t HW, int apply_act, void* stream) {
+    SB_REQUIRE(A && Wp && y_out, "pointwise_small_n: NULL argument");
+    SB_REQUIRE(N >= 1 && N <= 8, "pointwise_small_n: N=%d must be in [1,8]", N);
+    SB_REQUIRE(HW % 4 == 0, "pointwise_small_n: H*W must be a multiple of 4");
+    SB_REQUIRE(B <= 65535, "pointwise_small_n: batch too large");
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div64(HW, 1024), (unsigned)B);
+    const int NT = N <= 1 ? 1 : (N <= 2 ? 2 : (N <= 4 ? 4 : 8));
+    const size_t smem = (size_t)NT * M * sizeof(float);
+    SB_REQUIRE(smem <= 48 * 1024, "pointwise_small_n: M=%d too large", M);
+    switch (NT) {
+        case 1: pointwise_small_n_kernel<1><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        case 2: pointwise_small_n_kernel<2><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        case 4: pointwise_small_n_kernel<4><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        default: pointwise_small_n_kernel<8><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+    }
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ======================================================================================
+// weight gradient when one side has few channels (S <= 16):
+//   dot[s,l] = sum_{b,p} small[b,s,p] * big[b,l,p];  sum_small[s] = sum small;  sum_big[l] = sum big
+// (lifting fc1: small = x (Cin), big = g;   projection fc2: small = g (Cout), big = x)
+// one warp per big channel; deterministic two-phase reduction over (b, pixel-chunk).
+// ======================================================================================
+template <int ST>
+__global__ void __launch_bounds__(256)
+wgrad_small_partial_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ ws,
+                           int S, int L, int64_t HW, int64_t chunk_px, int chunks_per_b) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x;
+    const int b = chunk / chunks_per_b;
+    const int64_t pc0 = (int64_t)(chunk % chunks_per_b) * chunk_px;
+    int64_t pc1 = pc0 + chunk_px;
+    if (pc1 > HW) pc1 = HW;
+    const int l = blockIdx.y * 8 + warp;
+    float acc[ST], accs[ST];
+    float accl = 0.f;
+#pragma unroll
+    for (int s = 0; s < ST; ++s) { acc[s] = 0.f; accs[s] = 0.f; }
+    if (l < L) {
+        const float* bp = big + ((int64_t)b * L + l) * HW;
+        const float* sp = small + (int64_t)b * S * HW;
+        for (int64_t p = pc0 + lane * 4; p < pc1; p += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(bp + p));
+            accl += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+            for (int s = 0; s < ST; ++s) {
+                if (s < S) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(sp + (int64_t)s * HW + p));
+                    acc[s] = fmaf(g.x, v.x, acc[s]); acc[s] = fmaf(g.y, v.y, acc[s]);
+                    acc[s] = fmaf(g.z, v.z, acc[s]); acc[s] = fmaf(g.w, v.w, acc[s]);
+                    accs[s] += (g.x + g.y) + (g.z + g.w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        accl += __shfl_xor_sync(0xffffffffu, accl, off);
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+            acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], off);
+            accs[s] += __shfl_xor_sync(0xffffffffu, accs[s], off);
+        }
+    }
+    if (lane == 0 && l < L) {
+        // per-chunk layout: dot [S][L], sum_small [S], sum_big [L]
+        float* wsc = ws + (int64_t)chunk * ((int64_t)S * L + S + L);
+#pragma unroll
+        for (int s = 0; s < ST; ++s)
+            if (s < S) wsc[(int64_t)s * L + l] = acc[s];
+        wsc[(int64_t)S * L + S + l] = accl;
+        if (l == 0) {
+#pragma unroll
+            for (int s = 0; s < ST; ++s)
+                if (s < S) wsc[(int64_t)S * L + s] = accs[s];
+        }
+    }
+}
+
+// out_dot[s*L+l] (or transposed [l*S+s]), out_small[S], out_big[L] (either may be NULL)
+__global__ void __launch_bounds__(256)
+wgrad_small_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out_dot, float* __restrict__ out_small,
+                          float* __restrict__ out_big, int S, int L, int nchunks, int transpose) {
+    const int64_t E = (int64_t)S * L + S + L;
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= E) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < nchunks; ++c) s += __ldg(ws + (int64_t)c * E + e);
+    if (e < (int64_t)S * L) {
+        const int si = (int)(e / L), li = (int)(e % L);
+        out_dot[transpose ? (int64_t)li * S + si : e] = s;
+    } else if (e < (int64_t)S * L + S) {
+        if (out_small) out_small[e - (int64_t)S * L] = s;
+    } else {
+        if (out_big) out_big[e - (int64_t)S * L - S] = s;
+    }
+}
+
+static void wgrad_small_chunking(int B, int L, int64_t HW, int64_t* chunk_px, int* chunks_per_b) {
+    const int64_t blocks_per_chunk = (L + 7) / 8;
+    int64_t cpb = (2 * 148 + B * blocks_per_chunk - 1) / (B * blocks_per_chunk);
+    const int64_t max_cpb = (HW + 1023) / 1024;
+    if (cpb > max_cpb) cpb = max_cpb;
+    if (cpb < 1) cpb = 1;
+    int64_t px = (HW + cpb - 1) / cpb;
+    px = (px + 127) / 128 * 128;
+    *chunk_px = px;
+    *chunks_per_b = (int)((HW + px - 1) / px);
+}
+
+extern "C" int64_t sb200_wgrad_small_workspace(int B, int S, int L, int64_t HW) {
+    int64_t px; int cpb;
+    wgrad_small_chunking(B, L, HW, &px, &cpb);
+    return (int64_t)B * cpb * ((int64_t)S * L + S + L);
+}
+
+extern "C" int sb200_wgrad_small(const float* small, const float* big, float* out_dot, float* out_small,
+                                 float* out_big, int B, int S, int L, int64_t HW, int transpose, float* workspace,
+                                 void* stream) {
+    SB_REQUIRE(small && big && out_dot && workspace, "wgrad_small: NULL argument");
+    SB_REQUIRE(S >= 1 && S <= 16, "wgrad_small: S=%d must be in [1,16]", S);
+    SB_REQUIRE(HW % 4 == 0, "wgrad_small: H*W must be a multiple of 4");
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t px; int cpb;
+    wgrad_small_chunking(B, L, HW, &px, &cpb);
+    const int nchunks = B * cpb;
+    dim3 grid(nchunks, (L + 7) / 8);
+    SB_REQUIRE(grid.y <= 65535, "wgrad_small: L too large");
+    const int ST = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : (S <= 8 ? 8 : 16)));
+    switch (ST) {
+        case 1: wgrad_small_partial_kernel<1><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+        case 2: wgrad_small_partial_kernel<2><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+        case 4: wgrad_small_partial_kernel<4><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+        case 8: wgrad_small_partial_kernel<8><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+        default: wgrad_small_partial_kernel<16><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+    }
+    SB_LAUNCH_CHECK();
+    const int64_t E = (int64_t)S * L + S + L;
+    wgrad_small_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(workspace, out_dot, out_small, out_big, S,
+                                                                             L, nchunks, transpose);
+    SB_LAUNCH_CHECK();
     return 0;
 }
 

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .spectral_conv import SpectralConv as _SpectralConv, FNOBlockFn, FNOStackFn
+from .chain import FusedChainFn
 
 
 def _conv1x1_fp32(x, conv: nn.Conv2d):
@@ -180,6 +181,7 @@ class FNO(nn.Module):
             self.lifting = MLP(in_channels, hidden_channels, hidden_channels=hidden_channels, n_layers=1, n_dim=2)
         self.projection = MLP(hidden_channels, out_channels, hidden_channels=projection_channels, n_layers=2,
                               n_dim=2, non_linearity=non_linearity)
+        self.fused = True   # route the whole model through FusedChainFn (False: per-stage autograd nodes)
 
     @property
     def n_modes(self):
@@ -190,10 +192,30 @@ class FNO(nn.Module):
             raise NotImplementedError("FNO(B200): output_shape is only used by the 3-D wrappers (out of scope)")
         if not x.is_cuda:
             raise _lib.SpectralB200Error("FNO(B200) got a CPU tensor: there is no CPU / torch.fft path")
+        if self.fused and self.fno_blocks.convs.bias is not None and x.shape[-1] % 4 == 0:
+            return self._forward_fused(x)
         x = self.lifting(x)
         x = self.fno_blocks.forward_all(x)
         x = self.projection(x)
         return x
+
+    def _forward_fused(self, x):
+        """lifting + blocks + projection as one chain of C-ABI kernel launches (FusedChainFn)."""
+        H, W = x.shape[-2:]
+        spec, acts, params = [], [], []
+        nl_lift = len(self.lifting.fcs)
+        for i, fc in enumerate(self.lifting.fcs):
+            spec.append(False); acts.append(i < nl_lift - 1)
+            params += [None, fc.weight, fc.bias]
+        blocks = self.fno_blocks
+        for l in range(self.n_layers):
+            spec.append(True); acts.append(l < self.n_layers - 1)
+            params += [blocks.convs.dense_weight(l, H, W), blocks.fno_skips[l].weight, blocks.convs.bias[l]]
+        nl_proj = len(self.projection.fcs)
+        for i, fc in enumerate(self.projection.fcs):
+            spec.append(False); acts.append(i < nl_proj - 1)
+            params += [None, fc.weight, fc.bias]
+        return FusedChainFn.apply(x, tuple(blocks.convs.n_modes), tuple(spec), tuple(acts), *params)
 
 
 class TFNO(FNO):

@@ -139,3 +139,31 @@ def gelu_bwd(gy: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     gz = torch.empty_like(z)
     _lib.check(_lib.load().sb200_gelu_bwd(_p(gy), _p(z), _p(gz), z.numel(), _stream()), "gelu_bwd")
     return gz
+
+
+def pointwise_small_n(A: torch.Tensor, Wp: torch.Tensor, bias, apply_act: bool, want_z: bool = False):
+    """out[b,n,p] = sum_m Wp[n,m] A[b,m,p] + bias[n] for N <= 8; returns (y, z or None)."""
+    _req(A, "A"); _req(Wp, "Wp")
+    B, M, H, W = A.shape
+    N = Wp.shape[0]
+    y = torch.empty(B, N, H, W, device=A.device, dtype=torch.float32)
+    z = torch.empty_like(y) if want_z else None
+    _lib.check(_lib.load().sb200_pointwise_small_n(_p(A), _p(Wp), _p(bias), _p(z), _p(y), B, M, N, H * W,
+                                                   int(apply_act), _stream()), "pointwise_small_n")
+    return y, z
+
+
+def wgrad_small(small: torch.Tensor, big: torch.Tensor, transpose: bool, want_small_sum: bool, want_big_sum: bool):
+    """dot[s,l] = sum small[b,s,p] big[b,l,p] (returned as [l,s] if transpose); channel sums on request."""
+    _req(small, "small"); _req(big, "big")
+    B, S = small.shape[:2]
+    L = big.shape[1]
+    HW = small.shape[2] * small.shape[3]
+    lib = _lib.load()
+    ws = torch.empty(lib.sb200_wgrad_small_workspace(B, S, L, HW), device=small.device, dtype=torch.float32)
+    dot = torch.empty((L, S) if transpose else (S, L), device=small.device, dtype=torch.float32)
+    ss = torch.empty(S, device=small.device, dtype=torch.float32) if want_small_sum else None
+    bs = torch.empty(L, device=small.device, dtype=torch.float32) if want_big_sum else None
+    _lib.check(lib.sb200_wgrad_small(_p(small), _p(big), _p(dot), _p(ss), _p(bs), B, S, L, HW, int(transpose), _p(ws),
+                                     _stream()), "wgrad_small")
+    return dot, ss, bs

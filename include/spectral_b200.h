@@ -99,6 +99,19 @@ int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);
 int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias,
                           int B, int Cout, int Cin, int64_t HW, float* workspace, void* stream);
 
+/* Pointwise layer with few output channels (N <= 8), e.g. the FNO projection's last 1x1 conv
+ * (neuralop MLP.fcs[1], 256 -> out_channels):  acc[b,n,p] = sum_m Wp[n,m] A[b,m,p] + bias[n];
+ * z_out = acc (if non-NULL), y_out = gelu(acc) if apply_act else acc.  A is read once. */
+int sb200_pointwise_small_n(const float* A, const float* Wp, const float* bias, float* z_out, float* y_out,
+                            int B, int M, int N, int64_t HW, int apply_act, void* stream);
+/* Weight gradient of a 1x1 conv when one side has few channels (S <= 16):
+ *   out_dot[s,l] = sum_{b,p} small[b,s,p] * big[b,l,p]   (written as [l,s] when transpose != 0)
+ *   out_small[s] = sum small,  out_big[l] = sum big       (either may be NULL)
+ * small [B,S,HW], big [B,L,HW].  Deterministic two-phase reduction. */
+int64_t sb200_wgrad_small_workspace(int B, int S, int L, int64_t HW);
+int sb200_wgrad_small(const float* small, const float* big, float* out_dot, float* out_small, float* out_big,
+                      int B, int S, int L, int64_t HW, int transpose, float* workspace, void* stream);
+
 /* ---- channels-last (FourCastNet AFNO2D) stages ------------------------------------------
  * reference: AFNO2D.forward, src/nsbench/models/fourcastnet/fourcastnet.py:77-126
  * (identical copy src/dlwpbench/models/fourcastnet/fourcastnet.py:78-127).
