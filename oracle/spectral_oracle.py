@@ -149,9 +149,15 @@ def spectral_conv_tucker(x, core, factors, bias, n_modes, fft_norm="forward"):
     f2, f3 = factors[2][w_sl[0]], factors[3][w_sl[1]]
     x_sl = _centre_slices(fft_size, [f2.shape[0], f3.shape[0]])
     idx = (slice(None), slice(None), *x_sl)
-    out_fft[idx] = torch.einsum("abcd,fghi,bf,eg,ch,di->aecd", xf[idx], core.to(xf.dtype),
-                                factors[0].to(xf.dtype), factors[1].to(xf.dtype),
-                                f2.to(xf.dtype), f3.to(xf.dtype))
+    # 'abcd,fghi,bf,eg,ch,di->aecd' evaluated pairwise in the order a contraction-path optimiser
+    # (opt_einsum, which tensorly's einsum uses when present) picks; a naive left-to-right
+    # torch.einsum would build an 8-index outer product.
+    cd = xf.dtype
+    xs = xf[idx]
+    t1 = torch.einsum("abcd,bf->afcd", xs, factors[0].to(cd))
+    t2 = torch.einsum("fghi,ch,di->fgcd", core.to(cd), f2.to(cd), f3.to(cd))
+    t3 = torch.einsum("afcd,fgcd->agcd", t1, t2)
+    out_fft[idx] = torch.einsum("agcd,eg->aecd", t3, factors[1].to(cd))
     out_fft = torch.fft.fftshift(out_fft, dim=(-2,))
     y = torch.fft.irfftn(out_fft, s=(H, W), dim=(-2, -1), norm=fft_norm)
     if bias is not None:

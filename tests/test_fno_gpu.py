@@ -35,6 +35,10 @@ STAGE_SHAPES = [
     (2, 8, 32, 64, (12, 12)),    # dlwpbench grid
     (1, 2, 64, 128, (32, 32)),
     (1, 2, 12, 20, (6, 7)),      # W % 8 != 0, odd mode counts
+    (1, 2, 256, 256, (32, 32)),  # cfg3 grid
+    (1, 1, 128, 256, (16, 16)),
+    (1, 1, 256, 64, (32, 32)),
+    (2, 1, 128, 128, (32, 32)),  # cfg5 grid
 ]
 
 
