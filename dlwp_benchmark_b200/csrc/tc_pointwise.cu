@@ -1,0 +1,249 @@
+// tcgen05 (5th-gen tensor core) version of the fused [row synthesis +] pointwise channel mix + epilogue.
+//
+//   D[p, n] = sum_m A[b, m, p] * Wp[n, m]                   p = 128 pixels of one sample (UMMA M = 128)
+//                                                           n = all output channels        (UMMA N <= 256)
+// A tile:  TMA (cp.async.bulk.tensor.2d, 128B swizzle) straight from the NCHW activation viewed as
+//          [B*M, H*W]: four boxes {32 px, KC channels} = the canonical MN-major SWIZZLE_128B operand.
+// B tile:  the (tiny) weight matrix, written by the CTA's threads in the K-major SWIZZLE_128B layout.
+// D:       fp32 accumulator in TMEM; epilogue reads it with tcgen05.ld (lane = pixel), adds bias,
+//          applies GELU / GELU' and stores coalesced along the pixel dimension.
+//
+// Precision: kind::tf32 keeps 10 mantissa bits, so the fp32 parity path splits both operands
+// (x = hi + lo, hi = the tf32-representable part) and issues three MMAs per k-step
+// (hi*hi + lo*hi + hi*lo): error ~2^-21, inside the 1e-5 parity bar.  PASSES = 1 is the plain TF32
+// path (parity ~1e-3, the north_star's "tensor-core path" tolerance).
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+        g_encode = (PFN_encodeTiled)fn;
+    else
+        cudaGetLastError();
+}
+
+int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                           uint32_t box0, uint32_t box1, int swizzle128) {
+    std::call_once(g_encode_once, load_encode);
+    SB_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstr[1] = {stride1_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (dims %llu x %llu, box %u x %u)", (int)r,
+               (unsigned long long)dim0, (unsigned long long)dim1, box0, box1);
+    return 0;
+}
+
+static int g_tc_mode = 3;   // 0 = CUDA-core kernels only, 1 = TF32 single pass, 3 = 3xTF32 (fp32 parity)
+extern "C" int sb200_set_tc_mode(int mode) {
+    SB_REQUIRE(mode == 0 || mode == 1 || mode == 3, "set_tc_mode: mode must be 0, 1 or 3");
+    g_tc_mode = mode;
+    return 0;
+}
+extern "C" int sb200_get_tc_mode(void) { return g_tc_mode; }
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TP_PX = 128;
+
+struct TcPwParams {
+    const float* Wp; int64_t w_sn, w_sm;
+    const float* bias; const float* zprev;
+    float* z_out; float* y_out;
+    int B, M, N, KC;
+    int64_t HW;
+    int mode, apply_act;
+    uint32_t idesc, tmem_cols;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(128, 1)
+tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (all 1024-byte aligned): A_hi | A_lo | B_hi | B_lo | barriers
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KC = p.KC;
+    const uint32_t a_bytes = (uint32_t)KC * 512;                       // 4 boxes x KC rows x 128 B
+    const int nchunk = (KC + 31) / 32;
+    const uint32_t b_chunk_bytes = (uint32_t)p.N * 128;                // N rows x 128 B
+    const uint32_t b_bytes = (uint32_t)nchunk * b_chunk_bytes;
+    uint8_t* A_hi = base;
+    uint8_t* A_lo = A_hi + a_bytes;
+    uint8_t* B_hi = A_lo + (PASSES == 3 ? a_bytes : 0);
+    uint8_t* B_lo = B_hi + ((b_bytes + 1023) & ~1023u);
+    uint8_t* tail = B_lo + (PASSES == 3 ? ((b_bytes + 1023) & ~1023u) : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* mma_bar = full_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_per_b = (int)((p.HW + TP_PX - 1) / TP_PX);
+    const int b = blockIdx.x / tiles_per_b;
+    const int64_t p_base = (int64_t)(blockIdx.x % tiles_per_b) * TP_PX;
+
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmapA);
+        tc::mbar_init(full_bar, 1);
+        tc::mbar_init(mma_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_d = *tmem_slot;
+
+    uint32_t it = 0;
+    for (int m0 = 0; m0 < p.M; m0 += KC, ++it) {
+        // ---- producer: TMA the activation tile (async), threads stage the weight chunk meanwhile ----
+        if (tid == 0) {
+            tc::mbar_expect_tx(full_bar, a_bytes);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                tc::tma_load_2d(A_hi + (uint32_t)i * KC * 128, &tmapA, (int)(p_base + 32 * i), b * p.M + m0, full_bar);
+        }
+        for (int idx = tid; idx < p.N * KC; idx += 128) {
+            const int n = idx / KC, k = idx % KC;
+            const float w = __ldg(p.Wp + (int64_t)n * p.w_sn + (int64_t)(m0 + k) * p.w_sm);
+            const float hi = tc::tf32_trunc(w);
+            const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
+            *reinterpret_cast<float*>(B_hi + off) = hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
+        }
+        tc::mbar_wait(full_bar, it & 1);
+        if (PASSES == 3) {
+            // split the activation tile in place: hi = tf32 part, lo = remainder (layout-agnostic, element-wise)
+            float4* ah = reinterpret_cast<float4*>(A_hi);
+            float4* al = reinterpret_cast<float4*>(A_lo);
+            for (int idx = tid; idx < (int)(a_bytes / 16); idx += 128) {
+                float4 v = ah[idx];
+                float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                ah[idx] = h;
+                al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        // ---- MMA issue (one thread) ----
+        if (tid == 0) {
+            tc::tc_fence_after_sync();
+            const uint32_t a_lbo = (uint32_t)KC * 128;
+            for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint32_t a_off = (uint32_t)ks * 1024;
+                const uint32_t b_off = (uint32_t)(ks >> 2) * b_chunk_bytes + (uint32_t)(ks & 3) * 32;
+                const uint64_t ah = tc::make_smem_desc(tc::smem_u32(A_hi) + a_off, a_lbo, 1024, tc::LAYOUT_SW128);
+                const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
+                tc::umma_tf32(tmem_d, ah, bh, p.idesc, (m0 > 0 || ks > 0) ? 1u : 0u);
+                if (PASSES == 3) {
+                    const uint64_t al = tc::make_smem_desc(tc::smem_u32(A_lo) + a_off, a_lbo, 1024, tc::LAYOUT_SW128);
+                    const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
+                    tc::umma_tf32(tmem_d, al, bh, p.idesc, 1u);
+                    tc::umma_tf32(tmem_d, ah, bl, p.idesc, 1u);
+                }
+            }
+            tc::umma_commit(mma_bar);
+        }
+        tc::mbar_wait(mma_bar, it & 1);     // smem operands free again, accumulator complete for this chunk
+        tc::tc_fence_after_sync();
+    }
+
+    // ---- epilogue: TMEM -> registers -> global (lane = pixel, coalesced along pixels) ----
+    const int64_t pp = p_base + warp * 32 + lane;
+    const bool in_range = pp < p.HW;
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tc::tmem_ld_wait();
+        if (in_range) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = c0 + j;
+                if (n < p.N) {
+                    float v = __uint_as_float(r[j]);
+                    const int64_t off = ((int64_t)b * p.N + n) * p.HW + pp;
+                    if (p.bias) v += __ldg(p.bias + n);
+                    if (p.mode == 0) {
+                        if (p.z_out) p.z_out[off] = v;
+                        if (p.apply_act) v = gelu_f(v);
+                    } else if (p.zprev) {
+                        v *= gelu_grad_f(__ldg(p.zprev + off));
+                    }
+                    p.y_out[off] = v;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch (called from sb200_rowidft_pointwise)
+// ---------------------------------------------------------------------------------------------
+int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, cudaStream_t st, int* handled) {
+    *handled = 0;
+    (void)plan; (void)pass;
+    if (g_tc_mode == 0) return 0;
+    if (q.Phi != nullptr || q.Wp == nullptr) return 0;                  // spectral term: CUDA-core kernel for now
+    const int64_t HW = (int64_t)q.H * q.W;
+    const int M = q.M, N = q.N;
+    if (M % 8 != 0 || !(M <= 64 || M % 64 == 0)) return 0;
+    if (N % 16 != 0 || N < 16 || N > 256) return 0;
+    if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(q.A) & 15) != 0) return 0;
+    if ((int64_t)q.B * M >= (1LL << 31)) return 0;
+
+    TcPwParams p;
+    p.Wp = q.Wp; p.w_sn = q.w_sn; p.w_sm = q.w_sm; p.bias = q.bias; p.zprev = q.zprev;
+    p.z_out = q.z_out; p.y_out = q.y_out; p.B = q.B; p.M = M; p.N = N; p.KC = M < 64 ? M : 64; p.HW = HW;
+    p.mode = q.mode; p.apply_act = q.apply_act;
+    p.idesc = tc::make_idesc_tf32(128, N, /*A MN-major*/ 1, /*B K-major*/ 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)N) cols <<= 1;
+    p.tmem_cols = cols;
+
+    CUtensorMap tmap;
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 1))
+        return rc;
+
+    const int passes = g_tc_mode;
+    const size_t a_bytes = (size_t)p.KC * 512;
+    const size_t b_bytes = ((size_t)((p.KC + 31) / 32) * N * 128 + 1023) & ~(size_t)1023;
+    const size_t smem = 1024 + a_bytes * (passes == 3 ? 2 : 1) + b_bytes * (passes == 3 ? 2 : 1) + 64;
+    SB_REQUIRE(smem <= 227 * 1024, "tc_pointwise: shared memory %zu too large", smem);
+    const int64_t tiles = (HW + TP_PX - 1) / TP_PX * q.B;
+    SB_REQUIRE(tiles < (1LL << 31), "tc_pointwise: too many tiles");
+    if (passes == 3) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_pointwise_kernel<3><<<(unsigned)tiles, 128, smem, st>>>(tmap, p);
+    } else {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_pointwise_kernel<1><<<(unsigned)tiles, 128, smem, st>>>(tmap, p);
+    }
+    SB_LAUNCH_CHECK();
+    *handled = 1;
+    return 0;
+}

@@ -9,7 +9,3 @@ int sb200_tc_rowdft_fwd(sb200_plan_t, int, const float*, float*, int64_t, cudaSt
     *handled = 0;
     return 0;
 }
-int sb200_tc_rowidft_pointwise(sb200_plan_t, int, const PwParams&, cudaStream_t, int* handled) {
-    *handled = 0;
-    return 0;
-}

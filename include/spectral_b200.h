@@ -39,6 +39,12 @@ const char* sb200_last_error(void);
 /* compute capability major*10+minor of the current device, or <0 when no device */
 int sb200_device_arch(void);
 
+/* Tensor-core mode of the GEMM-shaped stages: 0 = CUDA-core (exact fp32 FFMA) kernels only,
+ * 1 = tcgen05 kind::tf32 single pass (parity ~1e-3), 3 = tcgen05 3xTF32 split (parity <= 1e-5; default).
+ * Shapes the tcgen05 kernels do not cover always run on the CUDA-core kernels. Process-global. */
+int sb200_set_tc_mode(int mode);
+int sb200_get_tc_mode(void);
+
 /* ---- plans ---------------------------------------------------------------------------
  * Retained block: rows ky = (ky0 + j) mod H, j in [0,My); cols kx in [0,Mx).
  * FNO (neuralop SpectralConv.forward, fftshift-era slicing): ky0 = lo - H/2, norm "forward"
