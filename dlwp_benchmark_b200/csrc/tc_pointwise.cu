@@ -13,6 +13,7 @@
 // (hi*hi + lo*hi + hi*lo): error ~2^-21, inside the 1e-5 parity bar.  PASSES = 1 is the plain TF32
 // path (parity ~1e-3, the north_star's "tensor-core path" tolerance).
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -74,6 +75,7 @@ struct TcPwParams {
     int64_t HW;
     int mode, apply_act;
     uint32_t idesc, tmem_cols;
+    int debug;
 };
 
 template <int PASSES>
@@ -108,6 +110,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         tc::fence_barrier_init();
     }
     if (warp == 0) {
+        __syncwarp();
         tc::tmem_alloc(tmem_slot, p.tmem_cols);
         tc::tmem_relinquish();
     }
@@ -148,7 +151,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         tc::fence_proxy_async_smem();
         __syncthreads();
         // ---- MMA issue (one thread) ----
-        if (tid == 0) {
+        if (tid == 0 && p.debug != 1 && p.debug != 2) {
             tc::tc_fence_after_sync();
             const uint32_t a_lbo = (uint32_t)KC * 128;
             for (int ks = 0; ks < KC / 8; ++ks) {
@@ -166,6 +169,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             }
             tc::umma_commit(mma_bar);
         }
+        if (p.debug == 1 || p.debug == 2) break;
         tc::mbar_wait(mma_bar, it & 1);     // smem operands free again, accumulator complete for this chunk
         tc::tc_fence_after_sync();
     }
@@ -183,6 +187,14 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 const int n = c0 + j;
                 if (n < p.N) {
                     float v = __uint_as_float(r[j]);
+                    if (p.debug == 1) {            // dump the TMA-loaded activation tile: y[b,n,px] = A_smem(k=n, px)
+                        const int px = warp * 32 + lane;
+                        v = n < KC ? *reinterpret_cast<const float*>(A_hi + (uint32_t)(px >> 5) * KC * 128 + n * 128 +
+                                                                   ((((px & 31) >> 2) ^ (n & 7)) << 4) + ((px & 3) << 2)) : 0.f;
+                    } else if (p.debug == 2) {     // dump the staged weight tile: y[b,n,px] = B_smem(n, k = px % KC)
+                        const int k = (warp * 32 + lane) % KC;
+                        v = *reinterpret_cast<const float*>(B_hi + (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31));
+                    }
                     const int64_t off = ((int64_t)b * p.N + n) * p.HW + pp;
                     if (p.bias) v += __ldg(p.bias + n);
                     if (p.mode == 0) {
@@ -224,6 +236,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     uint32_t cols = 32;
     while (cols < (uint32_t)N) cols <<= 1;
     p.tmem_cols = cols;
+    { const char* e = getenv("SB200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
     CUtensorMap tmap;
     if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 1))
