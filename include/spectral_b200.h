@@ -45,6 +45,12 @@ int sb200_device_arch(void);
 int sb200_set_tc_mode(int mode);
 int sb200_get_tc_mode(void);
 
+/* Bring-up self-test of the tcgen05 path: D[128,N] = A[128,K] * B[N,K]^T (tf32, single pass) with A staged
+ * K-major (a_layout 0) or MN-major (1; 2 = MN-major with LBO/SBO swapped) in 128B-swizzled shared memory.
+ * info[0..5] receives the TMEM base address, the instruction descriptor and the first A/B descriptors. */
+int sb200_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_layout, int use_mask,
+                      uint32_t* info, void* stream);
+
 /* ---- plans ---------------------------------------------------------------------------
  * Retained block: rows ky = (ky0 + j) mod H, j in [0,My); cols kx in [0,Mx).
  * FNO (neuralop SpectralConv.forward, fftshift-era slicing): ky0 = lo - H/2, norm "forward"
