@@ -120,7 +120,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)(layout & 7) << 61;
     return d;
 }
-constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6;
+constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6;
 
 // instruction descriptor, kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b format TF32(2) [7,10)/[10,13),
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
@@ -135,10 +135,19 @@ __device__ __forceinline__ uint32_t sw128_kmajor_off(int row, int k /* 0..31 */)
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
+// byte offset of element (mn, k) inside an MN-major tile of 32-bit elements in the SWIZZLE_128B_BASE32B layout
+// (the only MN-major layout tcgen05 accepts for tf32; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// rows = k (128 B = 32 mn elements each), 4-row atoms of 512 B, 32-byte chunk index XOR (k % 4);
+// 32-element mn blocks are `mn_block_stride` bytes apart.  Tile base must be 512-byte aligned.
+__device__ __forceinline__ uint32_t sw128b32_mnmajor_off(int mn, int k, uint32_t mn_block_stride) {
+    return (uint32_t)(mn >> 5) * mn_block_stride + (uint32_t)k * 128u + (uint32_t)(((((mn & 31) >> 3) ^ (k & 3)) & 3) << 5) +
+           (uint32_t)((mn & 7) << 2);
+}
+
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 }  // namespace tc
 
 // host side: build a 2-D tiled tensor map (fp32) through the driver entry point (no -lcuda needed)
 int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
-                           uint32_t box0, uint32_t box1, int swizzle128);
+                           uint32_t box0, uint32_t box1, int swizzle /* 0 none, 1 = 128B, 2 = 128B with 32B atoms */);

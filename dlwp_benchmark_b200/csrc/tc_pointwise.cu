@@ -3,7 +3,8 @@
 //   D[p, n] = sum_m A[b, m, p] * Wp[n, m]                   p = 128 pixels of one sample (UMMA M = 128)
 //                                                           n = all output channels        (UMMA N <= 256)
 // A tile:  TMA (cp.async.bulk.tensor.2d, 128B swizzle) straight from the NCHW activation viewed as
-//          [B*M, H*W]: four boxes {32 px, KC channels} = the canonical MN-major SWIZZLE_128B operand.
+//          [B*M, H*W]: four boxes {32 px, KC channels} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B = the MN-major
+//          SWIZZLE_128B_BASE32B operand layout (the only MN-major layout tcgen05 accepts for 32-bit types).
 // B tile:  the (tiny) weight matrix, written by the CTA's threads in the K-major SWIZZLE_128B layout.
 // D:       fp32 accumulator in TMEM; epilogue reads it with tcgen05.ld (lane = pixel), adds bias,
 //          applies GELU / GELU' and stores coalesced along the pixel dimension.
@@ -38,7 +39,7 @@ static void load_encode() {
 }
 
 int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
-                           uint32_t box0, uint32_t box1, int swizzle128) {
+                           uint32_t box0, uint32_t box1, int swizzle) {
     std::call_once(g_encode_once, load_encode);
     SB_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {dim0, dim1};
@@ -47,7 +48,8 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (dims %llu x %llu, box %u x %u)", (int)r,
                (unsigned long long)dim0, (unsigned long long)dim1, box0, box1);
@@ -157,11 +159,11 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             for (int ks = 0; ks < KC / 8; ++ks) {
                 const uint32_t a_off = (uint32_t)ks * 1024;
                 const uint32_t b_off = (uint32_t)(ks >> 2) * b_chunk_bytes + (uint32_t)(ks & 3) * 32;
-                const uint64_t ah = tc::make_smem_desc(tc::smem_u32(A_hi) + a_off, a_lbo, 1024, tc::LAYOUT_SW128);
+                const uint64_t ah = tc::make_smem_desc(tc::smem_u32(A_hi) + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
                 const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
                 tc::umma_tf32(tmem_d, ah, bh, p.idesc, (m0 > 0 || ks > 0) ? 1u : 0u);
                 if (PASSES == 3) {
-                    const uint64_t al = tc::make_smem_desc(tc::smem_u32(A_lo) + a_off, a_lbo, 1024, tc::LAYOUT_SW128);
+                    const uint64_t al = tc::make_smem_desc(tc::smem_u32(A_lo) + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
                     const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
                     tc::umma_tf32(tmem_d, al, bh, p.idesc, 1u);
                     tc::umma_tf32(tmem_d, ah, bl, p.idesc, 1u);
@@ -189,8 +191,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     float v = __uint_as_float(r[j]);
                     if (p.debug == 1) {            // dump the TMA-loaded activation tile: y[b,n,px] = A_smem(k=n, px)
                         const int px = warp * 32 + lane;
-                        v = n < KC ? *reinterpret_cast<const float*>(A_hi + (uint32_t)(px >> 5) * KC * 128 + n * 128 +
-                                                                   ((((px & 31) >> 2) ^ (n & 7)) << 4) + ((px & 3) << 2)) : 0.f;
+                        v = n < KC ? *reinterpret_cast<const float*>(A_hi + tc::sw128b32_mnmajor_off(px, n, (uint32_t)KC * 128u)) : 0.f;
                     } else if (p.debug == 2) {     // dump the staged weight tile: y[b,n,px] = B_smem(n, k = px % KC)
                         const int k = (warp * 32 + lane) % KC;
                         v = *reinterpret_cast<const float*>(B_hi + (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31));
@@ -239,7 +240,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     { const char* e = getenv("SB200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
     CUtensorMap tmap;
-    if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 1))
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2))
         return rc;
 
     const int passes = g_tc_mode;

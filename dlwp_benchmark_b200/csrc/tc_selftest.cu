@@ -8,7 +8,7 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
                    int a_layout, int use_mask, uint32_t* __restrict__ info) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = 128u * K * 4;
+    const uint32_t a_bytes = (uint32_t)((K + 31) / 32) * 128u * 128u;   // K-major rows are 128 B wide even when K < 32
     uint8_t* As = base;
     uint8_t* Bs = As + ((a_bytes + 1023) & ~1023u);
     const uint32_t b_chunk = (uint32_t)N * 128;
@@ -22,7 +22,7 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
         const float v = Ag[idx];
         uint32_t off;
         if (a_layout == 0) off = (uint32_t)(k >> 5) * (128u * 128u) + tc::sw128_kmajor_off(m, k & 31);
-        else off = (uint32_t)(m >> 5) * (uint32_t)K * 128u + (uint32_t)k * 128u + (((((m & 31) >> 2) ^ (k & 7)) & 7) << 4) + ((m & 3) << 2);
+        else off = tc::sw128b32_mnmajor_off(m, k, (uint32_t)K * 128u);
         *reinterpret_cast<float*>(As + off) = v;
     }
     for (int idx = tid; idx < N * K; idx += 128) {
@@ -54,9 +54,9 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
             if (a_layout == 0)
                 ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)(ks >> 2) * (128u * 128u) + (uint32_t)(ks & 3) * 32, 16, 1024, tc::LAYOUT_SW128);
             else if (a_layout == 1)
-                ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, (uint32_t)K * 128, 1024, tc::LAYOUT_SW128);
+                ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, (uint32_t)K * 128, 512, tc::LAYOUT_SW128_BASE32B);
             else
-                ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, 1024, (uint32_t)K * 128, tc::LAYOUT_SW128);
+                ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, 512, (uint32_t)K * 128, tc::LAYOUT_SW128_BASE32B);
             const uint64_t bd = tc::make_smem_desc(tc::smem_u32(Bs) + (uint32_t)(ks >> 2) * b_chunk + (uint32_t)(ks & 3) * 32, 16, 1024, tc::LAYOUT_SW128);
             if (ks == 0) { info[2] = (uint32_t)ad; info[3] = (uint32_t)(ad >> 32); info[4] = (uint32_t)bd; info[5] = (uint32_t)(bd >> 32); }
             if (use_mask) {
@@ -89,7 +89,7 @@ extern "C" int sb200_tc_selftest(const float* A, const float* B, float* D, int N
                                  uint32_t* info, void* stream) {
     SB_REQUIRE(A && B && D && info, "tc_selftest: NULL argument");
     SB_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && K <= 128, "tc_selftest: bad N/K");
-    const size_t smem = 1024 + ((128 * (size_t)K * 4 + 1023) & ~(size_t)1023) +
+    const size_t smem = 1024 + (size_t)((K + 31) / 32) * 128 * 128 +
                         (((size_t)((K + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) + 64;
     SB_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, a_layout, use_mask, info);
