@@ -65,50 +65,66 @@ extern "C" int sb200_set_tc_mode(int mode) {
 extern "C" int sb200_get_tc_mode(void) { return g_tc_mode; }
 
 // ---------------------------------------------------------------------------------------------
-// kernel
+// kernel: persistent, warp-specialised
+//   warp 0     TMA producer (one lane)           activation tiles -> smem ring
+//   warp 1     MMA issuer (one lane)             tcgen05.mma into a double-buffered TMEM accumulator
+//   warps 2-9  workers: (a) split a landed tile into tf32 hi/lo parts (3xTF32 only),
+//              (b) epilogue: TMEM -> registers -> bias / GELU / GELU' -> global
+// The workers split the NEXT tile before running the epilogue of the current one, so the MMAs of
+// tile t+1 execute while tile t is being written out; TMA loads run ahead by the ring depth.
 // ---------------------------------------------------------------------------------------------
 constexpr int TP_PX = 128;
+constexpr int TP_WORKER_WARPS = 8;
+constexpr int TP_THREADS = 32 * (2 + TP_WORKER_WARPS);
 
 struct TcPwParams {
     const float* Wp; int64_t w_sn, w_sm;
     const float* bias; const float* zprev;
     float* z_out; float* y_out;
-    int B, M, N, KC;
+    int B, M, N, KC, nkc, stages;
     int64_t HW;
+    int64_t ntiles;
     int mode, apply_act;
     uint32_t idesc, tmem_cols;
-    int debug;
 };
 
 template <int PASSES>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve (all 1024-byte aligned): A_hi | A_lo | B_hi | B_lo | barriers
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int KC = p.KC;
+    const int KC = p.KC, nkc = p.nkc, S = p.stages;
     const uint32_t a_bytes = (uint32_t)KC * 512;                       // 4 boxes x KC rows x 128 B
-    const int nchunk = (KC + 31) / 32;
+    const uint32_t a_stage_bytes = a_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
+    const int kchunks = (p.M + 31) / 32;                               // 32-wide K chunks of the resident weight tile
     const uint32_t b_chunk_bytes = (uint32_t)p.N * 128;                // N rows x 128 B
-    const uint32_t b_bytes = (uint32_t)nchunk * b_chunk_bytes;
-    uint8_t* A_hi = base;
-    uint8_t* A_lo = A_hi + a_bytes;
-    uint8_t* B_hi = A_lo + (PASSES == 3 ? a_bytes : 0);
-    uint8_t* B_lo = B_hi + ((b_bytes + 1023) & ~1023u);
-    uint8_t* tail = B_lo + (PASSES == 3 ? ((b_bytes + 1023) & ~1023u) : 0);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* mma_bar = full_bar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    const uint32_t b_bytes = ((uint32_t)kchunks * b_chunk_bytes + 1023) & ~1023u;
+    uint8_t* B_hi = base;
+    uint8_t* B_lo = B_hi + b_bytes;
+    uint8_t* A_st = B_lo + (PASSES == 3 ? b_bytes : 0);
+    uint8_t* tail = A_st + (uint32_t)S * a_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);           // [S]  TMA landed
+    uint64_t* split_bar = full_bar + S;                                // [S]  hi/lo split done (workers -> MMA)
+    uint64_t* empty_bar = split_bar + S;                               // [S]  MMAs that read the stage are done
+    uint64_t* tfull_bar = empty_bar + S;                               // [2]  accumulator complete
+    uint64_t* tempty_bar = tfull_bar + 2;                              // [2]  accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_per_b = (int)((p.HW + TP_PX - 1) / TP_PX);
-    const int b = blockIdx.x / tiles_per_b;
-    const int64_t p_base = (int64_t)(blockIdx.x % tiles_per_b) * TP_PX;
 
+    // ---- one-time setup ----
     if (tid == 0) {
         tc::tma_prefetch_desc(&tmapA);
-        tc::mbar_init(full_bar, 1);
-        tc::mbar_init(mma_bar, 1);
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(full_bar + s, 1);
+            tc::mbar_init(split_bar + s, TP_WORKER_WARPS);
+            tc::mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(tfull_bar + a, 1);
+            tc::mbar_init(tempty_bar + a, TP_WORKER_WARPS);
+        }
         tc::fence_barrier_init();
     }
     if (warp == 0) {
@@ -116,107 +132,162 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         tc::tmem_alloc(tmem_slot, p.tmem_cols);
         tc::tmem_relinquish();
     }
+    // resident weight tile: Wp[n, m] -> K-major 128B-swizzled rows, split into tf32 hi / lo
+    for (int idx = tid; idx < p.N * p.M; idx += TP_THREADS) {
+        const int n = idx / p.M, k = idx % p.M;
+        const float w = __ldg(p.Wp + (int64_t)n * p.w_sn + (int64_t)k * p.w_sm);
+        const float hi = tc::tf32_trunc(w);
+        const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
+        *reinterpret_cast<float*>(B_hi + off) = hi;
+        if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
+    }
+    tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
-    uint32_t it = 0;
-    for (int m0 = 0; m0 < p.M; m0 += KC, ++it) {
-        // ---- producer: TMA the activation tile (async), threads stage the weight chunk meanwhile ----
-        if (tid == 0) {
-            tc::mbar_expect_tx(full_bar, a_bytes);
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t my_tiles = first < p.ntiles ? (p.ntiles - first + stride - 1) / stride : 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int64_t q = 0;
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const int64_t tile = first + it * stride;
+                const int b = (int)(tile / tiles_per_b);
+                const int64_t p_base = (tile % tiles_per_b) * TP_PX;
+                for (int kc = 0; kc < nkc; ++kc, ++q) {
+                    const int s = (int)(q % S);
+                    const uint32_t round = (uint32_t)(q / S);
+                    tc::mbar_wait(empty_bar + s, (round & 1) ^ 1);
+                    uint8_t* dst = A_st + (uint32_t)s * a_stage_bytes;
+                    tc::mbar_expect_tx(full_bar + s, a_bytes);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                tc::tma_load_2d(A_hi + (uint32_t)i * KC * 128, &tmapA, (int)(p_base + 32 * i), b * p.M + m0, full_bar);
-        }
-        for (int idx = tid; idx < p.N * KC; idx += 128) {
-            const int n = idx / KC, k = idx % KC;
-            const float w = __ldg(p.Wp + (int64_t)n * p.w_sn + (int64_t)(m0 + k) * p.w_sm);
-            const float hi = tc::tf32_trunc(w);
-            const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
-            *reinterpret_cast<float*>(B_hi + off) = hi;
-            if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
-        }
-        tc::mbar_wait(full_bar, it & 1);
-        if (PASSES == 3) {
-            // split the activation tile in place: hi = tf32 part, lo = remainder (layout-agnostic, element-wise)
-            float4* ah = reinterpret_cast<float4*>(A_hi);
-            float4* al = reinterpret_cast<float4*>(A_lo);
-            for (int idx = tid; idx < (int)(a_bytes / 16); idx += 128) {
-                float4 v = ah[idx];
-                float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
-                ah[idx] = h;
-                al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    for (int i = 0; i < 4; ++i)
+                        tc::tma_load_2d(dst + (uint32_t)i * KC * 128, &tmapA, (int)(p_base + 32 * i), b * p.M + kc * KC,
+                                        full_bar + s);
+                }
             }
         }
-        tc::fence_proxy_async_smem();
-        __syncthreads();
-        // ---- MMA issue (one thread) ----
-        if (tid == 0 && p.debug != 1 && p.debug != 2) {
-            tc::tc_fence_after_sync();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int64_t q = 0;
             const uint32_t a_lbo = (uint32_t)KC * 128;
-            for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint32_t a_off = (uint32_t)ks * 1024;
-                const uint32_t b_off = (uint32_t)(ks >> 2) * b_chunk_bytes + (uint32_t)(ks & 3) * 32;
-                const uint64_t ah = tc::make_smem_desc(tc::smem_u32(A_hi) + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
-                const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
-                tc::umma_tf32(tmem_d, ah, bh, p.idesc, (m0 > 0 || ks > 0) ? 1u : 0u);
-                if (PASSES == 3) {
-                    const uint64_t al = tc::make_smem_desc(tc::smem_u32(A_lo) + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
-                    const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
-                    tc::umma_tf32(tmem_d, al, bh, p.idesc, 1u);
-                    tc::umma_tf32(tmem_d, ah, bl, p.idesc, 1u);
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const int a = (int)(it & 1);
+                const uint32_t tround = (uint32_t)(it >> 1);
+                tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
+                tc::tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + (uint32_t)a * (uint32_t)p.N;
+                for (int kc = 0; kc < nkc; ++kc, ++q) {
+                    const int s = (int)(q % S);
+                    const uint32_t round = (uint32_t)(q / S);
+                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, round & 1);
+                    tc::tc_fence_after_sync();
+                    const uint32_t A_hi = tc::smem_u32(A_st + (uint32_t)s * a_stage_bytes);
+                    const uint32_t A_lo = A_hi + a_bytes;
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const int kg = kc * KC + ks * 8;                         // global k of this step
+                        const uint32_t a_off = (uint32_t)ks * 1024;
+                        const uint32_t b_off = (uint32_t)(kg >> 5) * b_chunk_bytes + (uint32_t)((kg & 31) >> 3) * 32;
+                        const uint64_t ah = tc::make_smem_desc(A_hi + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
+                        const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
+                        tc::umma_tf32(tmem_d, ah, bh, p.idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        if (PASSES == 3) {
+                            const uint64_t al = tc::make_smem_desc(A_lo + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
+                            const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
+                            tc::umma_tf32(tmem_d, al, bh, p.idesc, 1u);
+                            tc::umma_tf32(tmem_d, ah, bl, p.idesc, 1u);
+                        }
+                    }
+                    tc::umma_commit(empty_bar + s);            // stage reusable once these MMAs have read it
                 }
+                tc::umma_commit(tfull_bar + a);                // accumulator of this tile complete
             }
-            tc::umma_commit(mma_bar);
         }
-        if (p.debug == 1 || p.debug == 2) break;
-        tc::mbar_wait(mma_bar, it & 1);     // smem operands free again, accumulator complete for this chunk
-        tc::tc_fence_after_sync();
-    }
+    } else {
+        // ================= workers: split (tile t+1) then epilogue (tile t) =================
+        const int wk = warp - 2;                               // 0..7
+        const int wtid = tid - 64;                             // 0..255
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        const int chalf = wk >> 2;                             // which half of the columns this warp drains
+        const int ncol_half = (p.N + 1) / 2;
+        int64_t q_split = 0;
 
-    // ---- epilogue: TMEM -> registers -> global (lane = pixel, coalesced along pixels) ----
-    const int64_t pp = p_base + warp * 32 + lane;
-    const bool in_range = pp < p.HW;
-    for (int c0 = 0; c0 < p.N; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-        tc::tmem_ld_wait();
-        if (in_range) {
+        auto split_tile_items = [&](int64_t /*it*/) {
+            for (int kc = 0; kc < nkc; ++kc, ++q_split) {
+                const int s = (int)(q_split % S);
+                const uint32_t round = (uint32_t)(q_split / S);
+                tc::mbar_wait(full_bar + s, round & 1);
+                float4* ah = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes);
+                float4* al = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes + a_bytes);
+                for (int idx = wtid; idx < (int)(a_bytes / 16); idx += 32 * TP_WORKER_WARPS) {
+                    const float4 v = ah[idx];
+                    const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                    ah[idx] = h;
+                    al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(split_bar + s);
+            }
+        };
+
+        if (PASSES == 3 && my_tiles > 0) split_tile_items(0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            if (PASSES == 3 && it + 1 < my_tiles) split_tile_items(it + 1);
+            const int64_t tile = first + it * stride;
+            const int b = (int)(tile / tiles_per_b);
+            const int64_t p_base = (tile % tiles_per_b) * TP_PX;
+            const int a = (int)(it & 1);
+            const uint32_t tround = (uint32_t)(it >> 1);
+            tc::mbar_wait(tfull_bar + a, tround & 1);
+            tc::tc_fence_after_sync();
+            const int64_t pp = p_base + quarter * 32 + lane;
+            const bool in_range = pp < p.HW;
+            const int c_begin = chalf * ncol_half;
+            const int c_end = min(p.N, c_begin + ncol_half);
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N + c0), r);
+                tc::tmem_ld_wait();
+                if (in_range) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = c0 + j;
-                if (n < p.N) {
-                    float v = __uint_as_float(r[j]);
-                    if (p.debug == 1) {            // dump the TMA-loaded activation tile: y[b,n,px] = A_smem(k=n, px)
-                        const int px = warp * 32 + lane;
-                        v = n < KC ? *reinterpret_cast<const float*>(A_hi + tc::sw128b32_mnmajor_off(px, n, (uint32_t)KC * 128u)) : 0.f;
-                    } else if (p.debug == 2) {     // dump the staged weight tile: y[b,n,px] = B_smem(n, k = px % KC)
-                        const int k = (warp * 32 + lane) % KC;
-                        v = *reinterpret_cast<const float*>(B_hi + (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31));
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = c0 + j;
+                        if (n < c_end) {
+                            float v = __uint_as_float(r[j]);
+                            const int64_t off = ((int64_t)b * p.N + n) * p.HW + pp;
+                            if (p.bias) v += __ldg(p.bias + n);
+                            if (p.mode == 0) {
+                                if (p.z_out) p.z_out[off] = v;
+                                if (p.apply_act) v = gelu_f(v);
+                            } else if (p.zprev) {
+                                v *= gelu_grad_f(__ldg(p.zprev + off));
+                            }
+                            p.y_out[off] = v;
+                        }
                     }
-                    const int64_t off = ((int64_t)b * p.N + n) * p.HW + pp;
-                    if (p.bias) v += __ldg(p.bias + n);
-                    if (p.mode == 0) {
-                        if (p.z_out) p.z_out[off] = v;
-                        if (p.apply_act) v = gelu_f(v);
-                    } else if (p.zprev) {
-                        v *= gelu_grad_f(__ldg(p.zprev + off));
-                    }
-                    p.y_out[off] = v;
                 }
             }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty_bar + a);
         }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_d, p.tmem_cols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
 // dispatch (called from sb200_rowidft_pointwise)
 // ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
 int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, cudaStream_t st, int* handled) {
     *handled = 0;
     (void)plan; (void)pass;
@@ -228,34 +299,43 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     if (N % 16 != 0 || N < 16 || N > 256) return 0;
     if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(q.A) & 15) != 0) return 0;
     if ((int64_t)q.B * M >= (1LL << 31)) return 0;
+    const int passes = g_tc_mode;
 
     TcPwParams p;
     p.Wp = q.Wp; p.w_sn = q.w_sn; p.w_sm = q.w_sm; p.bias = q.bias; p.zprev = q.zprev;
     p.z_out = q.z_out; p.y_out = q.y_out; p.B = q.B; p.M = M; p.N = N; p.KC = M < 64 ? M : 64; p.HW = HW;
+    p.nkc = M / p.KC;
     p.mode = q.mode; p.apply_act = q.apply_act;
     p.idesc = tc::make_idesc_tf32(128, N, /*A MN-major*/ 1, /*B K-major*/ 0);
     uint32_t cols = 32;
-    while (cols < (uint32_t)N) cols <<= 1;
+    while (cols < (uint32_t)(2 * N)) cols <<= 1;
     p.tmem_cols = cols;
-    { const char* e = getenv("SB200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.ntiles = (HW + TP_PX - 1) / TP_PX * q.B;
+
+    const size_t a_stage = (size_t)p.KC * 512 * (passes == 3 ? 2 : 1);
+    const size_t b_bytes = (((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * (passes == 3 ? 2 : 1);
+    const size_t fixed = 1024 + b_bytes + 256;
+    int stages = 4;
+    while (stages > 1 && fixed + stages * a_stage > 200 * 1024) --stages;
+    if (fixed + stages * a_stage > 227 * 1024) return 0;               // does not fit: CUDA-core kernel
+    p.stages = stages;
+    const size_t smem = fixed + stages * a_stage;
 
     CUtensorMap tmap;
     if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2))
         return rc;
-
-    const int passes = g_tc_mode;
-    const size_t a_bytes = (size_t)p.KC * 512;
-    const size_t b_bytes = ((size_t)((p.KC + 31) / 32) * N * 128 + 1023) & ~(size_t)1023;
-    const size_t smem = 1024 + a_bytes * (passes == 3 ? 2 : 1) + b_bytes * (passes == 3 ? 2 : 1) + 64;
-    SB_REQUIRE(smem <= 227 * 1024, "tc_pointwise: shared memory %zu too large", smem);
-    const int64_t tiles = (HW + TP_PX - 1) / TP_PX * q.B;
-    SB_REQUIRE(tiles < (1LL << 31), "tc_pointwise: too many tiles");
+    if (g_num_sms == 0) {
+        int dev = 0;
+        SB_CHECK_CUDA(cudaGetDevice(&dev));
+        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
     if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<3><<<(unsigned)tiles, 128, smem, st>>>(tmap, p);
+        tc_pointwise_kernel<3><<<grid, TP_THREADS, smem, st>>>(tmap, p);
     } else {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<1><<<(unsigned)tiles, 128, smem, st>>>(tmap, p);
+        tc_pointwise_kernel<1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
     }
     SB_LAUNCH_CHECK();
     *handled = 1;
