@@ -335,6 +335,8 @@ def run_b200(args, wl, rank, world, local_rank):
         roof = None
         log('e2e done; per-kernel rooflines')
         try:
+            if args.skip_roofline:
+                raise RuntimeError('skipped (--skip-roofline)')
             kr = kernel_rooflines(wl, peak)
             # launches per train step of each kernel on the spectral path (4 layers)
             L = wl["L"]
@@ -397,6 +399,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

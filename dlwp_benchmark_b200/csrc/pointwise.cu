@@ -323,10 +323,16 @@ static void wgrad_chunking(int B, int64_t HW, int64_t* chunk_px, int* chunks_per
     *chunks_per_b = (int)((HW + px - 1) / px);
 }
 
+int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);                                    // tc_wgrad.cu
+int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
+                             int64_t HW, float* workspace, cudaStream_t st, int* handled);
+
 extern "C" int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
     int64_t px; int cpb;
     wgrad_chunking(B, HW, &px, &cpb);
-    return (int64_t)B * cpb * ((int64_t)Cout * Cin + Cout);
+    const int64_t a = (int64_t)B * cpb * ((int64_t)Cout * Cin + Cout);
+    const int64_t b = sb200_tc_wgrad_workspace(B, Cout, Cin, HW);
+    return a > b ? a : b;
 }
 
 extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
@@ -335,6 +341,9 @@ extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, 
     SB_REQUIRE(HW % 4 == 0, "pointwise_wgrad: H*W=%lld must be a multiple of 4", (long long)HW);
     if (B <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    int handled = 0;
+    if (int rc = sb200_tc_pointwise_wgrad(g, x, gW, gbias, B, Cout, Cin, HW, workspace, st, &handled)) return rc;
+    if (handled) return 0;
     int64_t px; int cpb;
     wgrad_chunking(B, HW, &px, &cpb);
     const int nchunks = B * cpb;

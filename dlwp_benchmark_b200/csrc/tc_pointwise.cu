@@ -68,13 +68,13 @@ extern "C" int sb200_get_tc_mode(void) { return g_tc_mode; }
 // kernel: persistent, warp-specialised
 //   warp 0     TMA producer (one lane)           activation tiles -> smem ring
 //   warp 1     MMA issuer (one lane)             tcgen05.mma into a double-buffered TMEM accumulator
-//   warps 2-9  workers: (a) split a landed tile into tf32 hi/lo parts (3xTF32 only),
+//   warps 2-17 workers: (a) split a landed tile into tf32 hi/lo parts (3xTF32 only),
 //              (b) epilogue: TMEM -> registers -> bias / GELU / GELU' -> global
 // The workers split the NEXT tile before running the epilogue of the current one, so the MMAs of
 // tile t+1 execute while tile t is being written out; TMA loads run ahead by the ring depth.
 // ---------------------------------------------------------------------------------------------
 constexpr int TP_PX = 128;
-constexpr int TP_WORKER_WARPS = 8;
+constexpr int TP_WORKER_WARPS = 16;
 constexpr int TP_THREADS = 32 * (2 + TP_WORKER_WARPS);
 
 struct TcPwParams {
@@ -210,11 +210,11 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         }
     } else {
         // ================= workers: split (tile t+1) then epilogue (tile t) =================
-        const int wk = warp - 2;                               // 0..7
-        const int wtid = tid - 64;                             // 0..255
+        const int wk = warp - 2;                               // 0..15
+        const int wtid = tid - 64;                             // 0..511
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        const int chalf = wk >> 2;                             // which half of the columns this warp drains
-        const int ncol_half = (p.N + 1) / 2;
+        const int cpart = wk >> 2;                             // which quarter of the columns this warp drains
+        const int ncol_part = ((p.N + 3) / 4 + 3) & ~3;        // columns per part (multiple of 4)
         int64_t q_split = 0;
 
         auto split_tile_items = [&](int64_t /*it*/) {
@@ -248,25 +248,32 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             tc::tc_fence_after_sync();
             const int64_t pp = p_base + quarter * 32 + lane;
             const bool in_range = pp < p.HW;
-            const int c_begin = chalf * ncol_half;
-            const int c_end = min(p.N, c_begin + ncol_half);
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N + c0), r);
+            const int c_begin = cpart * ncol_part;
+            const int c_end = min(p.N, c_begin + ncol_part);
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t r[16];
+                float zp[16], bv[16];
+                const int64_t off0 = ((int64_t)b * p.N + c0) * p.HW + pp;
+                // issue every global load of this chunk before touching TMEM (independent loads in flight)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const bool ok = in_range && (c0 + j < c_end);
+                    zp[j] = (ok && p.mode == 1 && p.zprev) ? __ldg(p.zprev + off0 + (int64_t)j * p.HW) : 0.f;
+                    bv[j] = (ok && p.bias) ? __ldg(p.bias + c0 + j) : 0.f;
+                }
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N + c0), r);
                 tc::tmem_ld_wait();
                 if (in_range) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = c0 + j;
-                        if (n < c_end) {
-                            float v = __uint_as_float(r[j]);
-                            const int64_t off = ((int64_t)b * p.N + n) * p.HW + pp;
-                            if (p.bias) v += __ldg(p.bias + n);
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < c_end) {
+                            float v = __uint_as_float(r[j]) + bv[j];
+                            const int64_t off = off0 + (int64_t)j * p.HW;
                             if (p.mode == 0) {
                                 if (p.z_out) p.z_out[off] = v;
                                 if (p.apply_act) v = gelu_f(v);
                             } else if (p.zprev) {
-                                v *= gelu_grad_f(__ldg(p.zprev + off));
+                                v *= gelu_grad_f(zp[j]);
                             }
                             p.y_out[off] = v;
                         }

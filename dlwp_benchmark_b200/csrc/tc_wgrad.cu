@@ -1,0 +1,304 @@
+// tcgen05 weight gradient of the pointwise (1x1) channel mix:
+//       gW[o, i] = sum_{b,p} g[b, o, p] * x[b, i, p]
+// Both operands are K-major as they lie in memory (the contraction index, the pixel, is the contiguous
+// one), so TMA boxes {32 px, C channels} with the plain 128B swizzle are the UMMA operands directly.
+//   A rows = channels of the tensor with more channels ("P"), 128 per M-block,
+//   B rows = channels of the other tensor ("Q", UMMA N),  K = pixels, 8 per tcgen05.mma (tf32).
+// Each persistent CTA owns a contiguous range of pixel chunks, accumulates its partial product in TMEM
+// over the whole range and writes it to the workspace once; a second kernel reduces the partials
+// in a fixed order (deterministic).  3xTF32 operand split as in tc_pointwise.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+extern "C" int sb200_get_tc_mode(void);
+
+constexpr int TW_WORKER_WARPS = 16;
+constexpr int TW_THREADS = 32 * (2 + TW_WORKER_WARPS);
+
+struct TcWgParams {
+    int Pc, Qc;              // channels of the A-side / B-side tensors
+    int mblocks;             // ceil(Pc / 128)
+    int CH;                  // 32-pixel chunks per pipeline item
+    int stages;
+    int64_t HW;
+    int64_t items_per_b, nitems;
+    float* ws;               // [grid][mblocks*128][Qc]
+    uint32_t idesc, tmem_cols;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(TW_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapQ, const TcWgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = p.stages, CH = p.CH;
+    const uint32_t p_chunk = (uint32_t)p.Pc * 128, q_chunk = (uint32_t)p.Qc * 128;
+    const uint32_t chunk_bytes = p_chunk + q_chunk;                    // [P rows | Q rows], 128 B per row
+    const uint32_t raw_bytes = (uint32_t)CH * chunk_bytes;
+    const uint32_t stage_bytes = raw_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
+    uint8_t* St = base;
+    uint8_t* tail = St + (uint32_t)S * stage_bytes + 16384;            // slack: a short last M-block reads past its rows
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* split_bar = full_bar + S;
+    uint64_t* empty_bar = split_bar + S;
+    uint64_t* done_bar = empty_bar + S;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmapP);
+        tc::tma_prefetch_desc(&tmapQ);
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(full_bar + s, 1);
+            tc::mbar_init(split_bar + s, TW_WORKER_WARPS);
+            tc::mbar_init(empty_bar + s, 1);
+        }
+        tc::mbar_init(done_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous item range of this CTA
+    const int64_t per = (p.nitems + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * per;
+    const int64_t i1 = i0 + per < p.nitems ? i0 + per : p.nitems;
+    const int64_t my_items = i1 > i0 ? i1 - i0 : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int64_t q = 0; q < my_items; ++q) {
+                const int64_t item = i0 + q;
+                const int b = (int)(item / p.items_per_b);
+                const int64_t px0 = (item % p.items_per_b) * 32 * CH;
+                const int s = (int)(q % S);
+                tc::mbar_wait(empty_bar + s, (((uint32_t)(q / S)) & 1) ^ 1);
+                uint8_t* dst = St + (uint32_t)s * stage_bytes;
+                tc::mbar_expect_tx(full_bar + s, raw_bytes);
+                for (int j = 0; j < CH; ++j) {
+                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes, &tmapP, (int)(px0 + 32 * j), b * p.Pc, full_bar + s);
+                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes + p_chunk, &tmapQ, (int)(px0 + 32 * j), b * p.Qc, full_bar + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int64_t q = 0; q < my_items; ++q) {
+                const int s = (int)(q % S);
+                tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ((uint32_t)(q / S)) & 1);
+                tc::tc_fence_after_sync();
+                const uint32_t hi = tc::smem_u32(St + (uint32_t)s * stage_bytes);
+                const uint32_t lo = hi + raw_bytes;
+                for (int j = 0; j < CH; ++j) {
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t qoff = (uint32_t)j * chunk_bytes + p_chunk + (uint32_t)ks * 32;
+                        const uint64_t bh = tc::make_smem_desc(hi + qoff, 16, 1024, tc::LAYOUT_SW128);
+                        const uint64_t bl = tc::make_smem_desc(lo + qoff, 16, 1024, tc::LAYOUT_SW128);
+                        const uint32_t acc = (q > 0 || j > 0 || ks > 0) ? 1u : 0u;
+                        for (int mb = 0; mb < p.mblocks; ++mb) {
+                            const uint32_t poff = (uint32_t)j * chunk_bytes + (uint32_t)mb * 128 * 128 + (uint32_t)ks * 32;
+                            const uint64_t ah = tc::make_smem_desc(hi + poff, 16, 1024, tc::LAYOUT_SW128);
+                            const uint32_t d = tmem_base + (uint32_t)mb * (uint32_t)p.Qc;
+                            tc::umma_tf32(d, ah, bh, p.idesc, acc);
+                            if (PASSES == 3) {
+                                const uint64_t al = tc::make_smem_desc(lo + poff, 16, 1024, tc::LAYOUT_SW128);
+                                tc::umma_tf32(d, al, bh, p.idesc, 1u);
+                                tc::umma_tf32(d, ah, bl, p.idesc, 1u);
+                            }
+                        }
+                    }
+                }
+                tc::umma_commit(empty_bar + s);
+            }
+            tc::umma_commit(done_bar);
+        }
+    } else {
+        const int wk = warp - 2;
+        const int wtid = tid - 64;
+        if (PASSES == 3) {
+            for (int64_t q = 0; q < my_items; ++q) {
+                const int s = (int)(q % S);
+                tc::mbar_wait(full_bar + s, ((uint32_t)(q / S)) & 1);
+                float4* ah = reinterpret_cast<float4*>(St + (uint32_t)s * stage_bytes);
+                float4* al = reinterpret_cast<float4*>(St + (uint32_t)s * stage_bytes + raw_bytes);
+                for (int idx = wtid; idx < (int)(raw_bytes / 16); idx += 32 * TW_WORKER_WARPS) {
+                    const float4 v = ah[idx];
+                    const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                    ah[idx] = h;
+                    al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(split_bar + s);
+            }
+        }
+        // ---- epilogue: partial product -> workspace (zeros when this CTA had no work) ----
+        if (my_items > 0) {
+            tc::mbar_wait(done_bar, 0);
+            tc::tc_fence_after_sync();
+        }
+        const int quarter = warp & 3;
+        const int cpart = wk >> 2;                                   // 4 column parts
+        const int ncol_part = ((p.Qc + 3) / 4 + 3) & ~3;
+        const int c_begin = cpart * ncol_part;
+        const int c_end = min(p.Qc, c_begin + ncol_part);
+        float* wsc = p.ws + (int64_t)blockIdx.x * p.mblocks * 128 * p.Qc;
+        for (int mb = 0; mb < p.mblocks; ++mb) {
+            const int row = mb * 128 + quarter * 32 + lane;
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t r[16];
+                if (my_items > 0) {
+                    tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * p.Qc + c0), r);
+                    tc::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+                if (row < p.Pc) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < c_end) wsc[(int64_t)row * p.Qc + c0 + j] = __uint_as_float(r[j]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// out[(transpose ? q*Pc + pch : pch*Qc + q)] = sum_c ws[c][pch][q]   (ws rows padded to mblocks*128)
+__global__ void __launch_bounds__(256)
+tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int Pc, int Qc, int prow_pad, int nparts,
+                       int transpose) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= (int64_t)Pc * Qc) return;
+    const int pch = (int)(e / Qc), q = (int)(e % Qc);
+    float s = 0.f;
+    const int64_t part = (int64_t)prow_pad * Qc;
+#pragma unroll 8
+    for (int c = 0; c < nparts; ++c) s += __ldg(ws + c * part + e);
+    out[transpose ? (int64_t)q * Pc + pch : e] = s;
+}
+
+// per-channel sums: out[c] = sum_{b,p} g[b,c,p]   (one warp per (b,c) row, then a fixed-order sum over b)
+__global__ void __launch_bounds__(256)
+channel_rowsum_kernel(const float* __restrict__ g, float* __restrict__ part, int64_t rows, int64_t HW) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(g + row * HW);
+    float s = 0.f;
+    for (int64_t i = lane; i < HW / 4; i += 32) {
+        const float4 v = __ldg(src + i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) part[row] = s;
+}
+__global__ void __launch_bounds__(256)
+channel_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int C) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += part[(int64_t)b * C + c];
+    out[c] = s;
+}
+
+static int g_tw_sms = 0;
+static int tw_num_sms() {
+    if (g_tw_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_tw_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            g_tw_sms = 148;
+        }
+    }
+    return g_tw_sms;
+}
+
+// shape eligibility + geometry, shared by the workspace query and the launcher
+static bool tw_geometry(int Cout, int Cin, int64_t HW, int* Pc, int* Qc, int* transpose) {
+    if (HW % 4 != 0) return false;
+    int P = Cout, Q = Cin, tr = 0;
+    if (Cin > Cout) { P = Cin; Q = Cout; tr = 1; }
+    if (Q % 16 != 0 || Q < 16 || Q > 256) return false;
+    if (P % 8 != 0 || P > 256) return false;
+    if (P % 128 != 0 && P > 128) return false;
+    const int mblocks = (P + 127) / 128;
+    if (mblocks * Q > 512) return false;
+    *Pc = P; *Qc = Q; *transpose = tr;
+    return true;
+}
+
+int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
+    int Pc, Qc, tr;
+    if (sb200_get_tc_mode() == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
+    const int mblocks = (Pc + 127) / 128;
+    return (int64_t)tw_num_sms() * mblocks * 128 * Qc + (int64_t)B * Cout;
+}
+
+int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
+                             int64_t HW, float* workspace, cudaStream_t st, int* handled) {
+    *handled = 0;
+    const int passes = sb200_get_tc_mode();
+    int Pc, Qc, tr;
+    if (passes == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return 0;
+    if ((int64_t)B * Pc >= (1LL << 31)) return 0;
+    const float* Pt = tr ? x : g;
+    const float* Qt = tr ? g : x;
+
+    TcWgParams p;
+    p.Pc = Pc; p.Qc = Qc; p.mblocks = (Pc + 127) / 128; p.HW = HW;
+    const size_t chunk = (size_t)(Pc + Qc) * 128;
+    p.CH = chunk <= 16384 ? 2 : 1;
+    const size_t stage = chunk * p.CH * (passes == 3 ? 2 : 1);
+    int stages = 4;
+    while (stages > 1 && 1024 + stages * stage + 16384 + 256 > 200 * 1024) --stages;
+    if (1024 + stages * stage + 16384 + 256 > 227 * 1024) return 0;
+    p.stages = stages;
+    const size_t smem = 1024 + stages * stage + 16384 + 256;
+    p.items_per_b = (HW + 32 * p.CH - 1) / (32 * p.CH);
+    p.nitems = p.items_per_b * B;
+    p.idesc = tc::make_idesc_tf32(128, Qc, 0, 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.mblocks * Qc)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.ws = workspace;
+    const int sms = tw_num_sms();
+    const unsigned grid = (unsigned)(p.nitems < sms ? p.nitems : sms);
+
+    CUtensorMap tmP, tmQ;
+    if (int rc = sb200_make_tmap_2d_f32(&tmP, Pt, (uint64_t)HW, (uint64_t)B * Pc, (uint64_t)HW * 4, 32, (uint32_t)Pc, 1)) return rc;
+    if (int rc = sb200_make_tmap_2d_f32(&tmQ, Qt, (uint64_t)HW, (uint64_t)B * Qc, (uint64_t)HW * 4, 32, (uint32_t)Qc, 1)) return rc;
+    if (passes == 3) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_wgrad_kernel<3><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+    } else {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_wgrad_kernel<1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+    }
+    SB_LAUNCH_CHECK();
+    const int64_t E = (int64_t)Pc * Qc;
+    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(workspace, gW, Pc, Qc, p.mblocks * 128, (int)grid, tr);
+    SB_LAUNCH_CHECK();
+    if (gbias) {
+        float* part = workspace + (int64_t)sms * p.mblocks * 128 * Qc;
+        const int64_t rows = (int64_t)B * Cout;
+        channel_rowsum_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(g, part, rows, HW);
+        SB_LAUNCH_CHECK();
+        channel_sum_final_kernel<<<(unsigned)((Cout + 255) / 256), 256, 0, st>>>(part, gbias, B, Cout);
+        SB_LAUNCH_CHECK();
+    }
+    *handled = 1;
+    return 0;
+}

@@ -331,3 +331,18 @@ def test_tc_mode_0_is_exact_fp32_path():
     finally:
         _set_tc(3)
     assert rel_l2(y3, y0) < 2e-6
+
+
+@pytest.mark.parametrize("B,Co,Ci,H,W", [(3, 64, 64, 16, 16), (2, 256, 64, 32, 32), (2, 64, 256, 32, 32), (64, 64, 64, 64, 64),
+                                          (1, 128, 32, 12, 20), (2, 64, 64, 8, 8)])
+@pytest.mark.parametrize("mode,tol", [(3, 1e-5), (1, 2e-3)])
+def test_tc_wgrad(B, Co, Ci, H, W, mode, tol):
+    g = _rand(B, Co, H, W, seed=5)
+    x = _rand(B, Ci, H, W, seed=6)
+    try:
+        _set_tc(mode)
+        gW, gb = ops.pointwise_wgrad(g.to(DEV), x.to(DEV))
+    finally:
+        _set_tc(3)
+    assert rel_l2(gW, torch.einsum("bop,bip->oi", g.double().flatten(2), x.double().flatten(2))) < tol
+    assert rel_l2(gb, g.double().sum(dim=(0, 2, 3))) < 1e-5
