@@ -20,6 +20,7 @@ struct TcWgParams {
     int mblocks;             // ceil(Pc / 128)
     int CH;                  // 32-pixel chunks per pipeline item
     int stages;
+    int R;                   // rotating TMEM accumulators (shortens each tensor-core accumulation chain)
     int64_t HW;
     int64_t items_per_b, nitems;
     float* ws;               // [grid][mblocks*128][Qc]
@@ -101,11 +102,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                         const uint32_t qoff = (uint32_t)j * chunk_bytes + p_chunk + (uint32_t)ks * 32;
                         const uint64_t bh = tc::make_smem_desc(hi + qoff, 16, 1024, tc::LAYOUT_SW128);
                         const uint64_t bl = tc::make_smem_desc(lo + qoff, 16, 1024, tc::LAYOUT_SW128);
-                        const uint32_t acc = (q > 0 || j > 0 || ks > 0) ? 1u : 0u;
+                        const uint32_t acc = (q >= p.R || j > 0 || ks > 0) ? 1u : 0u;
                         for (int mb = 0; mb < p.mblocks; ++mb) {
                             const uint32_t poff = (uint32_t)j * chunk_bytes + (uint32_t)mb * 128 * 128 + (uint32_t)ks * 32;
                             const uint64_t ah = tc::make_smem_desc(hi + poff, 16, 1024, tc::LAYOUT_SW128);
-                            const uint32_t d = tmem_base + (uint32_t)mb * (uint32_t)p.Qc;
+                            const uint32_t d = tmem_base + (uint32_t)((int)(q % p.R) * p.mblocks + mb) * (uint32_t)p.Qc;
                             tc::umma_tf32(d, ah, bh, p.idesc, acc);
                             if (PASSES == 3) {
                                 const uint64_t al = tc::make_smem_desc(lo + poff, 16, 1024, tc::LAYOUT_SW128);
@@ -153,18 +154,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
         for (int mb = 0; mb < p.mblocks; ++mb) {
             const int row = mb * 128 + quarter * 32 + lane;
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                uint32_t r[16];
-                if (my_items > 0) {
-                    tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * p.Qc + c0), r);
-                    tc::tmem_ld_wait();
-                } else {
+                float r[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                for (int j = 0; j < 16; ++j) r[j] = 0.f;
+                const int nacc = (int)(my_items < p.R ? my_items : p.R);
+                for (int ra = 0; ra < nacc; ++ra) {                   // fp32 sum of the rotating accumulators
+                    uint32_t t[16];
+                    tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                               (uint32_t)((ra * p.mblocks + mb) * p.Qc + c0), t);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] += __uint_as_float(t[j]);
                 }
                 if (row < p.Pc) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < c_end) wsc[(int64_t)row * p.Qc + c0 + j] = __uint_as_float(r[j]);
+                        if (c0 + j < c_end) wsc[(int64_t)row * p.Qc + c0 + j] = r[j];
                 }
             }
         }
@@ -270,8 +275,11 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
     p.items_per_b = (HW + 32 * p.CH - 1) / (32 * p.CH);
     p.nitems = p.items_per_b * B;
     p.idesc = tc::make_idesc_tf32(128, Qc, 0, 0);
+    p.R = 512 / (p.mblocks * Qc);
+    if (p.R > 8) p.R = 8;
+    if (p.R < 1) p.R = 1;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(p.mblocks * Qc)) cols <<= 1;
+    while (cols < (uint32_t)(p.R * p.mblocks * Qc)) cols <<= 1;
     p.tmem_cols = cols;
     p.ws = workspace;
     const int sms = tw_num_sms();
