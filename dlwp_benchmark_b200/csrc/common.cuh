@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "spectral_b200.h"
 
@@ -18,6 +19,13 @@ struct sb200_plan_s {
     float2* rowI[2];   // [Mx][W]   (a*cos, -a*sin)
     // planar / padded copies for the tensor-core kernels are appended by tc_plan.cu
     void* tc;          // opaque (sb200_tc_tables*) or NULL
+};
+
+// tables for the tcgen05 row-synthesis (tc_plan.cu); NULL in the plan when the grid is not tileable
+struct sb200_tc_tables {
+    int R, V, K2, K2pad;
+    float* E[2];      // [K2pad][128]
+    float2* rot;      // [V][Mx]
 };
 
 void sb200_set_error(const char* fmt, ...);

@@ -144,6 +144,14 @@ __device__ __forceinline__ uint32_t sw128_kmajor_off(int row, int k /* 0..31 */)
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
+// byte offset of element (row, k) inside a K-major 32B-swizzled tile: one tile per k-step of 8 fp32
+// (rows of 32 B, 8-row atoms of 256 B, 16-byte chunk index XOR ((row >> 2) & 1)); consecutive k-steps
+// are `kstep_stride` bytes apart.  Descriptor: LAYOUT_SW32, SBO = 256.  Tile base 256-byte aligned.
+__device__ __forceinline__ uint32_t sw32_kmajor_off(int row, int k, uint32_t kstep_stride) {
+    return (uint32_t)(k >> 3) * kstep_stride + (uint32_t)row * 32u + (uint32_t)(((((k & 7) >> 2) ^ ((row >> 2) & 1)) & 1) << 4) +
+           (uint32_t)((k & 3) << 2);
+}
+
 // byte offset of element (mn, k) inside an MN-major tile of 32-bit elements in the SWIZZLE_128B_BASE32B layout
 // (the only MN-major layout tcgen05 accepts for tf32; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
 // rows = k (128 B = 32 mn elements each), 4-row atoms of 512 B, 32-byte chunk index XOR (k % 4);

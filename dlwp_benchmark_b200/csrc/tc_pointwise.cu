@@ -66,16 +66,23 @@ extern "C" int sb200_get_tc_mode(void) { return g_tc_mode; }
 
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent, warp-specialised
-//   warp 0     TMA producer (one lane)           activation tiles -> smem ring
-//   warp 1     MMA issuer (one lane)             tcgen05.mma into a double-buffered TMEM accumulator
-//   warps 2-17 workers: (a) split a landed tile into tf32 hi/lo parts (3xTF32 only),
-//              (b) epilogue: TMEM -> registers -> bias / GELU / GELU' -> global
-// The workers split the NEXT tile before running the epilogue of the current one, so the MMAs of
-// tile t+1 execute while tile t is being written out; TMA loads run ahead by the ring depth.
+//   warp 0      TMA producer (one lane)          activation K-chunks (32 channels x 128 px) -> smem ring
+//   warp 1      MMA issuer (one lane)            tcgen05.mma into a double-buffered TMEM accumulator
+//   warps 2-17  workers: (a) stage the Phi operand of the NEXT tile (spectral term) and split its landed
+//               activation chunks into tf32 hi/lo parts, (b) epilogue of the CURRENT tile:
+//               TMEM -> registers -> bias / GELU / GELU' -> global
+// so the MMAs of tile t+1 execute while tile t is being written out; TMA runs ahead by the ring depth.
+//
+// Spectral term (row synthesis):  D[p, n] += sum_kk E[p, kk] * Phi[b, n, y(p), kk]
+//   E   : constant [128 px][K2pad] operand (plan table; block-diagonal over the R image rows of a tile),
+//         K-major SWIZZLE_32B, resident in smem as hi/lo
+//   Phi : per tile [N][K2pad] (column-synthesised spectrum of the R rows of this tile, rotated to the
+//         tile's x offset), staged by the workers as K-major SWIZZLE_32B hi/lo, double-buffered
 // ---------------------------------------------------------------------------------------------
 constexpr int TP_PX = 128;
 constexpr int TP_WORKER_WARPS = 16;
 constexpr int TP_THREADS = 32 * (2 + TP_WORKER_WARPS);
+constexpr int TP_WTHREADS = 32 * TP_WORKER_WARPS;
 
 struct TcPwParams {
     const float* Wp; int64_t w_sn, w_sm;
@@ -85,7 +92,10 @@ struct TcPwParams {
     int64_t HW;
     int64_t ntiles;
     int mode, apply_act;
-    uint32_t idesc, tmem_cols;
+    uint32_t idesc, idesc_spec, tmem_cols;
+    // spectral term (Phi == NULL: none)
+    const float2* Phi; const float* E; const float2* rot;
+    int H, W, Mx, R, V, K2, K2pad;
 };
 
 template <int PASSES>
@@ -94,28 +104,38 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KC = p.KC, nkc = p.nkc, S = p.stages;
+    const bool spectral = p.Phi != nullptr;
     const uint32_t a_bytes = (uint32_t)KC * 512;                       // 4 boxes x KC rows x 128 B
     const uint32_t a_stage_bytes = a_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
     const int kchunks = (p.M + 31) / 32;                               // 32-wide K chunks of the resident weight tile
     const uint32_t b_chunk_bytes = (uint32_t)p.N * 128;                // N rows x 128 B
-    const uint32_t b_bytes = ((uint32_t)kchunks * b_chunk_bytes + 1023) & ~1023u;
+    const uint32_t b_bytes = nkc ? (((uint32_t)kchunks * b_chunk_bytes + 1023) & ~1023u) : 0u;
+    const int ksteps2 = spectral ? p.K2pad / 8 : 0;
+    const uint32_t e_bytes = (uint32_t)ksteps2 * 4096;                 // [kstep][128 rows][32 B]
+    const uint32_t phi_kstep = (uint32_t)p.N * 32;
+    const uint32_t phi_bytes = ((uint32_t)ksteps2 * phi_kstep + 1023) & ~1023u;
     uint8_t* B_hi = base;
     uint8_t* B_lo = B_hi + b_bytes;
-    uint8_t* A_st = B_lo + (PASSES == 3 ? b_bytes : 0);
+    uint8_t* E_hi = B_lo + (PASSES == 3 ? b_bytes : 0);
+    uint8_t* E_lo = E_hi + e_bytes;
+    uint8_t* Phi_s = E_lo + (PASSES == 3 ? e_bytes : 0);              // [2 buffers][hi | lo]
+    const uint32_t phi_buf_bytes = phi_bytes * (PASSES == 3 ? 2 : 1);
+    uint8_t* A_st = Phi_s + 2 * phi_buf_bytes;
     uint8_t* tail = A_st + (uint32_t)S * a_stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);           // [S]  TMA landed
     uint64_t* split_bar = full_bar + S;                                // [S]  hi/lo split done (workers -> MMA)
     uint64_t* empty_bar = split_bar + S;                               // [S]  MMAs that read the stage are done
     uint64_t* tfull_bar = empty_bar + S;                               // [2]  accumulator complete
     uint64_t* tempty_bar = tfull_bar + 2;                              // [2]  accumulator drained by the epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* phi_bar = tempty_bar + 2;                                // [2]  Phi operand staged
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(phi_bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_per_b = (int)((p.HW + TP_PX - 1) / TP_PX);
 
     // ---- one-time setup ----
     if (tid == 0) {
-        tc::tma_prefetch_desc(&tmapA);
+        if (nkc) tc::tma_prefetch_desc(&tmapA);
         for (int s = 0; s < S; ++s) {
             tc::mbar_init(full_bar + s, 1);
             tc::mbar_init(split_bar + s, TP_WORKER_WARPS);
@@ -124,6 +144,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(tfull_bar + a, 1);
             tc::mbar_init(tempty_bar + a, TP_WORKER_WARPS);
+            tc::mbar_init(phi_bar + a, TP_WORKER_WARPS);
         }
         tc::fence_barrier_init();
     }
@@ -133,13 +154,29 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         tc::tmem_relinquish();
     }
     // resident weight tile: Wp[n, m] -> K-major 128B-swizzled rows, split into tf32 hi / lo
-    for (int idx = tid; idx < p.N * p.M; idx += TP_THREADS) {
-        const int n = idx / p.M, k = idx % p.M;
-        const float w = __ldg(p.Wp + (int64_t)n * p.w_sn + (int64_t)k * p.w_sm);
-        const float hi = tc::tf32_trunc(w);
-        const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
-        *reinterpret_cast<float*>(B_hi + off) = hi;
-        if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
+    if (nkc) {
+        for (int idx = tid; idx < p.N * p.M; idx += TP_THREADS) {
+            const int n = idx / p.M, k = idx % p.M;
+            const float w = __ldg(p.Wp + (int64_t)n * p.w_sn + (int64_t)k * p.w_sm);
+            const float hi = tc::tf32_trunc(w);
+            const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
+            *reinterpret_cast<float*>(B_hi + off) = hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
+        }
+    }
+    if (spectral) {
+        // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo
+        for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
+            const int k = idx >> 7, px = idx & 127;
+            const float v = __ldg(p.E + idx);
+            const float hi = tc::tf32_trunc(v);
+            const uint32_t off = tc::sw32_kmajor_off(px, k, 4096u);
+            *reinterpret_cast<float*>(E_hi + off) = hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = v - hi;
+        }
+        // zero both Phi buffers once: the K padding columns are never written again
+        for (int idx = tid; idx < (int)(2 * phi_buf_bytes / 16); idx += TP_THREADS)
+            reinterpret_cast<float4*>(Phi_s)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
@@ -152,7 +189,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (lane == 0 && nkc) {
             int64_t q = 0;
             for (int64_t it = 0; it < my_tiles; ++it) {
                 const int64_t tile = first + it * stride;
@@ -182,6 +219,25 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
                 tc::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + (uint32_t)a * (uint32_t)p.N;
+                uint32_t started = 0;
+                if (spectral) {
+                    tc::mbar_wait(phi_bar + a, tround & 1);
+                    tc::tc_fence_after_sync();
+                    const uint32_t ph = tc::smem_u32(Phi_s + (uint32_t)a * phi_buf_bytes);
+                    const uint32_t pl = ph + phi_bytes;
+                    for (int ks = 0; ks < ksteps2; ++ks) {
+                        const uint64_t eh = tc::make_smem_desc(tc::smem_u32(E_hi) + (uint32_t)ks * 4096, 16, 256, tc::LAYOUT_SW32);
+                        const uint64_t fh = tc::make_smem_desc(ph + (uint32_t)ks * phi_kstep, 16, 256, tc::LAYOUT_SW32);
+                        tc::umma_tf32(tmem_d, eh, fh, p.idesc_spec, started);
+                        started = 1;
+                        if (PASSES == 3) {
+                            const uint64_t el = tc::make_smem_desc(tc::smem_u32(E_lo) + (uint32_t)ks * 4096, 16, 256, tc::LAYOUT_SW32);
+                            const uint64_t fl = tc::make_smem_desc(pl + (uint32_t)ks * phi_kstep, 16, 256, tc::LAYOUT_SW32);
+                            tc::umma_tf32(tmem_d, el, fh, p.idesc_spec, 1u);
+                            tc::umma_tf32(tmem_d, eh, fl, p.idesc_spec, 1u);
+                        }
+                    }
+                }
                 for (int kc = 0; kc < nkc; ++kc, ++q) {
                     const int s = (int)(q % S);
                     const uint32_t round = (uint32_t)(q / S);
@@ -195,7 +251,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         const uint32_t b_off = (uint32_t)(kg >> 5) * b_chunk_bytes + (uint32_t)((kg & 31) >> 3) * 32;
                         const uint64_t ah = tc::make_smem_desc(A_hi + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
                         const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
-                        tc::umma_tf32(tmem_d, ah, bh, p.idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        tc::umma_tf32(tmem_d, ah, bh, p.idesc, started);
+                        started = 1;
                         if (PASSES == 3) {
                             const uint64_t al = tc::make_smem_desc(A_lo + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
                             const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
@@ -209,7 +266,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             }
         }
     } else {
-        // ================= workers: split (tile t+1) then epilogue (tile t) =================
+        // ================= workers: stage/split (tile t+1) then epilogue (tile t) =================
         const int wk = warp - 2;                               // 0..15
         const int wtid = tid - 64;                             // 0..511
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
@@ -217,28 +274,57 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         const int ncol_part = ((p.N + 3) / 4 + 3) & ~3;        // columns per part (multiple of 4)
         int64_t q_split = 0;
 
-        auto split_tile_items = [&](int64_t /*it*/) {
-            for (int kc = 0; kc < nkc; ++kc, ++q_split) {
-                const int s = (int)(q_split % S);
-                const uint32_t round = (uint32_t)(q_split / S);
-                tc::mbar_wait(full_bar + s, round & 1);
-                float4* ah = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes);
-                float4* al = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes + a_bytes);
-                for (int idx = wtid; idx < (int)(a_bytes / 16); idx += 32 * TP_WORKER_WARPS) {
-                    const float4 v = ah[idx];
-                    const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
-                    ah[idx] = h;
-                    al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        auto prepare_tile = [&](int64_t it) {
+            if (spectral) {
+                const int64_t tile = first + it * stride;
+                const int b = (int)(tile / tiles_per_b);
+                const int64_t p_base = (tile % tiles_per_b) * TP_PX;
+                const int y0 = (int)(p_base / p.W);
+                const int v = (int)((p_base % p.W) >> 7);
+                uint8_t* ph = Phi_s + (uint32_t)(it & 1) * phi_buf_bytes;
+                uint8_t* pl = ph + phi_bytes;
+                const int per_n = p.R * p.Mx;
+                for (int idx = wtid; idx < p.N * per_n; idx += TP_WTHREADS) {
+                    const int n = idx / per_n, rem = idx % per_n;
+                    const int r = rem / p.Mx, kx = rem % p.Mx;
+                    float2 f = __ldg(p.Phi + (((int64_t)b * p.N + n) * p.H + y0 + r) * p.Mx + kx);
+                    if (p.V > 1) {
+                        const float2 c = __ldg(p.rot + v * p.Mx + kx);
+                        f = make_float2(f.x * c.x - f.y * c.y, f.x * c.y + f.y * c.x);
+                    }
+                    const int kk = r * 2 * p.Mx + 2 * kx;
+                    const uint32_t off = tc::sw32_kmajor_off(n, kk, phi_kstep);      // (re, im) are adjacent
+                    const float2 h = make_float2(tc::tf32_trunc(f.x), tc::tf32_trunc(f.y));
+                    *reinterpret_cast<float2*>(ph + off) = h;
+                    if (PASSES == 3) *reinterpret_cast<float2*>(pl + off) = make_float2(f.x - h.x, f.y - h.y);
                 }
                 tc::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(split_bar + s);
+                if (lane == 0) tc::mbar_arrive(phi_bar + (it & 1));
+            }
+            if (PASSES == 3) {
+                for (int kc = 0; kc < nkc; ++kc, ++q_split) {
+                    const int s = (int)(q_split % S);
+                    const uint32_t round = (uint32_t)(q_split / S);
+                    tc::mbar_wait(full_bar + s, round & 1);
+                    float4* ah = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes);
+                    float4* al = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes + a_bytes);
+                    for (int idx = wtid; idx < (int)(a_bytes / 16); idx += TP_WTHREADS) {
+                        const float4 v = ah[idx];
+                        const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                        ah[idx] = h;
+                        al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(split_bar + s);
+                }
             }
         };
 
-        if (PASSES == 3 && my_tiles > 0) split_tile_items(0);
+        if (my_tiles > 0) prepare_tile(0);
         for (int64_t it = 0; it < my_tiles; ++it) {
-            if (PASSES == 3 && it + 1 < my_tiles) split_tile_items(it + 1);
+            if (it + 1 < my_tiles) prepare_tile(it + 1);
             const int64_t tile = first + it * stride;
             const int b = (int)(tile / tiles_per_b);
             const int64_t p_base = (tile % tiles_per_b) * TP_PX;
@@ -297,40 +383,57 @@ static int g_num_sms = 0;
 
 int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, cudaStream_t st, int* handled) {
     *handled = 0;
-    (void)plan; (void)pass;
     if (g_tc_mode == 0) return 0;
-    if (q.Phi != nullptr || q.Wp == nullptr) return 0;                  // spectral term: CUDA-core kernel for now
     const int64_t HW = (int64_t)q.H * q.W;
     const int M = q.M, N = q.N;
-    if (M % 8 != 0 || !(M <= 64 || M % 64 == 0)) return 0;
+    const bool has_pw = q.Wp != nullptr, has_spec = q.Phi != nullptr;
+    if (has_pw && (M % 8 != 0 || !(M <= 32 || M % 32 == 0))) return 0;
     if (N % 16 != 0 || N < 16 || N > 256) return 0;
-    if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(q.A) & 15) != 0) return 0;
-    if ((int64_t)q.B * M >= (1LL << 31)) return 0;
+    if (HW % 4 != 0) return 0;
+    if (has_pw && ((reinterpret_cast<uintptr_t>(q.A) & 15) != 0 || (int64_t)q.B * M >= (1LL << 31))) return 0;
+    const sb200_tc_tables* tt = (const sb200_tc_tables*)plan->tc;
+    if (has_spec && (tt == nullptr || (reinterpret_cast<uintptr_t>(q.Phi) & 7) != 0)) return 0;
     const int passes = g_tc_mode;
 
     TcPwParams p;
+    memset(&p, 0, sizeof(p));
     p.Wp = q.Wp; p.w_sn = q.w_sn; p.w_sm = q.w_sm; p.bias = q.bias; p.zprev = q.zprev;
-    p.z_out = q.z_out; p.y_out = q.y_out; p.B = q.B; p.M = M; p.N = N; p.KC = M < 64 ? M : 64; p.HW = HW;
-    p.nkc = M / p.KC;
+    p.z_out = q.z_out; p.y_out = q.y_out; p.B = q.B; p.M = M; p.N = N; p.HW = HW;
+    p.KC = has_pw ? (M < 32 ? M : 32) : 8;
+    p.nkc = has_pw ? M / p.KC : 0;
     p.mode = q.mode; p.apply_act = q.apply_act;
     p.idesc = tc::make_idesc_tf32(128, N, /*A MN-major*/ 1, /*B K-major*/ 0);
+    p.idesc_spec = tc::make_idesc_tf32(128, N, 0, 0);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * N)) cols <<= 1;
     p.tmem_cols = cols;
     p.ntiles = (HW + TP_PX - 1) / TP_PX * q.B;
+    p.H = q.H; p.W = q.W; p.Mx = q.Mx;
+    if (has_spec) {
+        p.Phi = q.Phi; p.E = tt->E[pass]; p.rot = tt->rot;
+        p.R = tt->R; p.V = tt->V; p.K2 = tt->K2; p.K2pad = tt->K2pad;
+    }
 
-    const size_t a_stage = (size_t)p.KC * 512 * (passes == 3 ? 2 : 1);
-    const size_t b_bytes = (((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * (passes == 3 ? 2 : 1);
-    const size_t fixed = 1024 + b_bytes + 256;
-    int stages = 4;
-    while (stages > 1 && fixed + stages * a_stage > 200 * 1024) --stages;
-    if (fixed + stages * a_stage > 227 * 1024) return 0;               // does not fit: CUDA-core kernel
+    const size_t mult = passes == 3 ? 2 : 1;
+    const size_t a_stage = (size_t)p.KC * 512 * mult;
+    const size_t b_bytes = has_pw ? ((((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * mult) : 0;
+    const size_t e_bytes = has_spec ? (size_t)(p.K2pad / 8) * 4096 * mult : 0;
+    const size_t phi_bytes = has_spec ? ((((size_t)(p.K2pad / 8) * N * 32 + 1023) & ~(size_t)1023) * mult * 2) : 0;
+    const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512;
+    int stages = has_pw ? 6 : 1;
+    while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
+    if (fixed + stages * a_stage > 227 * 1024) {
+        stages = 1;
+        if (fixed + stages * a_stage > 227 * 1024) return 0;           // does not fit: CUDA-core kernel
+    }
     p.stages = stages;
     const size_t smem = fixed + stages * a_stage;
 
     CUtensorMap tmap;
-    if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2))
-        return rc;
+    memset(&tmap, 0, sizeof(tmap));
+    if (has_pw)
+        if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2))
+            return rc;
     if (g_num_sms == 0) {
         int dev = 0;
         SB_CHECK_CUDA(cudaGetDevice(&dev));

@@ -5,7 +5,8 @@
 
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, float* __restrict__ D, int N, int K,
-                   int a_layout, int use_mask, uint32_t* __restrict__ info) {
+                   int a_layout_in, int use_mask, uint32_t* __restrict__ info) {
+    const int a_layout = a_layout_in & 15, b_sw32 = a_layout_in >> 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = (uint32_t)((K + 31) / 32) * 128u * 128u;   // K-major rows are 128 B wide even when K < 32
@@ -22,12 +23,14 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
         const float v = Ag[idx];
         uint32_t off;
         if (a_layout == 0) off = (uint32_t)(k >> 5) * (128u * 128u) + tc::sw128_kmajor_off(m, k & 31);
+        else if (a_layout == 3) off = tc::sw32_kmajor_off(m, k, 128u * 32u);
         else off = tc::sw128b32_mnmajor_off(m, k, (uint32_t)K * 128u);
         *reinterpret_cast<float*>(As + off) = v;
     }
     for (int idx = tid; idx < N * K; idx += 128) {
         const int n = idx / K, k = idx % K;
-        *reinterpret_cast<float*>(Bs + (uint32_t)(k >> 5) * b_chunk + tc::sw128_kmajor_off(n, k & 31)) = Bg[idx];
+        if (b_sw32) *reinterpret_cast<float*>(Bs + tc::sw32_kmajor_off(n, k, (uint32_t)N * 32u)) = Bg[idx];
+        else *reinterpret_cast<float*>(Bs + (uint32_t)(k >> 5) * b_chunk + tc::sw128_kmajor_off(n, k & 31)) = Bg[idx];
     }
     if (tid == 0) {
         tc::mbar_init(mma_bar, 1);
@@ -47,17 +50,20 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
     const uint32_t tmem_d = *tmem_slot;
     if (tid == 0) {
         info[0] = tmem_d;
-        const uint32_t idesc = tc::make_idesc_tf32(128, N, a_layout != 0, 0);
+        const uint32_t idesc = tc::make_idesc_tf32(128, N, (a_layout == 1 || a_layout == 2), 0);
         info[1] = idesc;
         for (int ks = 0; ks < K / 8; ++ks) {
             uint64_t ad;
             if (a_layout == 0)
                 ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)(ks >> 2) * (128u * 128u) + (uint32_t)(ks & 3) * 32, 16, 1024, tc::LAYOUT_SW128);
+            else if (a_layout == 3)
+                ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * (128u * 32u), 16, 256, tc::LAYOUT_SW32);
             else if (a_layout == 1)
                 ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, (uint32_t)K * 128, 512, tc::LAYOUT_SW128_BASE32B);
             else
                 ad = tc::make_smem_desc(tc::smem_u32(As) + (uint32_t)ks * 1024, 512, (uint32_t)K * 128, tc::LAYOUT_SW128_BASE32B);
-            const uint64_t bd = tc::make_smem_desc(tc::smem_u32(Bs) + (uint32_t)(ks >> 2) * b_chunk + (uint32_t)(ks & 3) * 32, 16, 1024, tc::LAYOUT_SW128);
+            const uint64_t bd = b_sw32 ? tc::make_smem_desc(tc::smem_u32(Bs) + (uint32_t)ks * ((uint32_t)N * 32u), 16, 256, tc::LAYOUT_SW32)
+                                       : tc::make_smem_desc(tc::smem_u32(Bs) + (uint32_t)(ks >> 2) * b_chunk + (uint32_t)(ks & 3) * 32, 16, 1024, tc::LAYOUT_SW128);
             if (ks == 0) { info[2] = (uint32_t)ad; info[3] = (uint32_t)(ad >> 32); info[4] = (uint32_t)bd; info[5] = (uint32_t)(bd >> 32); }
             if (use_mask) {
                 uint32_t z = 0, acc = ks > 0;

@@ -346,3 +346,49 @@ def test_tc_wgrad(B, Co, Ci, H, W, mode, tol):
         _set_tc(3)
     assert rel_l2(gW, torch.einsum("bop,bip->oi", g.double().flatten(2), x.double().flatten(2))) < tol
     assert rel_l2(gb, g.double().sum(dim=(0, 2, 3))) < 1e-5
+
+
+TC_BLOCK_SHAPES = [
+    # B, Cin, Cout, H, W, n_modes, act, skip
+    (2, 16, 16, 64, 64, (12, 12), True, True),      # R = 2 rows per tile
+    (1, 32, 32, 256, 256, (32, 32), True, True),    # V = 2 x-offset variants (cfg3 grid)
+    (2, 16, 32, 32, 32, (8, 8), False, False),      # R = 4, pure SpectralConv (no pointwise operand)
+    (1, 16, 16, 128, 128, (16, 16), True, True),    # cfg5 grid
+    (2, 64, 64, 32, 64, (12, 12), True, True),      # dlwpbench grid
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,H,W,nm,act,skip", TC_BLOCK_SHAPES)
+@pytest.mark.parametrize("mode,tol", [(3, 1e-5), (1, 3e-3)])
+def test_tc_fno_block(B, Ci, Co, H, W, nm, act, skip, mode, tol):
+    """FNO block (spectral + skip + GELU) fwd+bwd with the row-synthesis stage on tcgen05."""
+    half = so.halve_last_mode(nm)
+    lo, My = so.retained_rows(H, half[0])
+    Mx = min(half[1], W // 2 + 1)
+    x = _rand(B, Ci, H, W, seed=1)
+    w = _rand(Ci, Co, My, Mx, 2, seed=2, scale=0.5)
+    ws = _rand(Co, Ci, 1, 1, seed=3, scale=0.2) if skip else None
+    b = _rand(Co, 1, 1, seed=4, scale=0.3)
+    gy = _rand(B, Co, H, W, seed=5)
+    xo, wo, bo = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    wso = ws.double().requires_grad_(True) if skip else None
+    yo = so.spectral_conv_dense(xo, torch.view_as_complex(wo), bo, [My, Mx])
+    if skip:
+        yo = yo + torch.nn.functional.conv2d(xo, wso)
+    if act:
+        yo = torch.nn.functional.gelu(yo)
+    yo.backward(gy.double())
+    xc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    wsc = ws.to(DEV).requires_grad_(True) if skip else None
+    try:
+        _set_tc(mode)
+        yc = FNOBlockFn.apply(xc, wc, wsc, bc, tuple(half), act)
+        yc.backward(gy.to(DEV))
+    finally:
+        _set_tc(3)
+    assert rel_l2(yc, yo) < tol
+    assert rel_l2(xc.grad, xo.grad) < tol
+    assert rel_l2(wc.grad, wo.grad) < 2 * tol
+    assert rel_l2(bc.grad, bo.grad) < 2 * tol
+    if skip:
+        assert rel_l2(wsc.grad, wso.grad) < 2 * tol
