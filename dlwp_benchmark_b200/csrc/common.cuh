@@ -66,16 +66,26 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // instructions instead of ~45 for erff + expf, which matters because every activation element of the
 // FNO passes through one of these in a fused epilogue.  Phi for z < 0 is formed without cancellation.
 // Both share exp(-z^2/2), so the derivative costs three more instructions than the value.
+__device__ __forceinline__ float sb_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sb_ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void gelu_core(float z, float& cdf, float& e) {
     const float x = fabsf(z) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+    const float t = sb_rcp_approx(fmaf(0.3275911f, x, 1.0f));
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
-    e = __expf(-x * x);                         // exp(-z^2 / 2)
-    const float half_tail = 0.5f * poly * e;    // 0.5 * erfc(|z| / sqrt 2)
+    e = sb_ex2_approx(-1.4426950408889634f * x * x);   // exp(-z^2 / 2)
+    const float half_tail = 0.5f * poly * e;            // 0.5 * erfc(|z| / sqrt 2)
     cdf = z < 0.f ? half_tail : 1.0f - half_tail;
 }
 __device__ __forceinline__ float gelu_f(float z) {

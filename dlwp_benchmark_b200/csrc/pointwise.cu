@@ -176,6 +176,8 @@ extern "C" int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float*
     p.nrows_max = (PW_PX + plan->W - 1) / plan->W + 1;
     cudaStream_t st = (cudaStream_t)stream;
     int handled = 0;
+    if (Phi == nullptr && M <= 16 && B <= 65535 && (N + 31) / 32 <= 65535 && ((int64_t)p.H * p.W) % 4 == 0)
+        return launch_small_m(p, st);
     if (int rc = sb200_tc_rowidft_pointwise(plan, pass, p, st, &handled)) return rc;
     if (handled) return 0;
     const int K2 = 2 * p.Mx;
@@ -425,6 +427,67 @@ extern "C" int sb200_pointwise_small_n(const float* A, const float* Wp, const fl
         case 4: pointwise_small_n_kernel<4><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
         default: pointwise_small_n_kernel<8><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
     }
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ======================================================================================
+// pointwise layer with few INPUT channels (M <= 16): lifting fc1 (in_channels -> 256) forward and the
+// data gradient of the projection's last conv (out_channels -> 256).  Pure streaming kernel:
+//   acc[b,n,p] = sum_m Wp[n*w_sn + m*w_sm] A[b,m,p] + bias[n];  epilogue as sb200_rowidft_pointwise.
+// ======================================================================================
+template <int MT>
+__global__ void __launch_bounds__(256)
+pointwise_small_m_kernel(const float* __restrict__ A, const float* __restrict__ Wp, int64_t w_sn, int64_t w_sm,
+                         const float* __restrict__ bias, const float* __restrict__ zprev, float* __restrict__ z_out,
+                         float* __restrict__ y_out, int M, int N, int64_t HW, int mode, int apply_act) {
+    __shared__ float wsm[32][MT + 1];
+    const int b = blockIdx.y, n0 = blockIdx.z * 32;
+    for (int idx = threadIdx.x; idx < 32 * MT; idx += 256) {
+        const int nl = idx / MT, m = idx % MT;
+        wsm[nl][m] = (n0 + nl < N && m < M) ? __ldg(Wp + (int64_t)(n0 + nl) * w_sn + (int64_t)m * w_sm) : 0.f;
+    }
+    __syncthreads();
+    const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p0 >= HW) return;
+    float4 a[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+        a[m] = m < M ? __ldg(reinterpret_cast<const float4*>(A + ((int64_t)b * M + m) * HW + p0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nend = min(32, N - n0);
+#pragma unroll 4
+    for (int nl = 0; nl < nend; ++nl) {
+        const int n = n0 + nl;
+        const float bv = bias ? __ldg(bias + n) : 0.f;
+        float4 v = make_float4(bv, bv, bv, bv);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const float w = wsm[nl][m];
+            v.x = fmaf(w, a[m].x, v.x); v.y = fmaf(w, a[m].y, v.y); v.z = fmaf(w, a[m].z, v.z); v.w = fmaf(w, a[m].w, v.w);
+        }
+        const int64_t off = ((int64_t)b * N + n) * HW + p0;
+        if (mode == 0) {
+            if (z_out) *reinterpret_cast<float4*>(z_out + off) = v;
+            if (apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+        } else if (zprev) {
+            const float4 z = __ldg(reinterpret_cast<const float4*>(zprev + off));
+            v.x *= gelu_grad_f(z.x); v.y *= gelu_grad_f(z.y); v.z *= gelu_grad_f(z.z); v.w *= gelu_grad_f(z.w);
+        }
+        *reinterpret_cast<float4*>(y_out + off) = v;
+    }
+}
+
+static int launch_small_m(const PwParams& p, cudaStream_t st) {
+    const int64_t HW = (int64_t)p.H * p.W;
+    dim3 grid((unsigned)ceil_div64(HW, 1024), (unsigned)p.B, (unsigned)((p.N + 31) / 32));
+#define SM_CASE(MT) pointwise_small_m_kernel<MT><<<grid, 256, 0, st>>>(p.A, p.Wp, p.w_sn, p.w_sm, p.bias, p.zprev, p.z_out, \
+                                                                      p.y_out, p.M, p.N, HW, p.mode, p.apply_act)
+    if (p.M <= 1) SM_CASE(1);
+    else if (p.M <= 2) SM_CASE(2);
+    else if (p.M <= 4) SM_CASE(4);
+    else if (p.M <= 8) SM_CASE(8);
+    else SM_CASE(16);
+#undef SM_CASE
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -96,9 +96,11 @@ struct TcPwParams {
     // spectral term (Phi == NULL: none)
     const float2* Phi; const float* E; const float2* rot;
     int H, W, Mx, R, V, K2, K2pad;
+    int tpr_log2;            // log2(threads cooperating on one channel while staging Phi)
 };
 
-template <int PASSES>
+// EPI: 0 fwd linear | 1 fwd GELU, also write pre-activation z | 2 fwd GELU | 3 bwd * GELU'(zprev) | 4 bwd plain
+template <int PASSES, int EPI>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -284,19 +286,24 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 uint8_t* ph = Phi_s + (uint32_t)(it & 1) * phi_buf_bytes;
                 uint8_t* pl = ph + phi_bytes;
                 const int per_n = p.R * p.Mx;
-                for (int idx = wtid; idx < p.N * per_n; idx += TP_WTHREADS) {
-                    const int n = idx / per_n, rem = idx % per_n;
-                    const int r = rem / p.Mx, kx = rem % p.Mx;
-                    float2 f = __ldg(p.Phi + (((int64_t)b * p.N + n) * p.H + y0 + r) * p.Mx + kx);
-                    if (p.V > 1) {
-                        const float2 c = __ldg(p.rot + v * p.Mx + kx);
-                        f = make_float2(f.x * c.x - f.y * c.y, f.x * c.y + f.y * c.x);
+                // tpr threads cooperate on one output channel n (tpr = power of two, tpr * N >= worker threads)
+                const int n = wtid >> p.tpr_log2, sub = wtid & ((1 << p.tpr_log2) - 1);
+                if (n < p.N) {
+                    const float2* src = p.Phi + (((int64_t)b * p.N + n) * p.H + y0) * p.Mx;   // R*Mx contiguous complex
+                    for (int rem = sub; rem < per_n; rem += (1 << p.tpr_log2)) {
+                        int r = 0, kx = rem;
+                        while (kx >= p.Mx) { kx -= p.Mx; ++r; }
+                        float2 f = __ldg(src + rem);
+                        if (p.V > 1) {
+                            const float2 c = __ldg(p.rot + v * p.Mx + kx);
+                            f = make_float2(f.x * c.x - f.y * c.y, f.x * c.y + f.y * c.x);
+                        }
+                        const uint32_t off = tc::sw32_kmajor_off(n, 2 * rem, phi_kstep);    // kk = r*2Mx + 2kx = 2*rem
+                        const float2 h = make_float2(tc::tf32_trunc(f.x), tc::tf32_trunc(f.y));
+                        *reinterpret_cast<float2*>(ph + off) = h;
+                        if (PASSES == 3) *reinterpret_cast<float2*>(pl + off) = make_float2(f.x - h.x, f.y - h.y);
+                        (void)r;
                     }
-                    const int kk = r * 2 * p.Mx + 2 * kx;
-                    const uint32_t off = tc::sw32_kmajor_off(n, kk, phi_kstep);      // (re, im) are adjacent
-                    const float2 h = make_float2(tc::tf32_trunc(f.x), tc::tf32_trunc(f.y));
-                    *reinterpret_cast<float2*>(ph + off) = h;
-                    if (PASSES == 3) *reinterpret_cast<float2*>(pl + off) = make_float2(f.x - h.x, f.y - h.y);
                 }
                 tc::fence_proxy_async_smem();
                 __syncwarp();
@@ -336,32 +343,33 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const bool in_range = pp < p.HW;
             const int c_begin = cpart * ncol_part;
             const int c_end = min(p.N, c_begin + ncol_part);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N);
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                const int nv = min(16, c_end - c0);
+                const int64_t off0 = ((int64_t)b * p.N + c0) * p.HW + pp;
                 uint32_t r[16];
                 float zp[16], bv[16];
-                const int64_t off0 = ((int64_t)b * p.N + c0) * p.HW + pp;
                 // issue every global load of this chunk before touching TMEM (independent loads in flight)
+                if (EPI == 3) {
+                    const float* zsrc = p.zprev + off0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const bool ok = in_range && (c0 + j < c_end);
-                    zp[j] = (ok && p.mode == 1 && p.zprev) ? __ldg(p.zprev + off0 + (int64_t)j * p.HW) : 0.f;
-                    bv[j] = (ok && p.bias) ? __ldg(p.bias + c0 + j) : 0.f;
+                    for (int j = 0; j < 16; ++j) zp[j] = (in_range && j < nv) ? __ldg(zsrc + (int64_t)j * p.HW) : 0.f;
                 }
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N + c0), r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bv[j] = (p.bias && j < nv) ? __ldg(p.bias + c0 + j) : 0.f;
+                tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
                 if (in_range) {
+                    float* ydst = p.y_out + off0;
+                    float* zdst = (EPI == 1) ? p.z_out + off0 : nullptr;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (c0 + j < c_end) {
+                        if (j < nv) {
                             float v = __uint_as_float(r[j]) + bv[j];
-                            const int64_t off = off0 + (int64_t)j * p.HW;
-                            if (p.mode == 0) {
-                                if (p.z_out) p.z_out[off] = v;
-                                if (p.apply_act) v = gelu_f(v);
-                            } else if (p.zprev) {
-                                v *= gelu_grad_f(zp[j]);
-                            }
-                            p.y_out[off] = v;
+                            if (EPI == 1) zdst[(int64_t)j * p.HW] = v;
+                            if (EPI == 1 || EPI == 2) v = gelu_f(v);
+                            if (EPI == 3) v *= gelu_grad_f(zp[j]);
+                            ydst[(int64_t)j * p.HW] = v;
                         }
                     }
                 }
@@ -440,13 +448,30 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
         SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
-    if (passes == 3) {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<3><<<grid, TP_THREADS, smem, st>>>(tmap, p);
-    } else {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
+    int tl = 0;
+    while ((1 << (tl + 1)) * N <= TP_WTHREADS) ++tl;
+    p.tpr_log2 = tl;
+    int epi;
+    if (q.mode == 0) epi = q.apply_act ? (q.z_out ? 1 : 2) : 0;
+    else epi = q.zprev ? 3 : 4;
+    if (q.mode == 0 && !q.apply_act && q.z_out) return 0;              // (never requested) keep the generic kernel
+#define TP_LAUNCH(PS, EP)                                                                                              \
+    do {                                                                                                               \
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem));                                                                \
+        tc_pointwise_kernel<PS, EP><<<grid, TP_THREADS, smem, st>>>(tmap, p);                                          \
+    } while (0)
+#define TP_LAUNCH_EPI(PS)                                                                                              \
+    switch (epi) {                                                                                                     \
+        case 0: TP_LAUNCH(PS, 0); break;                                                                               \
+        case 1: TP_LAUNCH(PS, 1); break;                                                                               \
+        case 2: TP_LAUNCH(PS, 2); break;                                                                               \
+        case 3: TP_LAUNCH(PS, 3); break;                                                                               \
+        default: TP_LAUNCH(PS, 4); break;                                                                              \
     }
+    if (passes == 3) { TP_LAUNCH_EPI(3) } else { TP_LAUNCH_EPI(1) }
+#undef TP_LAUNCH_EPI
+#undef TP_LAUNCH
     SB_LAUNCH_CHECK();
     *handled = 1;
     return 0;

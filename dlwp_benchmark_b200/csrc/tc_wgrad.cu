@@ -180,17 +180,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
 }
 
 // out[(transpose ? q*Pc + pch : pch*Qc + q)] = sum_c ws[c][pch][q]   (ws rows padded to mblocks*128)
+// one warp per output element: lanes stride over the partials, fixed-order shuffle reduction (deterministic)
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int Pc, int Qc, int prow_pad, int nparts,
                        int transpose) {
-    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (e >= (int64_t)Pc * Qc) return;
     const int pch = (int)(e / Qc), q = (int)(e % Qc);
-    float s = 0.f;
     const int64_t part = (int64_t)prow_pad * Qc;
-#pragma unroll 8
-    for (int c = 0; c < nparts; ++c) s += __ldg(ws + c * part + e);
-    out[transpose ? (int64_t)q * Pc + pch : e] = s;
+    float s = 0.f;
+    for (int c = lane; c < nparts; c += 32) s += __ldg(ws + c * part + e);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[transpose ? (int64_t)q * Pc + pch : e] = s;
 }
 
 // per-channel sums: out[c] = sum_{b,p} g[b,c,p]   (one warp per (b,c) row, then a fixed-order sum over b)
@@ -297,7 +300,7 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
     }
     SB_LAUNCH_CHECK();
     const int64_t E = (int64_t)Pc * Qc;
-    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(workspace, gW, Pc, Qc, p.mblocks * 128, (int)grid, tr);
+    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 8), 256, 0, st>>>(workspace, gW, Pc, Qc, p.mblocks * 128, (int)grid, tr);
     SB_LAUNCH_CHECK();
     if (gbias) {
         float* part = workspace + (int64_t)sms * p.mblocks * 128 * Qc;
