@@ -154,6 +154,7 @@ rowidft_pointwise_kernel(const PwParams p) {
 }
 
 int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& p, cudaStream_t st, int* handled);
+static int launch_small_m(const PwParams& p, cudaStream_t st);
 
 extern "C" int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float* Phi, const float* A, const float* Wp,
                                        int64_t w_sn, int64_t w_sm, const float* bias, const float* zprev,

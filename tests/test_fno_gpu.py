@@ -392,3 +392,21 @@ def test_tc_fno_block(B, Ci, Co, H, W, nm, act, skip, mode, tol):
     assert rel_l2(bc.grad, bo.grad) < 2 * tol
     if skip:
         assert rel_l2(wsc.grad, wso.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("B,M,N,H,W", [(2, 1, 256, 16, 16), (3, 13, 64, 32, 64), (2, 8, 70, 8, 12), (1, 16, 33, 16, 16)])
+def test_small_m_pointwise(B, M, N, H, W):
+    """lifting fc1 (few input channels): streaming kernel, forward with GELU + z and backward with GELU'."""
+    plan = fno_plan(DEV, H, W, [min(4, H), min(3, W // 2 + 1)])
+    A = _rand(B, M, H, W, seed=1)
+    Wp = _rand(N, M, seed=2, scale=0.5)
+    bias = _rand(N, seed=3)
+    zprev = _rand(B, N, H, W, seed=4)
+    ref_z = torch.einsum("nm,bmhw->bnhw", Wp.double(), A.double()) + bias.double().view(1, -1, 1, 1)
+    zp = zprev.double().requires_grad_(True)
+    torch.nn.functional.gelu(zp).backward(torch.ones_like(zp))
+    y, z = ops.rowidft_pointwise(plan, 0, None, A.to(DEV), Wp.to(DEV), M, 1, bias.to(DEV), None, B, M, N, 0, True, want_z=True)
+    g, _ = ops.rowidft_pointwise(plan, 1, None, A.to(DEV), Wp.t().contiguous().to(DEV), 1, N, None, zprev.to(DEV), B, M, N, 1, False)
+    assert rel_l2(z, ref_z) < TOL
+    assert rel_l2(y, torch.nn.functional.gelu(ref_z)) < TOL
+    assert rel_l2(g, (ref_z - bias.double().view(1, -1, 1, 1)) * zp.grad) < TOL
