@@ -129,6 +129,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)(layout & 7) << 61;
     return d;
 }
+// The same descriptor as two 32-bit halves, so that an issue loop only has to add to the low word:
+//   lo = start>>4 | (LBO>>4)<<16        hi = SBO>>4 | version(1)<<14 | layout<<29
+__host__ __device__ __forceinline__ constexpr uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout & 7u) << 29);
+}
+// D[tmem] (+)= A * B with descriptors given as (lo, hi) halves
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6;
 
 // instruction descriptor, kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b format TF32(2) [7,10)/[10,13),

@@ -212,9 +212,18 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // One thread issues every tcgen05.mma of the CTA, so the loop bodies are kept to a handful of
+        // integer instructions: descriptor high words are loop constants, low words advance by adds.
         if (lane == 0) {
             int64_t q = 0;
+            const uint32_t a_hi32 = tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B);
+            const uint32_t b_hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
+            const uint32_t s_hi32 = tc::desc_hi(256, tc::LAYOUT_SW32);
             const uint32_t a_lbo = (uint32_t)KC * 128;
+            const uint32_t bh_base = tc::desc_lo(tc::smem_u32(B_hi), 16), bl_base = tc::desc_lo(tc::smem_u32(B_lo), 16);
+            const uint32_t eh_base = tc::desc_lo(tc::smem_u32(E_hi), 16), el_base = tc::desc_lo(tc::smem_u32(E_lo), 16);
+            const uint32_t phi_step = phi_kstep >> 4;
+            const int ksteps = KC / 8;
             for (int64_t it = 0; it < my_tiles; ++it) {
                 const int a = (int)(it & 1);
                 const uint32_t tround = (uint32_t)(it >> 1);
@@ -225,19 +234,17 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 if (spectral) {
                     tc::mbar_wait(phi_bar + a, tround & 1);
                     tc::tc_fence_after_sync();
-                    const uint32_t ph = tc::smem_u32(Phi_s + (uint32_t)a * phi_buf_bytes);
-                    const uint32_t pl = ph + phi_bytes;
+                    uint32_t fh = tc::desc_lo(tc::smem_u32(Phi_s + (uint32_t)a * phi_buf_bytes), 16);
+                    uint32_t fl = fh + (phi_bytes >> 4);
+                    uint32_t eh = eh_base, el = el_base;
                     for (int ks = 0; ks < ksteps2; ++ks) {
-                        const uint64_t eh = tc::make_smem_desc(tc::smem_u32(E_hi) + (uint32_t)ks * 4096, 16, 256, tc::LAYOUT_SW32);
-                        const uint64_t fh = tc::make_smem_desc(ph + (uint32_t)ks * phi_kstep, 16, 256, tc::LAYOUT_SW32);
-                        tc::umma_tf32(tmem_d, eh, fh, p.idesc_spec, started);
+                        tc::umma_tf32_lh(tmem_d, eh, s_hi32, fh, s_hi32, p.idesc_spec, started);
                         started = 1;
                         if (PASSES == 3) {
-                            const uint64_t el = tc::make_smem_desc(tc::smem_u32(E_lo) + (uint32_t)ks * 4096, 16, 256, tc::LAYOUT_SW32);
-                            const uint64_t fl = tc::make_smem_desc(pl + (uint32_t)ks * phi_kstep, 16, 256, tc::LAYOUT_SW32);
-                            tc::umma_tf32(tmem_d, el, fh, p.idesc_spec, 1u);
-                            tc::umma_tf32(tmem_d, eh, fl, p.idesc_spec, 1u);
+                            tc::umma_tf32_lh(tmem_d, el, s_hi32, fh, s_hi32, p.idesc_spec, 1u);
+                            tc::umma_tf32_lh(tmem_d, eh, s_hi32, fl, s_hi32, p.idesc_spec, 1u);
                         }
+                        eh += 4096 >> 4; el += 4096 >> 4; fh += phi_step; fl += phi_step;
                     }
                 }
                 for (int kc = 0; kc < nkc; ++kc, ++q) {
@@ -245,22 +252,19 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     const uint32_t round = (uint32_t)(q / S);
                     tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, round & 1);
                     tc::tc_fence_after_sync();
-                    const uint32_t A_hi = tc::smem_u32(A_st + (uint32_t)s * a_stage_bytes);
-                    const uint32_t A_lo = A_hi + a_bytes;
-                    for (int ks = 0; ks < KC / 8; ++ks) {
-                        const int kg = kc * KC + ks * 8;                         // global k of this step
-                        const uint32_t a_off = (uint32_t)ks * 1024;
-                        const uint32_t b_off = (uint32_t)(kg >> 5) * b_chunk_bytes + (uint32_t)((kg & 31) >> 3) * 32;
-                        const uint64_t ah = tc::make_smem_desc(A_hi + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
-                        const uint64_t bh = tc::make_smem_desc(tc::smem_u32(B_hi) + b_off, 16, 1024, tc::LAYOUT_SW128);
-                        tc::umma_tf32(tmem_d, ah, bh, p.idesc, started);
+                    uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + (uint32_t)s * a_stage_bytes), a_lbo);
+                    uint32_t al = ah + (a_bytes >> 4);
+                    // weight tile: K chunk (kc*KC)/32, 32-byte k-steps inside the 128-byte swizzled rows
+                    const int kg0 = kc * KC;
+                    uint32_t boff = ((uint32_t)(kg0 >> 5) * b_chunk_bytes + (uint32_t)((kg0 & 31) >> 3) * 32) >> 4;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        tc::umma_tf32_lh(tmem_d, ah, a_hi32, bh_base + boff, b_hi32, p.idesc, started);
                         started = 1;
                         if (PASSES == 3) {
-                            const uint64_t al = tc::make_smem_desc(A_lo + a_off, a_lbo, 512, tc::LAYOUT_SW128_BASE32B);
-                            const uint64_t bl = tc::make_smem_desc(tc::smem_u32(B_lo) + b_off, 16, 1024, tc::LAYOUT_SW128);
-                            tc::umma_tf32(tmem_d, al, bh, p.idesc, 1u);
-                            tc::umma_tf32(tmem_d, ah, bl, p.idesc, 1u);
+                            tc::umma_tf32_lh(tmem_d, al, a_hi32, bh_base + boff, b_hi32, p.idesc, 1u);
+                            tc::umma_tf32_lh(tmem_d, ah, a_hi32, bl_base + boff, b_hi32, p.idesc, 1u);
                         }
+                        ah += 1024 >> 4; al += 1024 >> 4; boff += 32 >> 4;   // KC <= 32: stays inside one 32-wide K chunk
                     }
                     tc::umma_commit(empty_bar + s);            // stage reusable once these MMAs have read it
                 }

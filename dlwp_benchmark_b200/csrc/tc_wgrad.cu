@@ -90,30 +90,33 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             }
         }
     } else if (warp == 1) {
+        // single-thread MMA issue: constant descriptor high word, low words advance by adds
         if (lane == 0) {
+            const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
+            const uint32_t lo_delta = raw_bytes >> 4;
+            const uint32_t mb_step = (128u * 128u) >> 4;
             for (int64_t q = 0; q < my_items; ++q) {
                 const int s = (int)(q % S);
                 tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ((uint32_t)(q / S)) & 1);
                 tc::tc_fence_after_sync();
-                const uint32_t hi = tc::smem_u32(St + (uint32_t)s * stage_bytes);
-                const uint32_t lo = hi + raw_bytes;
+                const uint32_t base_lo = tc::desc_lo(tc::smem_u32(St + (uint32_t)s * stage_bytes), 16);
+                const uint32_t dacc = tmem_base + (uint32_t)((int)(q % p.R) * p.mblocks) * (uint32_t)p.Qc;
+                const uint32_t first_acc = q >= p.R ? 1u : 0u;
                 for (int j = 0; j < CH; ++j) {
+                    uint32_t pj = base_lo + (((uint32_t)j * chunk_bytes) >> 4);
+                    uint32_t qj = pj + (p_chunk >> 4);
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t qoff = (uint32_t)j * chunk_bytes + p_chunk + (uint32_t)ks * 32;
-                        const uint64_t bh = tc::make_smem_desc(hi + qoff, 16, 1024, tc::LAYOUT_SW128);
-                        const uint64_t bl = tc::make_smem_desc(lo + qoff, 16, 1024, tc::LAYOUT_SW128);
-                        const uint32_t acc = (q >= p.R || j > 0 || ks > 0) ? 1u : 0u;
+                        const uint32_t acc = (first_acc | (uint32_t)(j > 0) | (uint32_t)(ks > 0));
+                        uint32_t ph = pj, d = dacc;
                         for (int mb = 0; mb < p.mblocks; ++mb) {
-                            const uint32_t poff = (uint32_t)j * chunk_bytes + (uint32_t)mb * 128 * 128 + (uint32_t)ks * 32;
-                            const uint64_t ah = tc::make_smem_desc(hi + poff, 16, 1024, tc::LAYOUT_SW128);
-                            const uint32_t d = tmem_base + (uint32_t)((int)(q % p.R) * p.mblocks + mb) * (uint32_t)p.Qc;
-                            tc::umma_tf32(d, ah, bh, p.idesc, acc);
+                            tc::umma_tf32_lh(d, ph, hi32, qj, hi32, p.idesc, acc);
                             if (PASSES == 3) {
-                                const uint64_t al = tc::make_smem_desc(lo + poff, 16, 1024, tc::LAYOUT_SW128);
-                                tc::umma_tf32(d, al, bh, p.idesc, 1u);
-                                tc::umma_tf32(d, ah, bl, p.idesc, 1u);
+                                tc::umma_tf32_lh(d, ph + lo_delta, hi32, qj, hi32, p.idesc, 1u);
+                                tc::umma_tf32_lh(d, ph, hi32, qj + lo_delta, hi32, p.idesc, 1u);
                             }
+                            ph += mb_step; d += (uint32_t)p.Qc;
                         }
+                        pj += 32 >> 4; qj += 32 >> 4;
                     }
                 }
                 tc::umma_commit(empty_bar + s);
