@@ -97,6 +97,7 @@ struct TcPwParams {
     const float2* Phi; const float* E; const float2* rot;
     int H, W, Mx, R, V, K2, K2pad;
     int tpr_log2;            // log2(threads cooperating on one channel while staging Phi)
+    int bias_mma;            // bias rides in the spare K column of the synthesis operands (E row K2 = 1, Phi col K2 = bias)
 };
 
 // EPI: 0 fwd linear | 1 fwd GELU, also write pre-activation z | 2 fwd GELU | 3 bwd * GELU'(zprev) | 4 bwd plain
@@ -131,9 +132,12 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     uint64_t* tempty_bar = tfull_bar + 2;                              // [2]  accumulator drained by the epilogue
     uint64_t* phi_bar = tempty_bar + 2;                                // [2]  Phi operand staged
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(phi_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(tail + 256);              // [256] bias for the epilogue (zeros when unused); barriers use < 256 B
+    float2* rot_s = reinterpret_cast<float2*>(bias_s + 256);           // [V][Mx] tile phase table
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles_per_b = (int)((p.HW + TP_PX - 1) / TP_PX);
+    const uint32_t tiles_per_b = (uint32_t)((p.HW + TP_PX - 1) / TP_PX);
+    const bool bias_epi = p.bias != nullptr && !p.bias_mma;
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -166,19 +170,33 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
         }
     }
+    for (int idx = tid; idx < 256; idx += TP_THREADS) bias_s[idx] = (bias_epi && idx < p.N) ? __ldg(p.bias + idx) : 0.f;
     if (spectral) {
-        // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo
+        // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
         for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
             const int k = idx >> 7, px = idx & 127;
-            const float v = __ldg(p.E + idx);
+            const float v = (p.bias_mma && k == p.K2) ? 1.0f : __ldg(p.E + idx);
             const float hi = tc::tf32_trunc(v);
             const uint32_t off = tc::sw32_kmajor_off(px, k, 4096u);
             *reinterpret_cast<float*>(E_hi + off) = hi;
             if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = v - hi;
         }
+        for (int idx = tid; idx < p.V * p.Mx; idx += TP_THREADS) rot_s[idx] = __ldg(p.rot + idx);
         // zero both Phi buffers once: the K padding columns are never written again
         for (int idx = tid; idx < (int)(2 * phi_buf_bytes / 16); idx += TP_THREADS)
             reinterpret_cast<float4*>(Phi_s)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias_mma) {
+            __syncthreads();
+            // ... except column K2, which carries the bias (constant over tiles) in both buffers
+            for (int idx = tid; idx < 2 * p.N; idx += TP_THREADS) {
+                const int a = idx >= p.N, n = idx - a * p.N;
+                const float v = __ldg(p.bias + n);
+                const float hi = tc::tf32_trunc(v);
+                const uint32_t off = tc::sw32_kmajor_off(n, p.K2, phi_kstep);
+                *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + off) = hi;
+                if (PASSES == 3) *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + phi_bytes + off) = v - hi;
+            }
+        }
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
@@ -186,27 +204,26 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t first = blockIdx.x, stride = gridDim.x;
-    const int64_t my_tiles = first < p.ntiles ? (p.ntiles - first + stride - 1) / stride : 0;
+    const uint32_t first = blockIdx.x, stride = gridDim.x, ntiles = (uint32_t)p.ntiles;
+    const uint32_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0 && nkc) {
-            int64_t q = 0;
-            for (int64_t it = 0; it < my_tiles; ++it) {
-                const int64_t tile = first + it * stride;
-                const int b = (int)(tile / tiles_per_b);
-                const int64_t p_base = (tile % tiles_per_b) * TP_PX;
-                for (int kc = 0; kc < nkc; ++kc, ++q) {
-                    const int s = (int)(q % S);
-                    const uint32_t round = (uint32_t)(q / S);
-                    tc::mbar_wait(empty_bar + s, (round & 1) ^ 1);
-                    uint8_t* dst = A_st + (uint32_t)s * a_stage_bytes;
+            uint32_t s = 0, ph = 0;                                 // ring position / phase
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t tile = first + it * stride;
+                const uint32_t b = tile / tiles_per_b;
+                const int p_base = (int)((tile - b * tiles_per_b) * TP_PX);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(empty_bar + s, ph ^ 1);
+                    uint8_t* dst = A_st + s * a_stage_bytes;
                     tc::mbar_expect_tx(full_bar + s, a_bytes);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        tc::tma_load_2d(dst + (uint32_t)i * KC * 128, &tmapA, (int)(p_base + 32 * i), b * p.M + kc * KC,
+                        tc::tma_load_2d(dst + (uint32_t)i * KC * 128, &tmapA, p_base + 32 * i, (int)b * p.M + kc * KC,
                                         full_bar + s);
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -215,7 +232,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         // One thread issues every tcgen05.mma of the CTA, so the loop bodies are kept to a handful of
         // integer instructions: descriptor high words are loop constants, low words advance by adds.
         if (lane == 0) {
-            int64_t q = 0;
+            uint32_t s = 0, ph = 0;
             const uint32_t a_hi32 = tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B);
             const uint32_t b_hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t s_hi32 = tc::desc_hi(256, tc::LAYOUT_SW32);
@@ -224,9 +241,9 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const uint32_t eh_base = tc::desc_lo(tc::smem_u32(E_hi), 16), el_base = tc::desc_lo(tc::smem_u32(E_lo), 16);
             const uint32_t phi_step = phi_kstep >> 4;
             const int ksteps = KC / 8;
-            for (int64_t it = 0; it < my_tiles; ++it) {
-                const int a = (int)(it & 1);
-                const uint32_t tround = (uint32_t)(it >> 1);
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t a = it & 1;
+                const uint32_t tround = it >> 1;
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
                 tc::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + (uint32_t)a * (uint32_t)p.N;
@@ -247,12 +264,10 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         eh += 4096 >> 4; el += 4096 >> 4; fh += phi_step; fl += phi_step;
                     }
                 }
-                for (int kc = 0; kc < nkc; ++kc, ++q) {
-                    const int s = (int)(q % S);
-                    const uint32_t round = (uint32_t)(q / S);
-                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, round & 1);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
                     tc::tc_fence_after_sync();
-                    uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + (uint32_t)s * a_stage_bytes), a_lbo);
+                    uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + s * a_stage_bytes), a_lbo);
                     uint32_t al = ah + (a_bytes >> 4);
                     // weight tile: K chunk (kc*KC)/32, 32-byte k-steps inside the 128-byte swizzled rows
                     const int kg0 = kc * KC;
@@ -267,6 +282,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         ah += 1024 >> 4; al += 1024 >> 4; boff += 32 >> 4;   // KC <= 32: stays inside one 32-wide K chunk
                     }
                     tc::umma_commit(empty_bar + s);            // stage reusable once these MMAs have read it
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
                 tc::umma_commit(tfull_bar + a);                // accumulator of this tile complete
             }
@@ -278,35 +294,74 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
         const int cpart = wk >> 2;                             // which quarter of the columns this warp drains
         const int ncol_part = ((p.N + 3) / 4 + 3) & ~3;        // columns per part (multiple of 4)
-        int64_t q_split = 0;
+        const int c_begin = cpart * ncol_part;
+        const int c_end = min(p.N, c_begin + ncol_part);
+        uint32_t sp_s = 0, sp_ph = 0;                          // split-pass ring position / phase
+        // Phi staging geometry (tile-invariant): tpr threads cooperate on output channel n_st
+        const int tpr = 1 << p.tpr_log2;
+        const int n_st = wtid >> p.tpr_log2, sub = wtid & (tpr - 1);
+        const int per_n = p.R * p.Mx;
+        const bool st_active = spectral && n_st < p.N;
+        const int64_t HW = p.HW;
+        const uint64_t hw_bytes = (uint64_t)p.HW * 4;
 
-        auto prepare_tile = [&](int64_t it) {
+        // Phi elements of the first staging round are fetched one tile ahead (registers), so that their global-load
+        // latency is hidden behind the epilogue of the previous tile
+        float2 fpre[4];
+        // tile -> (sample b, first image row y0, 128-px segment v of the row); V == 1: a tile is R whole rows
+        const uint32_t Vseg = (uint32_t)p.V, Rrows = (uint32_t)p.R;
+        auto phi_src = [&](uint32_t it, uint32_t& v) -> const float2* {
+            const uint32_t tile = first + it * stride;
+            const uint32_t b = tile / tiles_per_b;
+            const uint32_t t_in = tile - b * tiles_per_b;
+            uint32_t y0;
+            if (Vseg == 1) { y0 = t_in * Rrows; v = 0; }
+            else { y0 = t_in / Vseg; v = t_in - y0 * Vseg; }
+            return p.Phi + ((size_t)(b * (uint32_t)p.N + (uint32_t)n_st) * (uint32_t)p.H + y0) * (uint32_t)p.Mx;   // R*Mx contiguous complex
+        };
+        auto prefetch_phi = [&](uint32_t it) {
+            if (st_active) {
+                uint32_t v;
+                const float2* src = phi_src(it, v);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rem = sub + u * tpr;
+                    fpre[u] = rem < per_n ? __ldg(src + rem) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        auto prepare_tile = [&](uint32_t it) {
             if (spectral) {
-                const int64_t tile = first + it * stride;
-                const int b = (int)(tile / tiles_per_b);
-                const int64_t p_base = (tile % tiles_per_b) * TP_PX;
-                const int y0 = (int)(p_base / p.W);
-                const int v = (int)((p_base % p.W) >> 7);
-                uint8_t* ph = Phi_s + (uint32_t)(it & 1) * phi_buf_bytes;
-                uint8_t* pl = ph + phi_bytes;
-                const int per_n = p.R * p.Mx;
-                // tpr threads cooperate on one output channel n (tpr = power of two, tpr * N >= worker threads)
-                const int n = wtid >> p.tpr_log2, sub = wtid & ((1 << p.tpr_log2) - 1);
-                if (n < p.N) {
-                    const float2* src = p.Phi + (((int64_t)b * p.N + n) * p.H + y0) * p.Mx;   // R*Mx contiguous complex
-                    for (int rem = sub; rem < per_n; rem += (1 << p.tpr_log2)) {
-                        int r = 0, kx = rem;
-                        while (kx >= p.Mx) { kx -= p.Mx; ++r; }
-                        float2 f = __ldg(src + rem);
-                        if (p.V > 1) {
-                            const float2 c = __ldg(p.rot + v * p.Mx + kx);
-                            f = make_float2(f.x * c.x - f.y * c.y, f.x * c.y + f.y * c.x);
+                uint8_t* ph = Phi_s + (it & 1) * phi_buf_bytes + (uint32_t)n_st * 32u;
+                if (st_active) {
+                    uint32_t v;
+                    const float2* src = phi_src(it, v);
+                    const float2* rt = rot_s + v * p.Mx;                                           // V > 1 implies R == 1: kx = rem
+                    for (int r0 = sub; r0 < per_n; r0 += 4 * tpr) {
+                        float2 f[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int rem = r0 + u * tpr;
+                            if (r0 == sub) f[u] = fpre[u];
+                            else f[u] = rem < per_n ? __ldg(src + rem) : make_float2(0.f, 0.f);
                         }
-                        const uint32_t off = tc::sw32_kmajor_off(n, 2 * rem, phi_kstep);    // kk = r*2Mx + 2kx = 2*rem
-                        const float2 h = make_float2(tc::tf32_trunc(f.x), tc::tf32_trunc(f.y));
-                        *reinterpret_cast<float2*>(ph + off) = h;
-                        if (PASSES == 3) *reinterpret_cast<float2*>(pl + off) = make_float2(f.x - h.x, f.y - h.y);
-                        (void)r;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int rem = r0 + u * tpr;
+                            if (rem < per_n) {
+                                float2 g = f[u];
+                                if (p.V > 1) {
+                                    const float2 c = rt[rem];
+                                    g = make_float2(f[u].x * c.x - f[u].y * c.y, f[u].x * c.y + f[u].y * c.x);
+                                }
+                                // kk = 2*rem: k-step rem/4, 16-byte half (rem/2)&1 XOR swizzle bit, 8-byte slot rem&1
+                                const uint32_t off = (uint32_t)(rem >> 2) * phi_kstep +
+                                                     (uint32_t)(((((rem >> 1) & 1) ^ ((n_st >> 2) & 1)) << 4) | ((rem & 1) << 3));
+                                const float2 h = make_float2(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y));
+                                *reinterpret_cast<float2*>(ph + off) = h;
+                                if (PASSES == 3) *reinterpret_cast<float2*>(ph + phi_bytes + off) = make_float2(g.x - h.x, g.y - h.y);
+                            }
+                        }
                     }
                 }
                 tc::fence_proxy_async_smem();
@@ -314,12 +369,10 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 if (lane == 0) tc::mbar_arrive(phi_bar + (it & 1));
             }
             if (PASSES == 3) {
-                for (int kc = 0; kc < nkc; ++kc, ++q_split) {
-                    const int s = (int)(q_split % S);
-                    const uint32_t round = (uint32_t)(q_split / S);
-                    tc::mbar_wait(full_bar + s, round & 1);
-                    float4* ah = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes);
-                    float4* al = reinterpret_cast<float4*>(A_st + (uint32_t)s * a_stage_bytes + a_bytes);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(full_bar + sp_s, sp_ph);
+                    float4* ah = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes);
+                    float4* al = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + a_bytes);
                     for (int idx = wtid; idx < (int)(a_bytes / 16); idx += TP_WTHREADS) {
                         const float4 v = ah[idx];
                         const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
@@ -328,52 +381,103 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(split_bar + s);
+                    if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
                 }
             }
         };
 
-        if (my_tiles > 0) prepare_tile(0);
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            if (it + 1 < my_tiles) prepare_tile(it + 1);
-            const int64_t tile = first + it * stride;
-            const int b = (int)(tile / tiles_per_b);
-            const int64_t p_base = (tile % tiles_per_b) * TP_PX;
-            const int a = (int)(it & 1);
-            const uint32_t tround = (uint32_t)(it >> 1);
+        if (my_tiles > 0) {
+            prefetch_phi(0);
+            prepare_tile(0);
+            if (my_tiles > 1) prefetch_phi(1);
+        }
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t tile = first + it * stride;
+            const uint32_t b = tile / tiles_per_b;
+            const uint32_t p_base = (tile - b * tiles_per_b) * TP_PX;
+            const int64_t pp = (int64_t)p_base + quarter * 32 + lane;
+            const bool in_range = pp < HW;
+            float zp[16];
+            if (EPI == 3) {
+                // GELU' inputs of the first column chunk: in flight while the next tile is prepared
+                const float* zsrc = p.zprev + ((int64_t)b * p.N + c_begin) * HW + pp;
+                const int nv = min(16, c_end - c_begin);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    zp[j] = (in_range && j < nv) ? __ldg(zsrc) : 0.f;
+                    zsrc += HW;
+                }
+            }
+            if (it + 1 < my_tiles) {
+                prepare_tile(it + 1);
+                if (it + 2 < my_tiles) prefetch_phi(it + 2);
+            }
+            const uint32_t a = it & 1;
+            const uint32_t tround = it >> 1;
             tc::mbar_wait(tfull_bar + a, tround & 1);
             tc::tc_fence_after_sync();
-            const int64_t pp = p_base + quarter * 32 + lane;
-            const bool in_range = pp < p.HW;
-            const int c_begin = cpart * ncol_part;
-            const int c_end = min(p.N, c_begin + ncol_part);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N;
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 const int nv = min(16, c_end - c0);
-                const int64_t off0 = ((int64_t)b * p.N + c0) * p.HW + pp;
+                const int64_t off0 = ((int64_t)b * p.N + c0) * HW + pp;
                 uint32_t r[16];
-                float zp[16], bv[16];
-                // issue every global load of this chunk before touching TMEM (independent loads in flight)
-                if (EPI == 3) {
+                if (EPI == 3 && c0 != c_begin) {
                     const float* zsrc = p.zprev + off0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) zp[j] = (in_range && j < nv) ? __ldg(zsrc + (int64_t)j * p.HW) : 0.f;
+                    for (int j = 0; j < 16; ++j) {
+                        zp[j] = (in_range && j < nv) ? __ldg(zsrc) : 0.f;
+                        zsrc += HW;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) bv[j] = (p.bias && j < nv) ? __ldg(p.bias + c0 + j) : 0.f;
                 tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
-                if (in_range) {
+                if (bias_epi) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + j);   // c0 % 4 == 0; bias_s zero-padded
+                        r[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + bq.x);
+                        r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + bq.y);
+                        r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + bq.z);
+                        r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + bq.w);
+                    }
+                }
+                if (in_range && nv == 16) {
+                    // fast path (whole chunk valid): straight-line code, 16 independent GELU chains in flight
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (EPI == 1) {
+                        uint64_t za = reinterpret_cast<uint64_t>(p.z_out + off0);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            asm volatile("st.global.f32 [%0], %1;" ::"l"(za), "f"(v[j]) : "memory");
+                            za += hw_bytes;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (EPI == 1 || EPI == 2) v[j] = gelu_f(v[j]);
+                        if (EPI == 3) v[j] *= gelu_grad_f(zp[j]);
+                    }
+                    uint64_t ya = reinterpret_cast<uint64_t>(p.y_out + off0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        asm volatile("st.global.f32 [%0], %1;" ::"l"(ya), "f"(v[j]) : "memory");
+                        ya += hw_bytes;
+                    }
+                } else if (in_range) {
                     float* ydst = p.y_out + off0;
                     float* zdst = (EPI == 1) ? p.z_out + off0 : nullptr;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (j < nv) {
-                            float v = __uint_as_float(r[j]) + bv[j];
-                            if (EPI == 1) zdst[(int64_t)j * p.HW] = v;
+                            float v = __uint_as_float(r[j]);
+                            if (EPI == 1) { *zdst = v; zdst += HW; }
                             if (EPI == 1 || EPI == 2) v = gelu_f(v);
                             if (EPI == 3) v *= gelu_grad_f(zp[j]);
-                            ydst[(int64_t)j * p.HW] = v;
+                            *ydst = v;
+                            ydst += HW;
                         }
                     }
                 }
@@ -404,7 +508,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     if (HW % 4 != 0) return 0;
     if (has_pw && ((reinterpret_cast<uintptr_t>(q.A) & 15) != 0 || (int64_t)q.B * M >= (1LL << 31))) return 0;
     const sb200_tc_tables* tt = (const sb200_tc_tables*)plan->tc;
-    if (has_spec && (tt == nullptr || (reinterpret_cast<uintptr_t>(q.Phi) & 7) != 0)) return 0;
+    if (has_spec && (tt == nullptr || (reinterpret_cast<uintptr_t>(q.Phi) & 7) != 0 || tt->V * q.Mx > 256)) return 0;
     const int passes = g_tc_mode;
 
     TcPwParams p;
@@ -424,6 +528,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     if (has_spec) {
         p.Phi = q.Phi; p.E = tt->E[pass]; p.rot = tt->rot;
         p.R = tt->R; p.V = tt->V; p.K2 = tt->K2; p.K2pad = tt->K2pad;
+        p.bias_mma = (passes == 3 && q.bias != nullptr && tt->K2 < tt->K2pad) ? 1 : 0;
     }
 
     const size_t mult = passes == 3 ? 2 : 1;
@@ -431,7 +536,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     const size_t b_bytes = has_pw ? ((((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * mult) : 0;
     const size_t e_bytes = has_spec ? (size_t)(p.K2pad / 8) * 4096 * mult : 0;
     const size_t phi_bytes = has_spec ? ((((size_t)(p.K2pad / 8) * N * 32 + 1023) & ~(size_t)1023) * mult * 2) : 0;
-    const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512;
+    const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512 + 1024 + 2048;   // + barriers, bias_s, rot_s
     int stages = has_pw ? 6 : 1;
     while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
     if (fixed + stages * a_stage > 227 * 1024) {

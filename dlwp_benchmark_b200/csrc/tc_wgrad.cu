@@ -17,9 +17,11 @@ constexpr int TW_THREADS = 32 * (2 + TW_WORKER_WARPS);
 
 struct TcWgParams {
     int Pc, Qc;              // channels of the A-side / B-side tensors
+    int Qn;                  // UMMA N: Qc, or Qc + 16 when a constant ones-row is appended (bias gradient = sum of the A side)
     int mblocks;             // ceil(Pc / 128)
     int CH;                  // 32-pixel chunks per pipeline item
     int stages;
+    int debug;               // bring-up switches (SB200_WG_DEBUG): 1 = skip the MMAs (measures the TMA ring alone)
     int R;                   // rotating TMEM accumulators (shortens each tensor-core accumulation chain)
     int64_t HW;
     int64_t items_per_b, nitems;
@@ -34,7 +36,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int S = p.stages, CH = p.CH;
     const uint32_t p_chunk = (uint32_t)p.Pc * 128, q_chunk = (uint32_t)p.Qc * 128;
-    const uint32_t chunk_bytes = p_chunk + q_chunk;                    // [P rows | Q rows], 128 B per row
+    const uint32_t ones_bytes = (uint32_t)(p.Qn - p.Qc) * 128;         // constant rows [1,1,...; 0...] behind the Q rows
+    const uint32_t chunk_bytes = p_chunk + q_chunk + ones_bytes;       // [P rows | Q rows | ones], 128 B per row
+    const uint32_t tma_bytes = (uint32_t)CH * (p_chunk + q_chunk);
     const uint32_t raw_bytes = (uint32_t)CH * chunk_bytes;
     const uint32_t stage_bytes = raw_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
     uint8_t* St = base;
@@ -62,6 +66,21 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
         tc::tmem_alloc(tmem_slot, p.tmem_cols);
         tc::tmem_relinquish();
     }
+    if (ones_bytes) {
+        // row Qc of the B operand is all ones (hi part; its lo part and the other padding rows are zero) in every
+        // chunk of every stage: D[:, Qc] = sum over pixels of the A side = the bias gradient.  TMA never writes here
+        // and the split pass maps (1, 0) to itself.
+        const int per_blk = (int)(ones_bytes / 4);
+        const int nblk = S * CH * (PASSES == 3 ? 2 : 1);
+        for (int idx = tid; idx < nblk * per_blk; idx += TW_THREADS) {
+            const int blk = idx / per_blk, e = idx % per_blk;
+            const int half = blk / (S * CH), sc = blk % (S * CH);
+            uint8_t* dst = St + (uint32_t)(sc / CH) * stage_bytes + (uint32_t)half * raw_bytes + (uint32_t)(sc % CH) * chunk_bytes +
+                           p_chunk + q_chunk;
+            reinterpret_cast<float*>(dst)[e] = (half == 0 && e < 32) ? 1.0f : 0.0f;
+        }
+        tc::fence_proxy_async_smem();
+    }
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
@@ -75,18 +94,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int64_t q = 0; q < my_items; ++q) {
-                const int64_t item = i0 + q;
-                const int b = (int)(item / p.items_per_b);
-                const int64_t px0 = (item % p.items_per_b) * 32 * CH;
-                const int s = (int)(q % S);
-                tc::mbar_wait(empty_bar + s, (((uint32_t)(q / S)) & 1) ^ 1);
-                uint8_t* dst = St + (uint32_t)s * stage_bytes;
-                tc::mbar_expect_tx(full_bar + s, raw_bytes);
+            uint32_t s = 0, ph = 0;
+            const uint32_t items_per_b = (uint32_t)p.items_per_b;
+            for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
+                const uint32_t item = (uint32_t)i0 + q;
+                const uint32_t b = item / items_per_b;
+                const int px0 = (int)((item - b * items_per_b) * 32u * (uint32_t)CH);
+                tc::mbar_wait(empty_bar + s, ph ^ 1);
+                uint8_t* dst = St + s * stage_bytes;
+                tc::mbar_expect_tx(full_bar + s, tma_bytes);
                 for (int j = 0; j < CH; ++j) {
-                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes, &tmapP, (int)(px0 + 32 * j), b * p.Pc, full_bar + s);
-                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes + p_chunk, &tmapQ, (int)(px0 + 32 * j), b * p.Qc, full_bar + s);
+                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes, &tmapP, px0 + 32 * j, (int)b * p.Pc, full_bar + s);
+                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes + p_chunk, &tmapQ, px0 + 32 * j, (int)b * p.Qc, full_bar + s);
                 }
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -95,31 +116,38 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t lo_delta = raw_bytes >> 4;
             const uint32_t mb_step = (128u * 128u) >> 4;
-            for (int64_t q = 0; q < my_items; ++q) {
-                const int s = (int)(q % S);
-                tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ((uint32_t)(q / S)) & 1);
+            uint32_t s = 0, ph = 0, ra = 0;
+            for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
+                tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
                 tc::tc_fence_after_sync();
-                const uint32_t base_lo = tc::desc_lo(tc::smem_u32(St + (uint32_t)s * stage_bytes), 16);
-                const uint32_t dacc = tmem_base + (uint32_t)((int)(q % p.R) * p.mblocks) * (uint32_t)p.Qc;
-                const uint32_t first_acc = q >= p.R ? 1u : 0u;
+                const uint32_t base_lo = tc::desc_lo(tc::smem_u32(St + s * stage_bytes), 16);
+                const uint32_t dacc = tmem_base + ra * (uint32_t)(p.mblocks * p.Qn);
+                const uint32_t first_acc = q >= (uint32_t)p.R ? 1u : 0u;
+                if (p.debug & 1) {
+                    tc::mbar_arrive(empty_bar + s);
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 for (int j = 0; j < CH; ++j) {
                     uint32_t pj = base_lo + (((uint32_t)j * chunk_bytes) >> 4);
                     uint32_t qj = pj + (p_chunk >> 4);
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t acc = (first_acc | (uint32_t)(j > 0) | (uint32_t)(ks > 0));
-                        uint32_t ph = pj, d = dacc;
+                        uint32_t ph_ = pj, d = dacc;
                         for (int mb = 0; mb < p.mblocks; ++mb) {
-                            tc::umma_tf32_lh(d, ph, hi32, qj, hi32, p.idesc, acc);
+                            tc::umma_tf32_lh(d, ph_, hi32, qj, hi32, p.idesc, acc);
                             if (PASSES == 3) {
-                                tc::umma_tf32_lh(d, ph + lo_delta, hi32, qj, hi32, p.idesc, 1u);
-                                tc::umma_tf32_lh(d, ph, hi32, qj + lo_delta, hi32, p.idesc, 1u);
+                                tc::umma_tf32_lh(d, ph_ + lo_delta, hi32, qj, hi32, p.idesc, 1u);
+                                tc::umma_tf32_lh(d, ph_, hi32, qj + lo_delta, hi32, p.idesc, 1u);
                             }
-                            ph += mb_step; d += (uint32_t)p.Qc;
+                            ph_ += mb_step; d += (uint32_t)p.Qn;
                         }
                         pj += 32 >> 4; qj += 32 >> 4;
                     }
                 }
                 tc::umma_commit(empty_bar + s);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                if (++ra == (uint32_t)p.R) ra = 0;
             }
             tc::umma_commit(done_bar);
         }
@@ -127,11 +155,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
         const int wk = warp - 2;
         const int wtid = tid - 64;
         if (PASSES == 3) {
-            for (int64_t q = 0; q < my_items; ++q) {
-                const int s = (int)(q % S);
-                tc::mbar_wait(full_bar + s, ((uint32_t)(q / S)) & 1);
-                float4* ah = reinterpret_cast<float4*>(St + (uint32_t)s * stage_bytes);
-                float4* al = reinterpret_cast<float4*>(St + (uint32_t)s * stage_bytes + raw_bytes);
+            uint32_t s = 0, ph = 0;
+            for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
+                tc::mbar_wait(full_bar + s, ph);
+                float4* ah = reinterpret_cast<float4*>(St + s * stage_bytes);
+                float4* al = reinterpret_cast<float4*>(St + s * stage_bytes + raw_bytes);
                 for (int idx = wtid; idx < (int)(raw_bytes / 16); idx += 32 * TW_WORKER_WARPS) {
                     const float4 v = ah[idx];
                     const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
@@ -141,6 +169,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                 tc::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(split_bar + s);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }
         // ---- epilogue: partial product -> workspace (zeros when this CTA had no work) ----
@@ -150,21 +179,21 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
         }
         const int quarter = warp & 3;
         const int cpart = wk >> 2;                                   // 4 column parts
-        const int ncol_part = ((p.Qc + 3) / 4 + 3) & ~3;
+        const int ncol_part = ((p.Qn + 3) / 4 + 3) & ~3;
         const int c_begin = cpart * ncol_part;
-        const int c_end = min(p.Qc, c_begin + ncol_part);
-        float* wsc = p.ws + (int64_t)blockIdx.x * p.mblocks * 128 * p.Qc;
+        const int c_end = min(p.Qn, c_begin + ncol_part);
+        float* wsc = p.ws + (int64_t)blockIdx.x * p.mblocks * 128 * p.Qn;
+        const int nacc = (int)(my_items < p.R ? my_items : p.R);
         for (int mb = 0; mb < p.mblocks; ++mb) {
             const int row = mb * 128 + quarter * 32 + lane;
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float r[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = 0.f;
-                const int nacc = (int)(my_items < p.R ? my_items : p.R);
                 for (int ra = 0; ra < nacc; ++ra) {                   // fp32 sum of the rotating accumulators
                     uint32_t t[16];
                     tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                               (uint32_t)((ra * p.mblocks + mb) * p.Qc + c0), t);
+                                               (uint32_t)((ra * p.mblocks + mb) * p.Qn + c0), t);
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] += __uint_as_float(t[j]);
@@ -172,7 +201,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                 if (row < p.Pc) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < c_end) wsc[(int64_t)row * p.Qc + c0 + j] = r[j];
+                        if (c0 + j < c_end) wsc[(int64_t)row * p.Qn + c0 + j] = r[j];
                 }
             }
         }
@@ -182,21 +211,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// out[(transpose ? q*Pc + pch : pch*Qc + q)] = sum_c ws[c][pch][q]   (ws rows padded to mblocks*128)
+// out[(transpose ? q*Pc + pch : pch*Qc + q)] = sum_c ws[c][pch][q]   (ws rows padded to mblocks*128, Qn columns);
+// column Qc (when Qn > Qc) is the ones-row product = the bias gradient of the A side.
 // one warp per output element: lanes stride over the partials, fixed-order shuffle reduction (deterministic)
 __global__ void __launch_bounds__(256)
-tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int Pc, int Qc, int prow_pad, int nparts,
-                       int transpose) {
+tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ gbias, int Pc, int Qc,
+                       int Qn, int prow_pad, int nparts, int transpose) {
     const int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (e >= (int64_t)Pc * Qc) return;
-    const int pch = (int)(e / Qc), q = (int)(e % Qc);
-    const int64_t part = (int64_t)prow_pad * Qc;
+    const int cols = Qn > Qc ? Qc + 1 : Qc;
+    if (e >= (int64_t)Pc * cols) return;
+    const int pch = (int)(e / cols), q = (int)(e % cols);
+    const int64_t part = (int64_t)prow_pad * Qn;
+    const float* src = ws + (int64_t)pch * Qn + q;
     float s = 0.f;
-    for (int c = lane; c < nparts; c += 32) s += __ldg(ws + c * part + e);
+    for (int c = lane; c < nparts; c += 32) s += __ldg(src + c * part);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) out[transpose ? (int64_t)q * Pc + pch : e] = s;
+    if (lane == 0) {
+        if (q == Qc) { if (gbias) gbias[pch] = s; }
+        else out[transpose ? (int64_t)q * Pc + pch : (int64_t)pch * Qc + q] = s;
+    }
 }
 
 // per-channel sums: out[c] = sum_{b,p} g[b,c,p]   (one warp per (b,c) row, then a fixed-order sum over b)
@@ -254,7 +289,7 @@ int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
     int Pc, Qc, tr;
     if (sb200_get_tc_mode() == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
     const int mblocks = (Pc + 127) / 128;
-    return (int64_t)tw_num_sms() * mblocks * 128 * Qc + (int64_t)B * Cout;
+    return (int64_t)tw_num_sms() * mblocks * 128 * (Qc + 16) + (int64_t)B * Cout;
 }
 
 int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
@@ -270,22 +305,30 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
 
     TcWgParams p;
     p.Pc = Pc; p.Qc = Qc; p.mblocks = (Pc + 127) / 128; p.HW = HW;
-    const size_t chunk = (size_t)(Pc + Qc) * 128;
-    p.CH = chunk <= 16384 ? 2 : 1;
+    // bias gradient = sum over pixels of g: free from the MMA when g is the A side (ones-row appended to the B side)
+    const bool bias_mma = passes == 3 && gbias != nullptr && tr == 0 && Qc + 16 <= 256 && p.mblocks * (Qc + 16) <= 512;
+    p.Qn = bias_mma ? Qc + 16 : Qc;
+    const size_t chunk = (size_t)(Pc + p.Qn) * 128;
+    static const int env_ch = getenv("SB200_WG_CH") ? atoi(getenv("SB200_WG_CH")) : 0;
+    static const int env_st = getenv("SB200_WG_STAGES") ? atoi(getenv("SB200_WG_STAGES")) : 0;
+    static const int env_dbg = getenv("SB200_WG_DEBUG") ? atoi(getenv("SB200_WG_DEBUG")) : 0;
+    p.debug = env_dbg;
+    p.CH = env_ch > 0 ? env_ch : 1;
     const size_t stage = chunk * p.CH * (passes == 3 ? 2 : 1);
-    int stages = 4;
-    while (stages > 1 && 1024 + stages * stage + 16384 + 256 > 200 * 1024) --stages;
+    int stages = env_st > 0 ? env_st : 8;
+    while (stages > 1 && 1024 + stages * stage + 16384 + 256 > 210 * 1024) --stages;
     if (1024 + stages * stage + 16384 + 256 > 227 * 1024) return 0;
     p.stages = stages;
     const size_t smem = 1024 + stages * stage + 16384 + 256;
     p.items_per_b = (HW + 32 * p.CH - 1) / (32 * p.CH);
     p.nitems = p.items_per_b * B;
-    p.idesc = tc::make_idesc_tf32(128, Qc, 0, 0);
-    p.R = 512 / (p.mblocks * Qc);
+    if (p.nitems >= (1LL << 31)) return 0;
+    p.idesc = tc::make_idesc_tf32(128, p.Qn, 0, 0);
+    p.R = 512 / (p.mblocks * p.Qn);
     if (p.R > 8) p.R = 8;
     if (p.R < 1) p.R = 1;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(p.R * p.mblocks * Qc)) cols <<= 1;
+    while (cols < (uint32_t)(p.R * p.mblocks * p.Qn)) cols <<= 1;
     p.tmem_cols = cols;
     p.ws = workspace;
     const int sms = tw_num_sms();
@@ -302,11 +345,12 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
         tc_wgrad_kernel<1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
     }
     SB_LAUNCH_CHECK();
-    const int64_t E = (int64_t)Pc * Qc;
-    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 8), 256, 0, st>>>(workspace, gW, Pc, Qc, p.mblocks * 128, (int)grid, tr);
+    const int64_t E = (int64_t)Pc * (bias_mma ? Qc + 1 : Qc);
+    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 8), 256, 0, st>>>(workspace, gW, bias_mma ? gbias : nullptr, Pc, Qc, p.Qn,
+                                                                       p.mblocks * 128, (int)grid, tr);
     SB_LAUNCH_CHECK();
-    if (gbias) {
-        float* part = workspace + (int64_t)sms * p.mblocks * 128 * Qc;
+    if (gbias && !bias_mma) {
+        float* part = workspace + (int64_t)sms * p.mblocks * 128 * (Qc + 16);
         const int64_t rows = (int64_t)B * Cout;
         channel_rowsum_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(g, part, rows, HW);
         SB_LAUNCH_CHECK();
