@@ -30,6 +30,8 @@ SIGNATURES = {
     "sb200_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "sb200_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "sb200_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "sb200_analysis_scratch": (_i64, [_vp, _i64]),
+    "sb200_analysis": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "sb200_modes_gemm": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
     "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),

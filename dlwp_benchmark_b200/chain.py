@@ -57,7 +57,7 @@ class FusedChainFn(torch.autograd.Function):
             want_z = acts[l] and need_grad
             Xh = None
             if spec[l]:
-                Xh = ops.coldft_fwd(plan, 0, ops.rowdft_fwd(plan, 0, h))
+                Xh = ops.analysis(plan, 0, h)
                 Phi = ops.coldft_inv(plan, 0, ops.mix_fwd(Xh, Ws[l]))
                 y, z = ops.rowidft_pointwise(plan, 0, Phi, h, Ps[l], M, 1, bs[l], None, B, M, N, 0, acts[l],
                                              want_z=want_z)
@@ -108,7 +108,7 @@ class FusedChainFn(torch.autograd.Function):
                 grads[3 * l + 2] = gb.reshape(ctx.shapes[l][1])
             gYh = None
             if spec[l]:
-                gYh = ops.coldft_fwd(plan, 1, ops.rowdft_fwd(plan, 1, gz))
+                gYh = ops.analysis(plan, 1, gz)
                 grads[3 * l] = ops.mix_bwd_weight(Xhs[l], gYh)
             # ---- data gradient (fused with GELU' of the previous layer) ----
             if l > 0 or ctx.needs_input_grad[0]:

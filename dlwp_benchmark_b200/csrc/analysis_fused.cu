@@ -1,0 +1,274 @@
+// Fused truncated 2-D analysis for small grids:  x[img, H, W] (real)  ->  Xh[img, My, Mx] (complex)
+//
+//   T[y, kx]   = sum_x  x[y, x] * rowF[x, kx]            (real -> complex, along W)
+//   Xh[ky, kx] = sum_y  colF[ky, y] * T[y, kx]            (complex, along H)
+//
+// replaces torch.fft.rfftn + fftshift + slice of neuralop SpectralConv.forward (and, with the pass-1
+// tables, the adjoint of irfftn in its backward) without ever writing the row-transformed spectrum T
+// to HBM: a persistent CTA streams groups of 256 image rows (G = 256 / H whole images) through a
+// two-deep TMA ring, four "row" warps turn a group into T in shared memory and five "column" warps
+// finish the previous group, so the only HBM traffic is x once (+ the tiny Xh).
+//
+// Row stage: one thread owns two image rows and uses the real-input symmetry
+//   Re T[k] = sum_{n=0}^{W/2} (x[n] + x[W-n]) cos,   Im T[k] = -sum_{n=1}^{W/2-1} (x[n] - x[W-n]) sin
+// which halves the FFMAs; twiddles are warp-uniform (broadcast LDS.128), image rows are read from the
+// 128B-swizzled TMA tile with conflict-free LDS.128.  Exact fp32 FFMA arithmetic (no tensor cores:
+// with N = 2*Mx <= 34 output columns a 3xTF32 MMA would be shared-memory-bandwidth bound).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+constexpr int AF_ROWS = 256;                 // image rows per group
+constexpr int AF_RTHREADS = 128;             // row-stage threads (2 rows each)
+constexpr int AF_CTHREADS = 160;             // column-stage threads
+constexpr int AF_THREADS = AF_RTHREADS + AF_CTHREADS;
+
+struct AfParams {
+    const float2* rowF;      // [W][MX]
+    const float2* colF;      // [My][H]
+    float2* Xh;              // [nimg][My][MX]
+    int64_t nimg;
+    int H, W, My, G;
+    int ngroups;
+};
+
+__device__ __forceinline__ float4 af_lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MX>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams p) {
+    constexpr int MXE = (MX + 1) & ~1;                   // MX rounded up to even: accumulators are fp32x2 pairs over k
+    constexpr int TWS = 2 * MXE;                         // floats per row-twiddle record [C0..C(MX-1), 0?, S0..S(MX-1), 0?]
+    static_assert(TWS % 4 == 0, "row-twiddle records are read as float4");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
+    // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int H = p.H, W = p.W, My = p.My;
+    const int Myp = (My + 3) & ~3;
+    const uint32_t half_bytes = AF_ROWS * 128;           // one 32-float column block of a group
+    const uint32_t xbuf_bytes = (uint32_t)(W / 32) * half_bytes;
+    uint8_t* xbuf = base;                                                         // [2][W/32][256][128 B]
+    float2* Tbuf = reinterpret_cast<float2*>(xbuf + 2 * xbuf_bytes);              // [2][256][MX]
+    float* rtw = reinterpret_cast<float*>(Tbuf + 2 * AF_ROWS * MX);              // [W/2+1][TWS]
+    float2* ctw = reinterpret_cast<float2*>(rtw + (W / 2 + 1) * TWS);            // [H][Myp]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ctw + (size_t)H * Myp);
+    uint64_t* xfull = bars;          // [2] TMA landed
+    uint64_t* tfull = bars + 2;      // [2] T written by the row warps
+    uint64_t* tempty = bars + 4;     // [2] T consumed by the column warps
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmapX);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(xfull + i, 1);
+            tc::mbar_init(tfull + i, AF_RTHREADS);
+            tc::mbar_init(tempty + i, AF_CTHREADS);
+        }
+        tc::fence_barrier_init();
+    }
+    // twiddle tables -> shared memory
+    for (int idx = tid; idx < (W / 2 + 1) * TWS; idx += AF_THREADS) {
+        const int n = idx / TWS, j = idx % TWS;
+        float v = 0.f;
+        if (j < MX) v = __ldg(&p.rowF[(size_t)n * MX + j].x);
+        else if (j >= MXE && j - MXE < MX) v = __ldg(&p.rowF[(size_t)n * MX + (j - MXE)].y);
+        rtw[idx] = v;
+    }
+    for (int idx = tid; idx < H * Myp; idx += AF_THREADS) {
+        const int y = idx / Myp, k = idx % Myp;
+        ctw[idx] = k < My ? __ldg(p.colF + (size_t)k * H + y) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_groups = first < p.ngroups ? (p.ngroups - first + stride - 1) / stride : 0;
+    const int nhalf = W / 32;
+
+    auto issue = [&](int i) {    // TMA loads of local group i into buffer i & 1 (one thread)
+        const int b = i & 1;
+        const int row0 = (first + i * stride) * AF_ROWS;
+        tc::mbar_expect_tx(xfull + b, xbuf_bytes);
+        for (int h = 0; h < nhalf; ++h)
+            tc::tma_load_2d(xbuf + (uint32_t)b * xbuf_bytes + (uint32_t)h * half_bytes, &tmapX, 32 * h, row0, xfull + b);
+    };
+
+    if (tid < AF_RTHREADS) {
+        // =========================== row stage ===========================
+        if (tid == 0) {
+            if (my_groups > 0) issue(0);
+            if (my_groups > 1) issue(1);
+        }
+        const int nch = W / 4;
+        for (int i = 0; i < my_groups; ++i) {
+            const int b = i & 1;
+            const uint32_t par = (uint32_t)(i >> 1) & 1;
+            tc::mbar_wait(xfull + b, par);
+            tc::mbar_wait(tempty + b, par ^ 1);
+            const uint8_t* xb = xbuf + (uint32_t)b * xbuf_bytes;
+            float2 are[2][MXE / 2], aim[2][MXE / 2];       // (k, k+1) pairs
+            float carry[2] = {0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int k = 0; k < MXE / 2; ++k) { are[q][k] = make_float2(0.f, 0.f); aim[q][k] = make_float2(0.f, 0.f); }
+#pragma unroll 1
+            for (int c = 0; c < nch / 2; ++c) {
+                const int cm = nch - 1 - c;
+                float e[2][4], o[2][4];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int r = tid + q * AF_RTHREADS;
+                    const uint8_t* rowp = xb + (uint32_t)r * 128;
+                    const float4 xa = af_lds128(rowp + (uint32_t)(c >> 3) * half_bytes + (uint32_t)(((c & 7) ^ (r & 7)) << 4));
+                    const float4 xm = af_lds128(rowp + (uint32_t)(cm >> 3) * half_bytes + (uint32_t)(((cm & 7) ^ (r & 7)) << 4));
+                    // n = 4c+j pairs with W-n: W-4c (the carry), then xm.w, xm.z, xm.y; xm.x is the next carry
+                    e[q][0] = c == 0 ? xa.x : xa.x + carry[q];
+                    o[q][0] = c == 0 ? 0.f : xa.x - carry[q];
+                    e[q][1] = xa.y + xm.w; o[q][1] = xa.y - xm.w;
+                    e[q][2] = xa.z + xm.z; o[q][2] = xa.z - xm.z;
+                    e[q][3] = xa.w + xm.y; o[q][3] = xa.w - xm.y;
+                    carry[q] = xm.x;
+                }
+                const float4* twp = reinterpret_cast<const float4*>(rtw + 4 * c * TWS);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 tw[TWS / 2];
+#pragma unroll
+                    for (int v = 0; v < TWS / 4; ++v) {
+                        const float4 t4 = twp[j * (TWS / 4) + v];
+                        tw[2 * v] = make_float2(t4.x, t4.y);
+                        tw[2 * v + 1] = make_float2(t4.z, t4.w);
+                    }
+#pragma unroll
+                    for (int k = 0; k < MXE / 2; ++k)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            are[q][k] = ffma2(make_float2(e[q][j], e[q][j]), tw[k], are[q][k]);
+                            aim[q][k] = ffma2(make_float2(o[q][j], o[q][j]), tw[MXE / 2 + k], aim[q][k]);
+                        }
+                }
+            }
+            {   // n = W/2: x[W/2] is the last carry, its sine term vanishes
+                const float2* twp = reinterpret_cast<const float2*>(rtw + (W / 2) * TWS);
+#pragma unroll
+                for (int k = 0; k < MXE / 2; ++k)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) are[q][k] = ffma2(make_float2(carry[q], carry[q]), twp[k], are[q][k]);
+            }
+            float2* Tb = Tbuf + (size_t)b * AF_ROWS * MX;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int k = 0; k < MX; ++k) {
+                    const float re = (k & 1) ? are[q][k / 2].y : are[q][k / 2].x;
+                    const float im = (k & 1) ? aim[q][k / 2].y : aim[q][k / 2].x;
+                    Tb[(tid + q * AF_RTHREADS) * MX + k] = make_float2(re, im);
+                }
+            tc::mbar_arrive(tfull + b);
+            // every row thread is done reading xbuf[b]: refill it with group i + 2
+            asm volatile("bar.sync 1, %0;" ::"n"(AF_RTHREADS) : "memory");
+            if (tid == 0 && i + 2 < my_groups) issue(i + 2);
+        }
+    } else {
+        // =========================== column stage ===========================
+        const int ct = tid - AF_RTHREADS;
+        const int kyq_n = Myp / 4;
+        const int items = p.G * kyq_n * MX;
+        for (int i = 0; i < my_groups; ++i) {
+            const int b = i & 1;
+            const uint32_t par = (uint32_t)(i >> 1) & 1;
+            tc::mbar_wait(tfull + b, par);
+            const float2* Tb = Tbuf + (size_t)b * AF_ROWS * MX;
+            const int64_t img0 = (int64_t)(first + i * stride) * p.G;
+            for (int item = ct; item < items; item += AF_CTHREADS) {
+                const int kx = item % MX;
+                const int rest = item / MX;
+                const int kyq = rest % kyq_n, g = rest / kyq_n;
+                const float2* Tg = Tb + (size_t)g * H * MX + kx;
+                const float4* twp = reinterpret_cast<const float4*>(ctw + kyq * 4);
+                float2 acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+                const float2* tp = Tg;
+                const int wstep = Myp >> 1;
+#pragma unroll 4
+                for (int y = 0; y < H; ++y) {
+                    const float2 tv = *tp;
+                    const float4 w01 = twp[0];
+                    const float4 w23 = twp[1];
+                    cmac2(acc[0], make_float2(w01.x, w01.y), tv);
+                    cmac2(acc[1], make_float2(w01.z, w01.w), tv);
+                    cmac2(acc[2], make_float2(w23.x, w23.y), tv);
+                    cmac2(acc[3], make_float2(w23.z, w23.w), tv);
+                    tp += MX;
+                    twp += wstep;
+                }
+                const int64_t img = img0 + g;
+                if (img < p.nimg) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ky = kyq * 4 + j;
+                        if (ky < My) p.Xh[(img * My + ky) * MX + kx] = acc[j];
+                    }
+                }
+            }
+            tc::mbar_arrive(tempty + b);
+        }
+    }
+}
+
+static int g_af_sms = 0;
+
+static size_t af_smem_bytes(const sb200_plan_s* p) {
+    const int Myp = (p->My + 3) & ~3;
+    const int TWS = (2 * p->Mx + 3) / 4 * 4;
+    return 1024 + 2 * (size_t)(p->W / 32) * AF_ROWS * 128 + 2 * (size_t)AF_ROWS * p->Mx * 8 +
+           (size_t)(p->W / 2 + 1) * TWS * 4 + (size_t)p->H * Myp * 8 + 64;
+}
+
+// geometry check shared by the scratch query and the launcher
+static bool af_supported(const sb200_plan_s* p) {
+    const int H = p->H, W = p->W, Mx = p->Mx;
+    if (W != 32 && W != 64) return false;
+    if (H < 8 || AF_ROWS % H != 0) return false;
+    if (!(Mx == 5 || Mx == 7 || Mx == 9 || Mx == 13 || Mx == 17)) return false;
+    if (Mx > W / 2 + 1) return false;
+    return af_smem_bytes(p) <= 227 * 1024;
+}
+
+bool sb200_analysis_fused_supported(sb200_plan_t plan) { return af_supported(plan); }
+
+int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, cudaStream_t st, int* handled) {
+    *handled = 0;
+    if (!af_supported(plan) || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 0;
+    const int H = plan->H, W = plan->W, My = plan->My, Mx = plan->Mx;
+    const int64_t rows = nimg * H;
+    if (rows >= (1LL << 31)) return 0;
+    AfParams p;
+    p.rowF = plan->rowF[pass]; p.colF = plan->colF[pass]; p.Xh = reinterpret_cast<float2*>(Xh);
+    p.nimg = nimg; p.H = H; p.W = W; p.My = My; p.G = AF_ROWS / H;
+    p.ngroups = (int)((rows + AF_ROWS - 1) / AF_ROWS);
+    const size_t smem = af_smem_bytes(plan);
+    CUtensorMap tmap;
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, x, (uint64_t)W, (uint64_t)rows, (uint64_t)W * 4, 32, AF_ROWS, 1)) return rc;
+    if (g_af_sms == 0) {
+        int dev = 0;
+        SB_CHECK_CUDA(cudaGetDevice(&dev));
+        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_af_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = (unsigned)(p.ngroups < g_af_sms ? p.ngroups : g_af_sms);
+#define AF_LAUNCH(MXV)                                                                                                  \
+    case MXV:                                                                                                           \
+        SB_CHECK_CUDA(cudaFuncSetAttribute(analysis_fused_kernel<MXV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           (int)smem));                                                                  \
+        analysis_fused_kernel<MXV><<<grid, AF_THREADS, smem, st>>>(tmap, p);                                             \
+        break;
+    switch (Mx) {
+        AF_LAUNCH(5) AF_LAUNCH(7) AF_LAUNCH(9) AF_LAUNCH(13) AF_LAUNCH(17)
+        default: return 0;
+    }
+#undef AF_LAUNCH
+    SB_LAUNCH_CHECK();
+    *handled = 1;
+    return 0;
+}

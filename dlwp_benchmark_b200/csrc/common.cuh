@@ -99,6 +99,25 @@ __device__ __forceinline__ float gelu_grad_f(float z) {
     return fmaf(z * 0.39894228040143267794f, e, cdf);
 }
 
+// Packed fp32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves with ONE issue slot.  ptxas folds operand
+// broadcasts (x, x), half swaps and the (-lo, +hi) sign pattern into FFMA2 operand modifiers, so a complex
+// multiply-accumulate costs two instructions instead of four.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// acc += a * b (complex), two FFMA2
+__device__ __forceinline__ void cmac2(float2& acc, const float2 a, const float2 b) {
+    acc = ffma2(make_float2(a.x, a.x), b, acc);
+    acc = ffma2(make_float2(a.y, a.y), make_float2(-b.y, b.x), acc);
+}
+
 __device__ __forceinline__ void cmac(float2& acc, const float2 a, const float2 b) {
     acc.x = fmaf(a.x, b.x, acc.x);
     acc.x = fmaf(-a.y, b.y, acc.x);

@@ -267,6 +267,30 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
 }
 
 // ======================================================================================
+// analysis: x -> Xh in one call (fused single kernel when the grid allows, else row + column stages)
+// ======================================================================================
+bool sb200_analysis_fused_supported(sb200_plan_t plan);                                              // analysis_fused.cu
+int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, cudaStream_t st, int* handled);
+
+extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
+    if (!p || nimg <= 0) return 0;
+    if (sb200_analysis_fused_supported(p)) return 0;
+    return nimg * p->H * p->Mx * 2;
+}
+
+extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream) {
+    SB_REQUIRE(p && x && Xh, "analysis: NULL argument");
+    SB_REQUIRE(pass == 0 || pass == 1, "analysis: pass must be 0 or 1");
+    if (nimg <= 0) return 0;
+    int handled = 0;
+    if (int rc = sb200_analysis_fused(p, pass, x, Xh, nimg, (cudaStream_t)stream, &handled)) return rc;
+    if (handled) return 0;
+    SB_REQUIRE(scratch != nullptr, "analysis: this grid needs sb200_analysis_scratch() floats of scratch");
+    if (int rc = sb200_rowdft_fwd(p, pass, x, scratch, nimg * p->H, stream)) return rc;
+    return sb200_coldft_fwd(p, pass, scratch, Xh, nimg, stream);
+}
+
+// ======================================================================================
 // modes_gemm: out[p,q,k] = sum_r opA(A[r,p,k]) * opB(B[r,q,k])
 // ======================================================================================
 constexpr int MG_RC = 8;

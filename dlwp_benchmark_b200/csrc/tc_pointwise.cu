@@ -105,7 +105,9 @@ template <int PASSES, int EPI>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
+    // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KC = p.KC, nkc = p.nkc, S = p.stages;
     const bool spectral = p.Phi != nullptr;
     const uint32_t a_bytes = (uint32_t)KC * 512;                       // 4 boxes x KC rows x 128 B

@@ -8,7 +8,9 @@ tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, f
                    int a_layout_in, int use_mask, uint32_t* __restrict__ info) {
     const int a_layout = a_layout_in & 15, b_sw32 = a_layout_in >> 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
+    // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_bytes = (uint32_t)((K + 31) / 32) * 128u * 128u;   // K-major rows are 128 B wide even when K < 32
     uint8_t* As = base;
     uint8_t* Bs = As + ((a_bytes + 1023) & ~1023u);

@@ -33,7 +33,9 @@ template <int PASSES>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapQ, const TcWgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
+    // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages, CH = p.CH;
     const uint32_t p_chunk = (uint32_t)p.Pc * 128, q_chunk = (uint32_t)p.Qc * 128;
     const uint32_t ones_bytes = (uint32_t)(p.Qn - p.Qc) * 128;         // constant rows [1,1,...; 0...] behind the Q rows

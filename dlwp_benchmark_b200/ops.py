@@ -62,6 +62,19 @@ def coldft_inv(plan: Plan, pas: int, Yh: torch.Tensor) -> torch.Tensor:
     return Phi
 
 
+def analysis(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
+    """x [..., H, W] -> Xh [..., My, Mx, 2] (row + column stages; one fused kernel on small grids)."""
+    _req(x, "x")
+    assert x.shape[-2:] == (plan.H, plan.W)
+    nimg = x.numel() // (plan.H * plan.W)
+    lib = _lib.load()
+    n = lib.sb200_analysis_scratch(plan.handle, nimg)
+    scratch = torch.empty(n, device=x.device, dtype=torch.float32) if n > 0 else None
+    Xh = torch.empty(*x.shape[:-2], plan.My, plan.Mx, 2, device=x.device, dtype=torch.float32)
+    _lib.check(lib.sb200_analysis(plan.handle, pas, _p(x), _p(Xh), nimg, _p(scratch), _stream()), "analysis")
+    return Xh
+
+
 def modes_gemm(A, sAr, sAp, B, sBr, sBq, out, sOp, sOq, P, Q, R, K, conj_flags=0):
     _req(A, "A"); _req(B, "B"); _req(out, "out")
     _lib.check(_lib.load().sb200_modes_gemm(_p(A), sAr, sAp, _p(B), sBr, sBq, _p(out), sOp, sOq,

@@ -39,7 +39,7 @@ class _SpectralStage:
 
     @staticmethod
     def analysis(plan, pas, x):
-        return ops.coldft_fwd(plan, pas, ops.rowdft_fwd(plan, pas, x))
+        return ops.analysis(plan, pas, x)
 
 
 class FNOBlockFn(torch.autograd.Function):

@@ -77,6 +77,13 @@ int sb200_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, int
  * replaces zeros + scatter + fftshift + the H-axis half of torch.fft.irfftn */
 int sb200_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, int64_t nimg, void* stream);
 
+/* x [nimg, H, W] real -> Xh [nimg, My, Mx] complex: the two stages above in one call.  On small grids
+ * (W in {32, 64}, H dividing 256) a single fused kernel keeps the row-transformed spectrum on chip and
+ * `scratch` may be NULL; otherwise `scratch` must hold sb200_analysis_scratch(plan, nimg) floats.
+ * replaces torch.fft.rfftn + fftshift + slice (pass 0) / the adjoint of irfftn (pass 1). */
+int64_t sb200_analysis_scratch(sb200_plan_t plan, int64_t nimg);
+int sb200_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream);
+
 /* Batched-over-modes complex contraction
  *      out[p,q,k] = sum_r opA(A[r,p,k]) * opB(B[r,q,k]),   k contiguous,
  * with element strides (in complex elements) for r/p/q.  conj flags: bit0 = conj A, bit1 = conj B.

@@ -58,6 +58,34 @@ def test_analysis_stages(B, C, H, W, nm):
     assert rel_l2(torch.view_as_complex(Xh), ref) < TOL
 
 
+ANALYSIS_SHAPES = STAGE_SHAPES + [
+    (5, 3, 64, 64, (16, 16)),    # fused kernel, 15 images: partial last group (G = 4)
+    (64, 8, 64, 64, (16, 16)),   # fused kernel, more groups than one wave per SM pair
+    (3, 5, 32, 64, (24, 24)),    # fused, G = 8, Mx = 13
+    (2, 3, 32, 32, (32, 32)),    # fused, W = 32, Mx = 17 (Nyquist column retained)
+    (1, 5, 128, 64, (32, 8)),    # fused, G = 2, Mx = 5, My = 32
+    (7, 1, 16, 32, (12, 12)),    # fused, G = 16, My = 12, Mx = 7
+    (1, 3, 64, 64, (20, 12)),    # fused, My = 20
+    (1, 3, 64, 64, (18, 16)),    # fused, My not a multiple of 4
+]
+
+
+@pytest.mark.parametrize("pas", [0, 1])
+@pytest.mark.parametrize("B,C,H,W,nm", ANALYSIS_SHAPES)
+def test_analysis_single_call(B, C, H, W, nm, pas):
+    """sb200_analysis (one fused kernel on small grids) == row stage + column stage == torch.fft."""
+    half = so.halve_last_mode(nm)
+    plan = fno_plan(DEV, H, W, half)
+    x = _rand(B, C, H, W, seed=11)
+    Xh = ops.analysis(plan, pas, x.to(DEV))
+    two = ops.coldft_fwd(plan, pas, ops.rowdft_fwd(plan, pas, x.to(DEV)))
+    assert rel_l2(Xh, two) < TOL
+    if pas == 0:
+        full = torch.fft.fftshift(torch.fft.rfftn(x.double(), norm="forward", dim=(-2, -1)), dim=(-2,))
+        lo, My = so.retained_rows(H, half[0])
+        assert rel_l2(torch.view_as_complex(Xh), full[:, :, lo:lo + My, :plan.Mx]) < TOL
+
+
 @pytest.mark.parametrize("B,C,H,W,nm", STAGE_SHAPES)
 def test_synthesis_stages(B, C, H, W, nm):
     half = so.halve_last_mode(nm)
