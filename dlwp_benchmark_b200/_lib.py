@@ -33,6 +33,9 @@ SIGNATURES = {
     "sb200_analysis_scratch": (_i64, [_vp, _i64]),
     "sb200_analysis": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "sb200_modes_gemm": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
+    "sb200_cgemm_workspace": (_i64, [_vp, _i]),
+    "sb200_cgemm_grouped": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sb200_cgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),
     "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp]),

@@ -135,8 +135,9 @@ class FNOBlocks(nn.Module):
             return y
         H, W = x.shape[-2:]
         params = []
+        dense = self.convs.dense_weights_all(H, W)
         for l in range(self.n_layers):
-            params += [self.convs.dense_weight(l, H, W), self.fno_skips[l].weight, self.convs.bias[l]]
+            params += [dense[l], self.fno_skips[l].weight, self.convs.bias[l]]
         return FNOStackFn.apply(x, tuple(self.convs.n_modes), self.n_layers, *params)
 
 
@@ -208,9 +209,10 @@ class FNO(nn.Module):
             spec.append(False); acts.append(i < nl_lift - 1)
             params += [None, fc.weight, fc.bias]
         blocks = self.fno_blocks
+        dense = blocks.convs.dense_weights_all(H, W)
         for l in range(self.n_layers):
             spec.append(True); acts.append(l < self.n_layers - 1)
-            params += [blocks.convs.dense_weight(l, H, W), blocks.fno_skips[l].weight, blocks.convs.bias[l]]
+            params += [dense[l], blocks.fno_skips[l].weight, blocks.convs.bias[l]]
         nl_proj = len(self.projection.fcs)
         for i, fc in enumerate(self.projection.fcs):
             spec.append(False); acts.append(i < nl_proj - 1)

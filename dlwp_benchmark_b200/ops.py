@@ -180,3 +180,35 @@ def wgrad_small(small: torch.Tensor, big: torch.Tensor, transpose: bool, want_sm
     _lib.check(lib.sb200_wgrad_small(_p(small), _p(big), _p(dot), _p(ss), _p(bs), B, S, L, HW, int(transpose), _p(ws),
                                      _stream()), "wgrad_small")
     return dot, ss, bs
+
+
+class CgemmDesc(ctypes.Structure):
+    """Mirror of ``sb200_cgemm_desc`` (include/spectral_b200.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("M", "N", "K", "M2", "K2", "conjA", "conjB", "reserved")] + \
+               [(n, ctypes.c_int64) for n in ("sAm1", "sAm2", "sAk1", "sAk2", "sBk1", "sBk2", "sBn",
+                                              "sCm1", "sCm2", "sCn")]
+
+
+def cgemm(A, B, C, *, M: int, N: int, K: int, sAm, sAk, sBk, sBn, sCm, sCn,
+          M2: int = 1, K2: int = 1, conjA: bool = False, conjB: bool = False):
+    """C[m,n] = sum_k opA(A[m,k]) opB(B[k,n]) on interleaved-complex fp32 storage; strides in complex elements.
+    ``sAm``/``sCm`` are (outer, inner) pairs when ``M2 > 1``, ``sAk``/``sBk`` likewise when ``K2 > 1``.
+    A, B, C may be lists (<= 8) of tensors of identical geometry: one launch computes all of them."""
+    single = isinstance(A, torch.Tensor)
+    As, Bs, Cs = ([A], [B], [C]) if single else (list(A), list(B), list(C))
+    assert len(As) == len(Bs) == len(Cs) and 1 <= len(As) <= 8
+    for t in As + Bs + Cs:
+        _req(t, "cgemm operand")
+    pair = lambda s: (int(s[0]), int(s[1])) if isinstance(s, (tuple, list)) else (0, int(s))
+    d = CgemmDesc()
+    d.M, d.N, d.K, d.M2, d.K2, d.conjA, d.conjB = M, N, K, M2, K2, int(conjA), int(conjB)
+    d.sAm1, d.sAm2 = pair(sAm); d.sAk1, d.sAk2 = pair(sAk)
+    d.sBk1, d.sBk2 = pair(sBk); d.sBn = int(sBn)
+    d.sCm1, d.sCm2 = pair(sCm); d.sCn = int(sCn)
+    lib = _lib.load()
+    ng = len(As)
+    nws = lib.sb200_cgemm_workspace(ctypes.byref(d), ng)
+    ws = torch.empty(nws, device=As[0].device, dtype=torch.float32) if nws > 0 else None
+    arr = lambda ts: (ctypes.c_void_p * ng)(*[t.data_ptr() for t in ts])
+    _lib.check(lib.sb200_cgemm_grouped(ctypes.byref(d), ng, arr(As), arr(Bs), arr(Cs), _p(ws), _stream()), "cgemm")
+    return C

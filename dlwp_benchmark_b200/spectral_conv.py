@@ -238,9 +238,20 @@ class SpectralConv(nn.Module):
         n_modes[-1] = n_modes[-1] // 2 + 1
         self._n_modes = n_modes
 
+    def dense_weights_all(self, H: int, W: int):
+        """``dense_weight`` of every layer; Tucker layers are reconstructed together (one launch per mode
+        product for all layers, forward and backward)."""
+        if self.factorization == "tucker" and self.weight[0].core.is_cuda and len(self.weight[0].shape) == 4:
+            from .tucker_fn import reconstruct_many
+            dense = reconstruct_many(list(self.weight))
+            return [self._slice_modes(w, H, W) for w in dense]
+        return [self.dense_weight(l, H, W) for l in range(self.n_layers)]
+
     def dense_weight(self, index: int, H: int, W: int) -> torch.Tensor:
         """Real view [Cin,Cout,My,Mx,2] of layer ``index`` sliced like SpectralConv.forward does."""
-        w = self.weight[index].to_dense_real()          # [Cin,Cout,*max_n_modes,2]
+        return self._slice_modes(self.weight[index].to_dense_real(), H, W)   # [Cin,Cout,*max_n_modes,2]
+
+    def _slice_modes(self, w: torch.Tensor, H: int, W: int) -> torch.Tensor:
         fft_size = [H, W // 2 + 1]
         kept = [min(s, n) for s, n in zip(fft_size, self.n_modes)]
         starts = [m - k for m, k in zip(self.max_n_modes, kept)]

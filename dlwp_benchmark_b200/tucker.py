@@ -89,11 +89,16 @@ class TuckerWeight(nn.Module):
         self.factors = FactorList([cplx(s, rk) for s, rk in zip(self.shape, self.rank)])
 
     def to_dense_complex(self) -> torch.Tensor:
-        c = torch.view_as_complex(self.core)
-        f = [torch.view_as_complex(x) for x in self.factors]
-        # mode products ordered so the intermediate stays small (spatial modes first)
-        t = torch.einsum("fghj,ph,qj->fgpq", c, f[2], f[3])
-        return torch.einsum("fgpq,if,og->iopq", t, f[0], f[1])
+        return torch.view_as_complex(self.to_dense_real())
 
     def to_dense_real(self) -> torch.Tensor:
-        return torch.view_as_real(self.to_dense_complex().contiguous())
+        if self.core.is_cuda and len(self.shape) == 4:
+            from .tucker_fn import TuckerReconstructFn       # C-ABI kernels, forward and backward
+            return TuckerReconstructFn.apply(self.core, *list(self.factors))
+        # host-side inspection of a CPU module only (the layers themselves refuse CPU inputs)
+        c = torch.view_as_complex(self.core)
+        f = [torch.view_as_complex(x) for x in self.factors]
+        letters = "ijklmn"[:len(self.shape)]
+        ranks = "uvwxyz"[:len(self.shape)]
+        eq = ranks + "," + ",".join(a + b for a, b in zip(letters, ranks)) + "->" + letters
+        return torch.view_as_real(torch.einsum(eq, c, *f).contiguous())

@@ -94,6 +94,26 @@ int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp,
                      float* out, int64_t sOp, int64_t sOq,
                      int P, int Q, int R, int K, int conj_flags, void* stream);
 
+/* Strided complex GEMM   C[m,n] = sum_k opA(A[m,k]) * opB(B[k,n])   (complex64, strides in complex elements).
+ * m and k may be two-level composite indices: m -> (m / M2, m % M2) addressed with (s?m1, s?m2), likewise k
+ * with K2 (M2 = 1 / K2 = 1: plain index using the *2 stride).  This expresses every mode product, core /
+ * input gradient and factor gradient of a Tucker tensor without permuting it.  When the output tile count is
+ * small and K long the reduction is split (deterministically) and needs sb200_cgemm_workspace() floats.
+ * replaces tltorch TuckerTensor reconstruction / tensorly's einsum chain behind neuralop
+ * SpectralConv(factorization="Tucker") (src/dlwpbench/models/fno/fno.py:136-146) and its autograd backward. */
+typedef struct sb200_cgemm_desc {
+    int32_t M, N, K, M2, K2, conjA, conjB, reserved;
+    int64_t sAm1, sAm2, sAk1, sAk2;
+    int64_t sBk1, sBk2, sBn;
+    int64_t sCm1, sCm2, sCn;
+} sb200_cgemm_desc;
+int64_t sb200_cgemm_workspace(const sb200_cgemm_desc* desc, int ngroups);
+int sb200_cgemm(const sb200_cgemm_desc* desc, const float* A, const float* B, float* C, float* workspace, void* stream);
+/* the same product for `ngroups` (1..8) operand triples of identical geometry in ONE launch (the layers of an
+ * FNO); A/B/C are HOST arrays of device pointers; workspace sized by sb200_cgemm_workspace(desc, ngroups) */
+int sb200_cgemm_grouped(const sb200_cgemm_desc* desc, int ngroups, const float* const* A, const float* const* B,
+                        float* const* C, float* workspace, void* stream);
+
 /* Fused row synthesis + pointwise (1x1) channel mix + epilogue.
  *   acc[b,n,y,x] = sum_kx ( Phi[b,n,y,kx].re * RI[kx][x].x + Phi.im * RI[kx][x].y )
  *                + sum_m  Wp[n,m] * A[b,m,y,x]            (skipped when Wp == NULL)

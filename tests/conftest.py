@@ -19,6 +19,9 @@ def golden_dir():
 
 def rel_l2(a, b):
     import torch
-    a = a.detach().double().cpu()
-    b = b.detach().double().cpu()
+    cv = lambda t: torch.view_as_real(t.detach().cpu().to(torch.complex128)) if t.is_complex() else t.detach().double().cpu()
+    a, b = cv(a), cv(b)
+    if a.shape != b.shape:      # one side complex, the other its (re, im) real view
+        assert a.numel() == b.numel(), (a.shape, b.shape)
+        b = b.reshape(a.shape)
     return (torch.linalg.norm(a - b) / torch.linalg.norm(b).clamp_min(1e-30)).item()
