@@ -168,6 +168,90 @@ __global__ void __launch_bounds__(CG_THREADS) cgemm_kernel(const CgParams p) {
     }
 }
 
+// Skinny products (N <= 32, K <= 64, many rows): the small spatial modes of a Tucker tensor.  One thread owns TWO
+// rows and all N outputs of each in registers; opB(B) sits in shared memory as (re, im, -im, re) so a complex MAC is
+// two FFMA2 with the thread's A element as the broadcast scalar and one warp-uniform LDS.128.
+constexpr int CS_THREADS = 128;
+constexpr int CS_MAXK = 64;
+
+template <int NP>
+__global__ void __launch_bounds__(CS_THREADS) cskinny_kernel(const CgParams p) {
+    __shared__ __align__(16) float4 Bs[CS_MAXK * NP];
+    const int g = blockIdx.y;
+    const float2* __restrict__ Ag = p.A[g];
+    const float2* __restrict__ Bg = p.B[g];
+    float2* __restrict__ Cg = p.C[g];
+    const float sb = p.conjB ? -1.f : 1.f, sa = p.conjA ? -1.f : 1.f;
+    for (int idx = threadIdx.x; idx < p.K * NP; idx += CS_THREADS) {
+        const int k = idx / NP, n = idx % NP;
+        float2 u = make_float2(0.f, 0.f);
+        if (n < p.N) u = __ldg(Bg + (long long)k * p.sBk2 + (long long)n * p.sBn);
+        u.y *= sb;
+        Bs[idx] = make_float4(u.x, u.y, -u.y, u.x);
+    }
+    __syncthreads();
+    const int mbase = blockIdx.x * (2 * CS_THREADS) + threadIdx.x;
+    int m[2] = {mbase, mbase + CS_THREADS};
+    long long aoff[2];
+    bool ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        ok[r] = m[r] < p.M;
+        aoff[r] = ok[r] ? cg_off2(m[r], p.M2, p.sAm1, p.sAm2) : 0;
+    }
+    float2 acc[2][NP];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int n = 0; n < NP; ++n) acc[r][n] = make_float2(0.f, 0.f);
+    // k in chunks of 8: the loads of a chunk are issued back to back and the NEXT chunk is in flight during the math
+    constexpr int KC = 8;
+    float2 cur[2][KC], nxt[2][KC];
+    auto fetch = [&](float2 (&dst)[2][KC], int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                const int k = k0 + kk;
+                float2 v = make_float2(0.f, 0.f);
+                if (ok[r] && k < p.K) v = __ldg(Ag + aoff[r] + (long long)k * p.sAk2);
+                v.y *= sa;
+                dst[r][kk] = v;
+            }
+    };
+    fetch(cur, 0);
+    for (int k0 = 0; k0 < p.K; k0 += KC) {
+        if (k0 + KC < p.K) fetch(nxt, k0 + KC);
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            if (k0 + kk < p.K) {
+                const float4* bk = Bs + (k0 + kk) * NP;
+#pragma unroll
+                for (int n = 0; n < NP; ++n) {
+                    const float4 u = bk[n];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        acc[r][n] = ffma2(make_float2(cur[r][kk].x, cur[r][kk].x), make_float2(u.x, u.y), acc[r][n]);
+                        acc[r][n] = ffma2(make_float2(cur[r][kk].y, cur[r][kk].y), make_float2(u.z, u.w), acc[r][n]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) cur[r][kk] = nxt[r][kk];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!ok[r]) continue;
+        float2* dst = Cg + cg_off2(m[r], p.M2, p.sCm1, p.sCm2);
+#pragma unroll
+        for (int n = 0; n < NP; ++n)
+            if (n < p.N) dst[(long long)n * p.sCn] = acc[r][n];
+    }
+}
+
 // C_g[m, n] = sum_s ws[g][s][m][n]   (deterministic split-K reduction; output through the C strides).
 // 32 consecutive outputs x 8 split lanes per block: coalesced partial reads, shared-memory tree at the end.
 struct CgOut { float2* C[CG_MAXG]; };
@@ -239,6 +323,7 @@ int cg_splits(const sb200_cgemm_desc* d, int ngroups, int* kchunk) {
 extern "C" int64_t sb200_cgemm_workspace(const sb200_cgemm_desc* d, int ngroups) {
     if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0 || ngroups <= 0) return 0;
     int kc = 0;
+    if (d->N <= 32 && d->K <= CS_MAXK && d->K2 == 1 && d->M >= 2048) return 0;     // skinny kernel: no split
     const int splits = cg_splits(d, ngroups, &kc);
     return splits > 1 ? 2LL * ngroups * splits * d->M * d->N : 0;
 }
@@ -258,7 +343,9 @@ extern "C" int sb200_cgemm_grouped(const sb200_cgemm_desc* d, int ngroups, const
     p.conjA = d->conjA; p.conjB = d->conjB;
     p.a_kfast = (d->sAk2 == 1 && d->sAm2 != 1) ? 1 : 0;
     p.b_kfast = (d->sBk2 == 1 && d->sBn != 1) ? 1 : 0;
-    p.splits = cg_splits(d, ngroups, &p.kchunk);
+    const bool skinny = d->N <= 32 && d->K <= CS_MAXK && d->K2 == 1 && d->M >= 2048 && getenv("SB200_CGEMM_NOSKINNY") == nullptr;
+    p.splits = skinny ? 1 : cg_splits(d, ngroups, &p.kchunk);
+    if (skinny) p.kchunk = d->K;
     p.partial = p.splits > 1;
     SB_REQUIRE(!p.partial || workspace, "cgemm: this shape needs sb200_cgemm_workspace() floats of workspace");
     CgOut out;
@@ -269,6 +356,14 @@ extern "C" int sb200_cgemm_grouped(const sb200_cgemm_desc* d, int ngroups, const
         p.B[g] = reinterpret_cast<const float2*>(B[gg]);
         out.C[g] = reinterpret_cast<float2*>(C[gg]);
         p.C[g] = p.partial ? reinterpret_cast<float2*>(workspace) : out.C[g];
+    }
+    if (skinny) {
+        dim3 sgrid((unsigned)((d->M + 2 * CS_THREADS - 1) / (2 * CS_THREADS)), (unsigned)ngroups);
+        if (d->N <= 8) cskinny_kernel<8><<<sgrid, CS_THREADS, 0, st>>>(p);
+        else if (d->N <= 16) cskinny_kernel<16><<<sgrid, CS_THREADS, 0, st>>>(p);
+        else cskinny_kernel<32><<<sgrid, CS_THREADS, 0, st>>>(p);
+        SB_LAUNCH_CHECK();
+        return 0;
     }
     const CgShape t = cg_pick(d->M, d->N);
     dim3 grid((unsigned)((d->M + t.bm - 1) / t.bm), (unsigned)((d->N + t.bn - 1) / t.bn), (unsigned)(p.splits * ngroups));

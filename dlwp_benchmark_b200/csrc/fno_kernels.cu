@@ -216,6 +216,66 @@ coldft_inv_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, 
     }
 }
 
+// v2 of the zero-padded inverse column transform: one thread owns one (image, kx) pair and a segment of output rows;
+// its My input modes live in registers (plus the (-im, re) rotated copy, so that a complex MAC is two FFMA2 with a
+// warp-uniform twiddle broadcast from shared memory).  Reads and writes are kx-contiguous per image.
+template <int MYP>
+__global__ void __launch_bounds__(128)
+coldft_inv2_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
+                   int64_t nitems, int H, int My, int Mx, int yseg) {
+    extern __shared__ __align__(16) float2 tw[];          // [yseg][MYP] twiddles of this block's rows
+    const int y0 = blockIdx.y * yseg;
+    const int ny = min(yseg, H - y0);
+    for (int idx = threadIdx.x; idx < yseg * MYP; idx += blockDim.x) {
+        const int yy = idx / MYP, ky = idx % MYP;
+        tw[idx] = (yy < ny && ky < My) ? __ldg(CI + (int64_t)(y0 + yy) * My + ky) : make_float2(0.f, 0.f);
+    }
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = item < nitems;
+    const int64_t img = active ? item / Mx : 0;
+    const int kx = active ? (int)(item % Mx) : 0;
+    float2 v[MYP], vr[MYP];
+    const float2* src = Yh + img * My * Mx + kx;
+#pragma unroll
+    for (int ky = 0; ky < MYP; ++ky) {
+        v[ky] = (active && ky < My) ? __ldg(src + (int64_t)ky * Mx) : make_float2(0.f, 0.f);
+        vr[ky] = make_float2(-v[ky].y, v[ky].x);
+    }
+    __syncthreads();
+    if (!active) return;
+    float2* dst = Phi + (img * H + y0) * Mx + kx;
+    for (int yy = 0; yy < ny; ++yy) {
+        const float4* t4 = reinterpret_cast<const float4*>(tw + yy * MYP);
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int h = 0; h < MYP / 2; ++h) {
+            const float4 t = t4[h];                        // twiddles of ky = 2h, 2h+1
+            a0 = ffma2(make_float2(t.x, t.x), v[2 * h], a0);
+            a1 = ffma2(make_float2(t.y, t.y), vr[2 * h], a1);
+            a2 = ffma2(make_float2(t.z, t.z), v[2 * h + 1], a2);
+            a3 = ffma2(make_float2(t.w, t.w), vr[2 * h + 1], a3);
+        }
+        dst[(int64_t)yy * Mx] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+    }
+}
+
+template <int MYP>
+static int coldft_inv2_launch(const float2* Yh, const float2* CI, float2* Phi, int64_t nimg, int H, int My, int Mx,
+                              cudaStream_t st) {
+    const int64_t nitems = nimg * Mx;
+    // enough row segments to give every SM sub-partition several warps
+    int segs = 1;
+    while (segs < 8 && (nitems / 32) * segs < 4 * 4 * 148 && H / (segs * 2) >= 8) segs *= 2;
+    const int yseg = (H + segs - 1) / segs;
+    dim3 grid((unsigned)ceil_div64(nitems, 128), (unsigned)((H + yseg - 1) / yseg));
+    const size_t smem = (size_t)yseg * MYP * sizeof(float2);
+    if (smem > 48 * 1024)
+        SB_CHECK_CUDA(cudaFuncSetAttribute(coldft_inv2_kernel<MYP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    coldft_inv2_kernel<MYP><<<grid, 128, smem, st>>>(Yh, CI, Phi, nitems, H, My, Mx, yseg);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
 static int col_launch_cfg(int outer_groups, int Mx, int* GB, int* IPB, int* threads) {
     int gb = 256 / Mx;
     if (gb < 1) gb = 1;
@@ -252,6 +312,15 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
     SB_REQUIRE(pass == 0 || pass == 1, "coldft_inv: pass must be 0 or 1");
     if (nimg <= 0) return 0;
     const int H = p->H, My = p->My, Mx = p->Mx;
+    if (My <= 32 && getenv("SB200_COLDFT_INV_V1") == nullptr) {
+        const float2* Y2 = reinterpret_cast<const float2*>(Yh);
+        float2* P2 = reinterpret_cast<float2*>(Phi);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (My <= 8) return coldft_inv2_launch<8>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
+        if (My <= 16) return coldft_inv2_launch<16>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
+        if (My <= 24) return coldft_inv2_launch<24>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
+        return coldft_inv2_launch<32>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
+    }
     int YGB, IPB, threads;
     SB_REQUIRE(col_launch_cfg((H + 3) / 4, Mx, &YGB, &IPB, &threads) == 0, "coldft_inv: Mx=%d too large", Mx);
     if ((int64_t)IPB > nimg) IPB = (int)nimg;
@@ -294,6 +363,109 @@ extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* X
 // modes_gemm: out[p,q,k] = sum_r opA(A[r,p,k]) * opB(B[r,q,k])
 // ======================================================================================
 constexpr int MG_RC = 8;
+
+// v2: CTA tile = 32 p x 32 q x 4 modes, 8 warps; a warp owns ONE mode (so the shared-memory operand reads are
+// warp-broadcast LDS.128) and a thread owns p = tp + 8i, q = tq + 8j (i, j < 4).  Operands are staged planar
+// (re / im) with the p (q) axis permuted, pos(p) = 4*(p & 7) + (p >> 3), so that a thread's four p are one
+// LDS.128; the complex MAC is four broadcast FFMA2 over q pairs; the next r-slab is prefetched into registers
+// during the math; the output goes through shared memory so that global stores are k-contiguous full sectors.
+// Every shared-memory access pattern below is bank-conflict free (see the lane maps).
+constexpr int MG2_PS = 40;                    // floats per (r, k) row: 32 positions + pad (bank = 8*k + pos)
+constexpr int MG2_OS = 40;                    // float2 per (k, q) output row
+constexpr int MG2_OPLANE = 32 * MG2_OS + 4;   // float2 per k plane of the output stage
+
+__global__ void __launch_bounds__(256)
+modes_gemm2_kernel(const float2* __restrict__ A, int64_t sAr, int64_t sAp,
+                   const float2* __restrict__ B, int64_t sBr, int64_t sBq,
+                   float2* __restrict__ out, int64_t sOp, int64_t sOq,
+                   int P, int Q, int R, int K, int conjA, int conjB) {
+    constexpr int STAGE_FLOATS = 4 * MG_RC * 4 * MG2_PS, OUT_FLOATS = 2 * 4 * MG2_OPLANE;
+    __shared__ __align__(16) float smem[STAGE_FLOATS > OUT_FLOATS ? STAGE_FLOATS : OUT_FLOATS];
+    float (*As_re)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem);
+    float (*As_im)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem + MG_RC * 4 * MG2_PS);
+    float (*Bs_re)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem + 2 * MG_RC * 4 * MG2_PS);
+    float (*Bs_im)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem + 3 * MG_RC * 4 * MG2_PS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kk = warp & 3;                            // mode of this warp
+    const int tp = lane & 7;                            // p = tp + 8i
+    const int tq = (lane >> 3) + 4 * (warp >> 2);       // q = tq + 8j
+    const int k0 = blockIdx.x * 4, p0 = blockIdx.y * 32, q0 = blockIdx.z * 32;
+
+    // loader lane map: k = lane & 3 (one 32-byte sector per (r, p)), p = i + 8c with i = ((lane >> 2) & 1) + 2*(warp & 3),
+    // c = lane >> 3; r = (warp >> 2) + 2j.  Staging position 4i + c -> bank 8k + 4i + c: 32 distinct banks per warp.
+    const int l_k = lane & 3, l_i = ((lane >> 2) & 1) + 2 * (warp & 3), l_c = lane >> 3, l_r = warp >> 2;
+    const int l_p = l_i + 8 * l_c, l_pos = 4 * l_i + l_c;
+    const bool ka = k0 + l_k < K;
+    const bool pa = ka && (p0 + l_p < P), qa = ka && (q0 + l_p < Q);
+    const float2* Ap = A + (int64_t)(p0 + l_p) * sAp + k0 + l_k;
+    const float2* Bp = B + (int64_t)(q0 + l_p) * sBq + k0 + l_k;
+    const float sa = conjA ? -1.f : 1.f, sb = conjB ? -1.f : 1.f;
+
+    float2 ra[4], rb[4];
+    auto fetch = [&](int r0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + l_r + 2 * j;
+            ra[j] = (pa && r < R) ? __ldg(Ap + (int64_t)r * sAr) : make_float2(0.f, 0.f);
+            rb[j] = (qa && r < R) ? __ldg(Bp + (int64_t)r * sBr) : make_float2(0.f, 0.f);
+        }
+    };
+    float2 acc_re[4][2], acc_im[4][2];                  // [i][q pair]: q = tq + 8*(2*pair), tq + 8*(2*pair + 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc_re[i][j] = make_float2(0.f, 0.f); acc_im[i][j] = make_float2(0.f, 0.f); }
+
+    fetch(0);
+    for (int r0 = 0; r0 < R; r0 += MG_RC) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = l_r + 2 * j;
+            As_re[rr][l_k][l_pos] = ra[j].x; As_im[rr][l_k][l_pos] = sa * ra[j].y;
+            Bs_re[rr][l_k][l_pos] = rb[j].x; Bs_im[rr][l_k][l_pos] = sb * rb[j].y;
+        }
+        __syncthreads();
+        if (r0 + MG_RC < R) fetch(r0 + MG_RC);
+#pragma unroll
+        for (int rr = 0; rr < MG_RC; ++rr) {
+            const float4 ar = *reinterpret_cast<const float4*>(&As_re[rr][kk][4 * tp]);
+            const float4 ai = *reinterpret_cast<const float4*>(&As_im[rr][kk][4 * tp]);
+            const float4 br = *reinterpret_cast<const float4*>(&Bs_re[rr][kk][4 * tq]);
+            const float4 bi = *reinterpret_cast<const float4*>(&Bs_im[rr][kk][4 * tq]);
+            const float a_r[4] = {ar.x, ar.y, ar.z, ar.w}, a_i[4] = {ai.x, ai.y, ai.z, ai.w};
+            const float2 brp[2] = {make_float2(br.x, br.y), make_float2(br.z, br.w)};
+            const float2 bip[2] = {make_float2(bi.x, bi.y), make_float2(bi.z, bi.w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    acc_re[i][j] = ffma2(make_float2(a_r[i], a_r[i]), brp[j], acc_re[i][j]);
+                    acc_re[i][j] = ffma2(make_float2(-a_i[i], -a_i[i]), bip[j], acc_re[i][j]);
+                    acc_im[i][j] = ffma2(make_float2(a_r[i], a_r[i]), bip[j], acc_im[i][j]);
+                    acc_im[i][j] = ffma2(make_float2(a_i[i], a_i[i]), brp[j], acc_im[i][j]);
+                }
+        }
+    }
+    // ---- epilogue: Os[k][q][p] through shared memory, then k-contiguous (full-sector) global stores ----
+    __syncthreads();
+    float2* Os = reinterpret_cast<float2*>(smem);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float re = (j & 1) ? acc_re[i][j >> 1].y : acc_re[i][j >> 1].x;
+            const float im = (j & 1) ? acc_im[i][j >> 1].y : acc_im[i][j >> 1].x;
+            Os[kk * MG2_OPLANE + (tq + 8 * j) * MG2_OS + tp + 8 * i] = make_float2(re, im);
+        }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = tid; e < 32 * 32 * 4; e += 256) {
+        const int k = e & 3, pp = (e >> 2) & 31, q = e >> 7;
+        if (k0 + k < K && p0 + pp < P && q0 + q < Q)
+            out[(int64_t)(p0 + pp) * sOp + (int64_t)(q0 + q) * sOq + k0 + k] = Os[k * MG2_OPLANE + q * MG2_OS + pp];
+    }
+}
 
 template <int KT>
 __global__ void __launch_bounds__(256)
@@ -386,6 +558,12 @@ extern "C" int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp, const 
     const float2* A2 = reinterpret_cast<const float2*>(A);
     const float2* B2 = reinterpret_cast<const float2*>(B);
     float2* O2 = reinterpret_cast<float2*>(out);
+    if (getenv("SB200_MODES_GEMM_V1") == nullptr) {
+        dim3 grid((K + 3) / 4, pb, qb);
+        modes_gemm2_kernel<<<grid, 256, 0, st>>>(A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
+        SB_LAUNCH_CHECK();
+        return 0;
+    }
     // prefer 8 modes per block; fall back to 4 when that would leave SMs idle
     const int64_t blocks8 = (int64_t)((K + 7) / 8) * pb * qb;
     if (blocks8 >= 2 * 148) {

@@ -23,6 +23,7 @@ CGEMM_SHAPES = [
     # M, N, K  (tile pickers: 16x16, 32x32, 256x16, 128x32, 64x64; split-K when few tiles and long K)
     (9, 8, 5000), (16, 15, 333), (30, 17, 4100), (1000, 9, 8), (777, 16, 15), (500, 30, 33), (130, 70, 60),
     (64, 60, 7680), (1, 1, 1), (65, 129, 17),
+    (5000, 9, 8), (4100, 16, 15), (3001, 30, 33), (2048, 5, 64),     # skinny kernel (thread owns two rows)
 ]
 
 
