@@ -172,16 +172,14 @@ def kernel_rooflines(wl, peak_gbs, reps=10):
     Wc = torch.randn(C, C, My, Mx, 2, device=dev) * 0.1
     ws = torch.randn(C, C, device=dev) * 0.1
     bv = torch.randn(C, device=dev)
-    T = ops.rowdft_fwd(plan, 0, x)
-    Xh = ops.coldft_fwd(plan, 0, T)
+    Xh = ops.analysis(plan, 0, x)
     Yh = ops.mix_fwd(Xh, Wc)
     Phi = ops.coldft_inv(plan, 0, Yh)
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)     # > 126 MB L2
     spec = 8 * B * C * M                                         # bytes of one [B,C,My,Mx] complex tensor
     tb = 8 * B * C * H * Mx                                      # bytes of T / Phi
     cases = {
-        "rowdft_fwd": (lambda: ops.rowdft_fwd(plan, 0, x), 4 * P + tb),
-        "coldft_fwd": (lambda: ops.coldft_fwd(plan, 0, T), tb + spec),
+        "analysis": (lambda: ops.analysis(plan, 0, x), 4 * P + spec),
         "modes_gemm(mix_fwd)": (lambda: ops.mix_fwd(Xh, Wc), 2 * spec + 8 * C * C * M),
         "modes_gemm(wgrad)": (lambda: ops.mix_bwd_weight(Xh, Yh), 2 * spec + 8 * C * C * M),
         "coldft_inv": (lambda: ops.coldft_inv(plan, 0, Yh), spec + tb),
@@ -249,8 +247,17 @@ def run_b200(args, wl, rank, world, local_rank):
             sync.allreduce()
         opt.step()
 
+    from dlwp_benchmark_b200 import _lib
+    lib = _lib.load()
+    step_eager()                                   # also the first-touch of plans / workspaces
+    torch.cuda.synchronize()
+    n0 = lib.sb200_kernel_launches()
+    step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.sb200_kernel_launches() - n0)   # kernels of libspectral_b200.so per train step
+
     use_graph = not args.no_graph
-    log(f'model built, graph={use_graph}')
+    log(f'model built, graph={use_graph}, library kernel launches per step = {launches_per_step}')
     graph = None
     if use_graph:
         s = torch.cuda.Stream()
@@ -340,7 +347,7 @@ def run_b200(args, wl, rank, world, local_rank):
             kr = kernel_rooflines(wl, peak)
             # launches per train step of each kernel on the spectral path (4 layers)
             L = wl["L"]
-            per_step = {"rowdft_fwd": 2 * L, "coldft_fwd": 2 * L, "modes_gemm(mix_fwd)": 2 * L - 0,
+            per_step = {"analysis": 2 * L, "modes_gemm(mix_fwd)": 2 * L - 0,
                         "modes_gemm(wgrad)": L, "coldft_inv": 2 * L - 0, "rowidft_pointwise(fwd)": L,
                         "rowidft_pointwise(bwd)": L - 1, "pointwise_wgrad": L}
             share = {k: v["ms"] * per_step.get(k, 1) for k, v in kr.items()}
@@ -358,7 +365,7 @@ def run_b200(args, wl, rank, world, local_rank):
             rate, med, cores = cpu_oracle_rate(wl, sample, 5, 2)
             cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": f"batch {sample} of {B}, fwd+MSE+bwd (no optimizer), median of 5, oracle restatement"}
-        n_launch = count_launches(wl)
+        n_launch = launches_per_step
         line = {
             "metric": "FNO2D train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
@@ -378,16 +385,6 @@ def run_b200(args, wl, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def count_launches(wl):
-    """Kernels of libspectral_b200.so launched per train step (counted from the call graph:
-    FNOStackFn forward = 5 per layer; backward = 2 analysis + wgrad_spec + wgrad (partial+2 reduce) +
-    [mix_bwd_input + coldft_inv + rowidft_pointwise] for every layer but the first)."""
-    L = wl["L"]
-    fwd = 5 * L
-    bwd = L * (2 + 1 + 3) + (L - 1) * 3
-    return fwd + bwd
 
 
 def main():

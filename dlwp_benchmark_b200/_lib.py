@@ -21,6 +21,7 @@ _vp, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_doub
 SIGNATURES = {
     "sb200_version": (_i, []),
     "sb200_last_error": (ctypes.c_char_p, []),
+    "sb200_kernel_launches": (_i64, []),
     "sb200_device_arch": (_i, []),
     "sb200_set_tc_mode": (_i, [_i]),
     "sb200_get_tc_mode": (_i, []),

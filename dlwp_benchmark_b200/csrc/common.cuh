@@ -48,8 +48,13 @@ void sb200_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// every kernel launch of the library is followed by exactly one SB_LAUNCH_CHECK: it also counts launches
+// (sb200_kernel_launches(), reported by bench.py as gpu_launches)
+extern unsigned long long g_sb200_launches;
+
 #define SB_LAUNCH_CHECK()                                                                \
     do {                                                                                 \
+        __atomic_fetch_add(&g_sb200_launches, 1ULL, __ATOMIC_RELAXED);                   \
         cudaError_t _e = cudaGetLastError();                                             \
         if (_e != cudaSuccess) {                                                         \
             sb200_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,       \

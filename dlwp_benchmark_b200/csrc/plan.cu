@@ -17,6 +17,8 @@ void sb200_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* sb200_last_error(void) { return g_err; }
+unsigned long long g_sb200_launches = 0;
+extern "C" int64_t sb200_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_sb200_launches, __ATOMIC_RELAXED); }
 extern "C" int sb200_version(void) { return 10000 * 0 + 100 * 1 + 0; }
 
 extern "C" int sb200_device_arch(void) {

@@ -34,6 +34,8 @@ typedef struct sb200_plan_s* sb200_plan_t;
 
 /* library / build identification: returns 10000*major + 100*minor + patch */
 int sb200_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; for launch accounting) */
+int64_t sb200_kernel_launches(void);
 /* thread-local description of the last failure (never NULL) */
 const char* sb200_last_error(void);
 /* compute capability major*10+minor of the current device, or <0 when no device */
