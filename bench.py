@@ -259,6 +259,7 @@ def run_b200(args, wl, rank, world, local_rank):
     use_graph = not args.no_graph
     log(f'model built, graph={use_graph}, library kernel launches per step = {launches_per_step}')
     graph = None
+    graph_mode = "whole step" if use_graph else "none"
     if use_graph:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -275,16 +276,35 @@ def run_b200(args, wl, rank, world, local_rank):
                 opt.step()
             step = graph.replay
         else:
-            # grads live in GradSync's flat buffer (static addresses); NCCL stays outside the graph
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                sync.zero()
-                fwd_bwd()
-
-            def step():
+            # grads live in GradSync's flat buffer (static addresses).  First choice: the whole step, NCCL
+            # all-reduce and Adam included, as ONE graph; if this NCCL build refuses capture, keep the
+            # collective and the optimizer outside the graph.
+            step = None
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    sync.zero()
+                    fwd_bwd()
+                    sync.allreduce()
+                    opt.step()
+                torch.cuda.synchronize()
                 graph.replay()
-                sync.allreduce()
-                opt.step()
+                torch.cuda.synchronize()
+                step = graph.replay
+                graph_mode = "whole step incl. NCCL all-reduce"
+            except Exception as ex:  # noqa: BLE001
+                log(f"whole-step capture failed ({ex!r}); capturing fwd+bwd only")
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    sync.zero()
+                    fwd_bwd()
+                graph_mode = "fwd+bwd (all-reduce + Adam eager)"
+
+                def step():
+                    graph.replay()
+                    sync.allreduce()
+                    opt.step()
     else:
         step = step_eager
 
@@ -372,7 +392,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [wl["H"], wl["W"]],
                        "parallelism": f"dp{world}", "step": "fwd+MSE+bwd+Adam(fused)" + ("+allreduce" if world > 1 else ""),
-                       "cuda_graph": bool(use_graph),
+                       "cuda_graph": bool(use_graph), "graph_scope": graph_mode,
                        "l2": "per-step working set (activations of 4 layers + 256-ch lifting/projection, >1 GB) exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",

@@ -34,6 +34,9 @@ SIGNATURES = {
     "sb200_analysis_scratch": (_i64, [_vp, _i64]),
     "sb200_analysis": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "sb200_modes_gemm": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
+    "sb200_mlp_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_mlp_head_bwd_workspace": (_i64, []),
+    "sb200_mlp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "sb200_cgemm_workspace": (_i64, [_vp, _i]),
     "sb200_cgemm_grouped": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb200_cgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -52,7 +52,17 @@ class FusedChainFn(torch.autograd.Function):
             bs.append(b.reshape(-1).contiguous().float() if b is not None else None)
         hs, Xhs, zs = [], [], []
         h = x
+        # fused head: the last two layers are a pointwise MLP  C -> 256 (GELU) -> 1: the hidden tensor stays on chip
+        head = (nl >= 2 and not spec[nl - 2] and not spec[nl - 1] and acts[nl - 2] and not acts[nl - 1]
+                and bs[nl - 2] is not None
+                and ops.mlp_head_supported(Ps[nl - 2].shape[1], Ps[nl - 2].shape[0], Ps[nl - 1].shape[0], H * Wd))
+        ctx.head = head
         for l in range(nl):
+            if head and l == nl - 2:
+                y = ops.mlp_head_fwd(h, Ps[l], bs[l], Ps[l + 1].reshape(-1), bs[l + 1])
+                hs += [h, None]; Xhs += [None, None]; zs += [None, None]
+                h = y
+                break
             N, M = Ps[l].shape
             want_z = acts[l] and need_grad
             Xh = None
@@ -71,8 +81,9 @@ class FusedChainFn(torch.autograd.Function):
         ctx.plan, ctx.nl, ctx.spec, ctx.acts = plan, nl, tuple(spec), tuple(acts)
         ctx.shapes = [(params[3 * l + 1].shape, params[3 * l + 2].shape if params[3 * l + 2] is not None else None)
                       for l in range(nl)]
-        saved = list(hs) + [t for t in Xhs if t is not None] + [t for t in zs if t is not None] \
-            + [t for t in Ws if t is not None] + Ps
+        ctx.has_h = [t is not None for t in hs]
+        saved = [t for t in hs if t is not None] + [t for t in Xhs if t is not None] + [t for t in zs if t is not None] \
+            + [t for t in Ws if t is not None] + Ps + ([bs[nl - 2]] if head else [])
         ctx.has_z = [t is not None for t in zs]
         ctx.save_for_backward(*saved)
         return h
@@ -82,20 +93,37 @@ class FusedChainFn(torch.autograd.Function):
         nl, spec, acts, plan = ctx.nl, ctx.spec, ctx.acts, ctx.plan
         sv = list(ctx.saved_tensors)
         it = iter(sv)
-        hs = [next(it) for _ in range(nl)]
+        hs = [next(it) if ctx.has_h[l] else None for l in range(nl)]
         Xhs = [next(it) if spec[l] else None for l in range(nl)]
         zs = [next(it) if ctx.has_z[l] else None for l in range(nl)]
         Ws = [next(it) if spec[l] else None for l in range(nl)]
         Ps = [next(it) for _ in range(nl)]
+        head_b1 = next(it) if ctx.head else None
         B = hs[0].shape[0]
         gz = gy.contiguous().float()
         if acts[nl - 1]:
             gz = ops.gelu_bwd(gz, zs[nl - 1])
         grads: List[Optional[torch.Tensor]] = [None] * (3 * nl)
         gx = None
-        for l in range(nl - 1, -1, -1):
+        top = nl - 1
+        bias_known = None
+        if ctx.head:
+            # stage 1 of the fused head backward: z1 recomputed on the tensor cores; gz1 = w2 gy gelu'(z1) and the
+            # reductions for b1, w2, b2 come out of one kernel
+            l1 = nl - 2
+            gz, gb1, gw2, gb2 = ops.mlp_head_bwd(hs[l1], Ps[l1], head_b1, Ps[nl - 1].reshape(-1), gz,
+                                                 want_gb2=ctx.shapes[nl - 1][1] is not None)
+            grads[3 * (nl - 1) + 1] = gw2.reshape(ctx.shapes[nl - 1][0])
+            if gb2 is not None:
+                grads[3 * (nl - 1) + 2] = gb2.reshape(ctx.shapes[nl - 1][1])
+            bias_known = gb1
+            top = l1
+        for l in range(top, -1, -1):
             N, M = Ps[l].shape
             has_b = ctx.shapes[l][1] is not None
+            if bias_known is not None and l == top:
+                grads[3 * l + 2] = bias_known.reshape(ctx.shapes[l][1])
+                has_b = False
             # ---- weight gradients ----
             if N <= SMALL_W and N <= M:
                 gP, gb, _ = ops.wgrad_small(gz, hs[l], False, has_b, False)

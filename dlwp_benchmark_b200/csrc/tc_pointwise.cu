@@ -98,9 +98,43 @@ struct TcPwParams {
     int H, W, Mx, R, V, K2, K2pad;
     int tpr_log2;            // log2(threads cooperating on one channel while staging Phi)
     int bias_mma;            // bias rides in the spare K column of the synthesis operands (E row K2 = 1, Phi col K2 = bias)
+    // fused MLP head (EPI 5 / 6): second (1-output) layer folded into the epilogue
+    const float* w2;         // [N] weights of the output channel
+    const float* b2;         // [1] or NULL
+    const float* gy;         // EPI 6: [B, HW] gradient of the head output
+    float* colsum_ws;        // EPI 6: [grid*4][2][256] per-warp-row partial column sums (gb1 | gw2) + [grid*4] partial sum(gy)
 };
 
 // EPI: 0 fwd linear | 1 fwd GELU, also write pre-activation z | 2 fwd GELU | 3 bwd * GELU'(zprev) | 4 bwd plain
+//      5 fused head forward:  y[b,p] = sum_n w2[n] GELU(D[p,n] + b1[n]) + b2     (the N-channel hidden never leaves the SM)
+//      6 fused head backward: recomputed D = z1;  gz1[b,n,p] = w2[n] gy[b,p] GELU'(z1) is written (y_out) and the pixel
+//        reductions gb1[n] = sum gz1, gw2[n] = sum gy GELU(z1), gb2 = sum gy leave through colsum_ws (N == 256)
+
+// sums of 16 per-lane values over the 32 lanes of a warp, transposing while reducing: 16 SHFL instead of 80.
+// Returns, in every lane, the total of column ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = h8 ? a[i + 4] : a[i], send = h8 ? a[i] : a[i + 4];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = h4 ? b[i + 2] : b[i], send = h4 ? b[i] : b[i + 2];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float keep = h2 ? c[1] : c[0], send = h2 ? c[0] : c[1];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
 template <int PASSES, int EPI>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
@@ -136,6 +170,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(phi_bar + 2);
     float* bias_s = reinterpret_cast<float*>(tail + 256);              // [256] bias for the epilogue (zeros when unused); barriers use < 256 B
     float2* rot_s = reinterpret_cast<float2*>(bias_s + 256);           // [V][Mx] tile phase table
+    float* w2_s = reinterpret_cast<float*>(rot_s + 256);               // [256]       EPI 5 / 6 (launcher adds the bytes)
+    float* red_s = w2_s + 256;                                         // [2][4][128] EPI 5 cross-warp partial sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tiles_per_b = (uint32_t)((p.HW + TP_PX - 1) / TP_PX);
@@ -173,6 +209,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         }
     }
     for (int idx = tid; idx < 256; idx += TP_THREADS) bias_s[idx] = (bias_epi && idx < p.N) ? __ldg(p.bias + idx) : 0.f;
+    if (EPI == 5 || EPI == 6)
+        for (int idx = tid; idx < 256; idx += TP_THREADS) w2_s[idx] = idx < p.N ? __ldg(p.w2 + idx) : 0.f;
     if (spectral) {
         // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
         for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
@@ -389,6 +427,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             }
         };
 
+        float hsum[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // EPI 6: column sums (gb1 x4 | gw2 x4) and sum(gy)
         if (my_tiles > 0) {
             prefetch_phi(0);
             prepare_tile(0);
@@ -420,6 +459,73 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             tc::mbar_wait(tfull_bar + a, tround & 1);
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N;
+            if constexpr (EPI == 5) {
+                // ---- fused head forward: this warp's columns -> one partial dot product per pixel ----
+                float part = 0.f;
+                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                    uint32_t r[16];
+                    tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        const float4 wq = *reinterpret_cast<const float4*>(w2_s + c0 + j);
+                        part = fmaf(wq.x, gelu_f(__uint_as_float(r[j + 0]) + bq.x), part);
+                        part = fmaf(wq.y, gelu_f(__uint_as_float(r[j + 1]) + bq.y), part);
+                        part = fmaf(wq.z, gelu_f(__uint_as_float(r[j + 2]) + bq.z), part);
+                        part = fmaf(wq.w, gelu_f(__uint_as_float(r[j + 3]) + bq.w), part);
+                    }
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+                // the four warps sharing this TMEM lane quarter hold the four column parts of the same 32 pixels
+                float* red = red_s + (it & 1) * 512;
+                red[cpart * 128 + quarter * 32 + lane] = part;
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+                if (cpart == 0 && in_range) {
+                    const int q = quarter * 32 + lane;
+                    const float y = (red[q] + red[128 + q]) + (red[256 + q] + red[384 + q]) + (p.b2 ? __ldg(p.b2) : 0.f);
+                    p.y_out[(int64_t)b * HW + pp] = y;
+                }
+                continue;
+            }
+            if constexpr (EPI == 6) {
+                // ---- fused head backward, stage 1 (N == 256: four 16-column chunks per warp) ----
+                const float gyv = in_range ? __ldg(p.gy + (int64_t)b * HW + pp) : 0.f;
+                if (cpart == 0) hsum[8] += gyv;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c0 = c_begin + 16 * ci;
+                    uint32_t r[16];
+                    tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+                    tc::tmem_ld_wait();
+                    float s0[16], s1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float z = __uint_as_float(r[j]) + bias_s[c0 + j];
+                        float cdf, e;
+                        gelu_core(z, cdf, e);
+                        const float gp = fmaf(z * 0.39894228040143267794f, e, cdf);
+                        s0[j] = w2_s[c0 + j] * gyv * gp;            // gz1 (0 outside the image: gyv = 0)
+                        s1[j] = gyv * (z * cdf);                     // gy * GELU(z1)
+                    }
+                    if (in_range) {
+                        uint64_t ya = reinterpret_cast<uint64_t>(p.y_out + ((int64_t)b * p.N + c0) * HW + pp);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            asm volatile("st.global.f32 [%0], %1;" ::"l"(ya), "f"(s0[j]) : "memory");
+                            ya += hw_bytes;
+                        }
+                    }
+                    hsum[ci] += warp_colsum16(s0, lane);
+                    hsum[4 + ci] += warp_colsum16(s1, lane);
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+                continue;
+            }
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 const int nv = min(16, c_end - c0);
                 const int64_t off0 = ((int64_t)b * p.N + c0) * HW + pp;
@@ -488,10 +594,43 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty_bar + a);
         }
+        if (EPI == 6) {
+            // flush the per-warp column sums: row = (CTA, lane quarter); each cpart owns 64 of the 256 columns
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            float* row = p.colsum_ws + (size_t)(blockIdx.x * 4 + quarter) * 512;
+            if (!(lane & 1)) {
+    #pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    row[cpart * 64 + 16 * ci + col] = hsum[ci];
+                    row[256 + cpart * 64 + 16 * ci + col] = hsum[4 + ci];
+                }
+            }
+            if (cpart == 0) {
+                float g = hsum[8];
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                if (lane == 0) p.colsum_ws[(size_t)gridDim.x * 4 * 512 + blockIdx.x * 4 + quarter] = g;
+            }
+        }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// out[0][n] = gb1, out[1][n] = gw2 (n < 256), gb2 = sum(gy): fixed-order sums over the (CTA, quarter) rows
+__global__ void __launch_bounds__(256) head_colsum_reduce_kernel(const float* __restrict__ ws, int rows, float* __restrict__ gb1,
+                                                                 float* __restrict__ gw2, float* __restrict__ gb2, int N) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;      // 0..511
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += ws[(size_t)r * 512 + idx];
+    if (idx < 256) { if (idx < N) gb1[idx] = acc; }
+    else if (idx - 256 < N) gw2[idx - 256] = acc;
+    if (idx == 0 && gb2) {
+        float g = 0.f;
+        for (int r = 0; r < rows; ++r) g += ws[(size_t)rows * 512 + r];
+        *gb2 = g;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -585,5 +724,93 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
 #undef TP_LAUNCH
     SB_LAUNCH_CHECK();
     *handled = 1;
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fused pointwise MLP head (projection of the FNO: C -> N=256 -> 1 channel)
+// ---------------------------------------------------------------------------------------------
+static int tp_head_launch(int epi, const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
+                          const float* gy, float* out, float* ws, int B, int M, int N, int64_t HW, cudaStream_t st,
+                          unsigned* grid_out) {
+    SB_REQUIRE(g_tc_mode != 0, "mlp_head: the fused head runs on the tcgen05 path (tc mode 1 or 3)");
+    SB_REQUIRE(M % 8 == 0 && (M <= 32 || M % 32 == 0), "mlp_head: in-channels %d not supported (multiple of 8; of 32 above 32)", M);
+    SB_REQUIRE(N == 256, "mlp_head: hidden width must be 256 (got %d)", N);
+    SB_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (int64_t)B * M < (1LL << 31), "mlp_head: layout");
+    const int passes = g_tc_mode;
+    TcPwParams p;
+    memset(&p, 0, sizeof(p));
+    p.Wp = W1; p.w_sn = M; p.w_sm = 1; p.bias = b1; p.y_out = out; p.B = B; p.M = M; p.N = N; p.HW = HW;
+    p.KC = M < 32 ? M : 32;
+    p.nkc = M / p.KC;
+    p.idesc = tc::make_idesc_tf32(128, N, 1, 0);
+    p.idesc_spec = tc::make_idesc_tf32(128, N, 0, 0);
+    p.tmem_cols = 512;
+    p.ntiles = (HW + TP_PX - 1) / TP_PX * B;
+    p.w2 = w2; p.b2 = b2; p.gy = gy; p.colsum_ws = ws;
+    const size_t mult = passes == 3 ? 2 : 1;
+    const size_t a_stage = (size_t)p.KC * 512 * mult;
+    const size_t b_bytes = ((((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * mult);
+    const size_t fixed = 1024 + b_bytes + 512 + 1024 + 2048 + 1024 + 4096;      // + barriers, bias_s, rot_s, w2_s, red_s
+    int stages = 6;
+    while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
+    SB_REQUIRE(fixed + stages * a_stage <= 227 * 1024, "mlp_head: shared memory does not fit (M=%d)", M);
+    p.stages = stages;
+    const size_t smem = fixed + stages * a_stage;
+    CUtensorMap tmap;
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, h, (uint64_t)HW, (uint64_t)B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2)) return rc;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        SB_CHECK_CUDA(cudaGetDevice(&dev));
+        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
+    *grid_out = grid;
+    int tl = 0;
+    while ((1 << (tl + 1)) * N <= TP_WTHREADS) ++tl;
+    p.tpr_log2 = tl;
+#define TP_HEAD(PS, EP)                                                                                                \
+    do {                                                                                                               \
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem));                                                                \
+        tc_pointwise_kernel<PS, EP><<<grid, TP_THREADS, smem, st>>>(tmap, p);                                          \
+    } while (0)
+    if (epi == 5) { if (passes == 3) TP_HEAD(3, 5); else TP_HEAD(1, 5); }
+    else          { if (passes == 3) TP_HEAD(3, 6); else TP_HEAD(1, 6); }
+#undef TP_HEAD
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int tp_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return 148;
+    }
+    return g_num_sms;
+}
+
+extern "C" int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
+                                  float* y, int B, int M, int N, int64_t HW, void* stream) {
+    SB_REQUIRE(h && W1 && b1 && w2 && y, "mlp_head_fwd: NULL argument");
+    if (B <= 0) return 0;
+    unsigned grid;
+    return tp_head_launch(5, h, W1, b1, w2, b2, nullptr, y, nullptr, B, M, N, HW, (cudaStream_t)stream, &grid);
+}
+
+extern "C" int64_t sb200_mlp_head_bwd_workspace(void) { return (int64_t)tp_sms() * 4 * 513; }
+
+extern "C" int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const float* w2, const float* gy,
+                                  float* gz1, float* gb1, float* gw2, float* gb2, float* workspace, int B, int M, int N,
+                                  int64_t HW, void* stream) {
+    SB_REQUIRE(h && W1 && b1 && w2 && gy && gz1 && gb1 && gw2 && workspace, "mlp_head_bwd: NULL argument");
+    if (B <= 0) return 0;
+    unsigned grid;
+    if (int rc = tp_head_launch(6, h, W1, b1, w2, nullptr, gy, gz1, workspace, B, M, N, HW, (cudaStream_t)stream, &grid)) return rc;
+    head_colsum_reduce_kernel<<<2, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw2, gb2, N);
+    SB_LAUNCH_CHECK();
     return 0;
 }

@@ -212,3 +212,38 @@ def cgemm(A, B, C, *, M: int, N: int, K: int, sAm, sAk, sBk, sBn, sCm, sCn,
     arr = lambda ts: (ctypes.c_void_p * ng)(*[t.data_ptr() for t in ts])
     _lib.check(lib.sb200_cgemm_grouped(ctypes.byref(d), ng, arr(As), arr(Bs), arr(Cs), _p(ws), _stream()), "cgemm")
     return C
+
+
+def mlp_head_supported(M: int, N: int, n_out: int, HW: int) -> bool:
+    """Shapes the fused head kernels cover (sb200_mlp_head_fwd / _bwd)."""
+    return (n_out == 1 and N == 256 and M % 8 == 0 and (M <= 32 or M % 32 == 0) and HW % 4 == 0
+            and _lib.load().sb200_get_tc_mode() != 0)
+
+
+def mlp_head_fwd(h, W1, b1, w2, b2):
+    """y[b,0,:,:] = w2 . gelu(W1 h + b1) + b2;  h [B,M,H,W], W1 [256,M], b1 [256], w2 [256], b2 [1] or None."""
+    for t, n in ((h, "h"), (W1, "W1"), (b1, "b1"), (w2, "w2")):
+        _req(t, n)
+    B, M, H, W = h.shape
+    y = torch.empty(B, 1, H, W, device=h.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_mlp_head_fwd(_p(h), _p(W1), _p(b1), _p(w2), _p(b2), _p(y), B, M, W1.shape[0], H * W,
+                                              _stream()), "mlp_head_fwd")
+    return y
+
+
+def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True):
+    """Returns (gz1 [B,256,H,W], gb1 [256], gw2 [256], gb2 [1] or None)."""
+    for t, n in ((h, "h"), (W1, "W1"), (b1, "b1"), (w2, "w2"), (gy, "gy")):
+        _req(t, n)
+    B, M, H, W = h.shape
+    N = W1.shape[0]
+    lib = _lib.load()
+    dev = h.device
+    gz1 = torch.empty(B, N, H, W, device=dev, dtype=torch.float32)
+    gb1 = torch.empty(N, device=dev, dtype=torch.float32)
+    gw2 = torch.empty(N, device=dev, dtype=torch.float32)
+    gb2 = torch.empty(1, device=dev, dtype=torch.float32) if want_gb2 else None
+    ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=dev, dtype=torch.float32)
+    _lib.check(lib.sb200_mlp_head_bwd(_p(h), _p(W1), _p(b1), _p(w2), _p(gy), _p(gz1), _p(gb1), _p(gw2), _p(gb2), _p(ws),
+                                      B, M, N, H * W, _stream()), "mlp_head_bwd")
+    return gz1, gb1, gw2, gb2

@@ -96,6 +96,23 @@ int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp,
                      float* out, int64_t sOp, int64_t sOq,
                      int P, int Q, int R, int K, int conj_flags, void* stream);
 
+/* Fused pointwise MLP head (the FNO projection  C -> 256 -> 1,  neuralop FNO.projection = MLP(n_layers=2),
+ * reached from src/nsbench/models/fno/fno.py:19-27):
+ *      y[b,p] = sum_n w2[n] * gelu( sum_m W1[n,m] h[b,m,p] + b1[n] ) + b2
+ * on the tcgen05 path; the 256-channel hidden tensor never reaches HBM.  h [B,M,HW], W1 [256,M], y [B,HW].
+ * Restrictions (else non-zero return, caller uses the two-kernel path): N == 256, M % 8 == 0 (M % 32 == 0
+ * above 32), HW % 4 == 0, tc mode != 0. */
+int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
+                       float* y, int B, int M, int N, int64_t HW, void* stream);
+/* Backward, stage 1: recomputes z1 = W1 h + b1 on the tensor cores and writes
+ *      gz1[b,n,p] = w2[n] gy[b,p] gelu'(z1[b,n,p])          (input of the W1 weight / data gradient kernels)
+ *      gb1[n] = sum_{b,p} gz1,   gw2[n] = sum_{b,p} gy gelu(z1),   gb2 = sum gy   (gb2 may be NULL)
+ * workspace: sb200_mlp_head_bwd_workspace() floats. */
+int64_t sb200_mlp_head_bwd_workspace(void);
+int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const float* w2, const float* gy,
+                       float* gz1, float* gb1, float* gw2, float* gb2, float* workspace, int B, int M, int N,
+                       int64_t HW, void* stream);
+
 /* Strided complex GEMM   C[m,n] = sum_k opA(A[m,k]) * opB(B[k,n])   (complex64, strides in complex elements).
  * m and k may be two-level composite indices: m -> (m / M2, m % M2) addressed with (s?m1, s?m2), likewise k
  * with K2 (M2 = 1 / K2 = 1: plain index using the *2 stride).  This expresses every mode product, core /

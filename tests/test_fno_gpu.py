@@ -438,3 +438,47 @@ def test_small_m_pointwise(B, M, N, H, W):
     assert rel_l2(z, ref_z) < TOL
     assert rel_l2(y, torch.nn.functional.gelu(ref_z)) < TOL
     assert rel_l2(g, (ref_z - bias.double().view(1, -1, 1, 1)) * zp.grad) < TOL
+
+
+@pytest.mark.parametrize("B,M,H,W", [(2, 64, 64, 64), (3, 32, 16, 32), (1, 16, 8, 16), (5, 64, 32, 64)])
+def test_fused_mlp_head(B, M, H, W):
+    """sb200_mlp_head_fwd / _bwd (projection C -> 256 -> 1 with the hidden tensor on chip) vs fp64 torch."""
+    N = 256
+    h = _rand(B, M, H, W, seed=1)
+    W1 = _rand(N, M, seed=2, scale=M ** -0.5)
+    b1 = _rand(N, seed=3, scale=0.3)
+    w2 = _rand(N, seed=4, scale=N ** -0.5)
+    b2 = _rand(1, seed=5)
+    gy = _rand(B, 1, H, W, seed=6)
+    ho, W1o, b1o, w2o, b2o = (t.double().requires_grad_(True) for t in (h, W1, b1, w2, b2))
+    z1 = torch.einsum("nm,bmhw->bnhw", W1o, ho) + b1o.view(1, -1, 1, 1)
+    z1.retain_grad()
+    yo = torch.einsum("n,bnhw->bhw", w2o, torch.nn.functional.gelu(z1)).unsqueeze(1) + b2o
+    yo.backward(gy.double())
+    d = lambda t: t.to(DEV).contiguous()
+    yc = ops.mlp_head_fwd(d(h), d(W1), d(b1), d(w2), d(b2))
+    assert rel_l2(yc, yo) < TOL
+    gz1, gb1, gw2, gb2 = ops.mlp_head_bwd(d(h), d(W1), d(b1), d(w2), d(gy))
+    assert rel_l2(gz1, z1.grad) < TOL
+    assert rel_l2(gb1, b1o.grad) < 2e-5
+    assert rel_l2(gw2, w2o.grad) < 2e-5
+    assert rel_l2(gb2, b2o.grad) < 2e-5
+
+
+def test_model_with_fused_head_vs_oracle():
+    """Whole FNO (projection_channels = 256 -> fused head path) forward + all gradients against the oracle."""
+    torch.manual_seed(7)
+    m = pkg.FNO(n_modes=(8, 8), hidden_channels=32, in_channels=1, out_channels=1, lifting_channels=256,
+                projection_channels=256, n_layers=2)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    x = _rand(3, 1, 32, 32, seed=1)
+    tgt = _rand(3, 1, 32, 32, seed=2)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    yo = so.fno_forward(leaves, x.double(), (8, 8), 2)
+    torch.nn.functional.mse_loss(yo, tgt.double()).backward()
+    m = m.to(DEV)
+    yc = m(x.to(DEV))
+    torch.nn.functional.mse_loss(yc, tgt.to(DEV)).backward()
+    assert rel_l2(yc, yo) < TOL
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad, leaves[k].grad) < 2e-5, k
