@@ -37,6 +37,7 @@ SIGNATURES = {
     "sb200_mlp_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "sb200_mlp_head_bwd_workspace": (_i64, []),
     "sb200_mlp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_lift_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "sb200_cgemm_workspace": (_i64, [_vp, _i]),
     "sb200_cgemm_grouped": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb200_cgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -57,6 +57,12 @@ class FusedChainFn(torch.autograd.Function):
                 and bs[nl - 2] is not None
                 and ops.mlp_head_supported(Ps[nl - 2].shape[1], Ps[nl - 2].shape[0], Ps[nl - 1].shape[0], H * Wd))
         ctx.head = head
+        # lifting tail: a 1-input-channel lifting MLP  x -> gelu(w1 x + b1) [256] -> C: its pre-activation is
+        # recomputed from x in the backward (sb200_lift_tail_bwd), so z_0 is never written
+        lift_tail = (nl >= 2 and need_grad and not ctx.needs_input_grad[0] and not spec[0] and not spec[1] and acts[0]
+                     and tuple(Ps[0].shape) == (256, 1) and bs[0] is not None and Ps[1].shape[1] == 256
+                     and ops.mlp_head_supported(Ps[1].shape[0], 256, 1, H * Wd))
+        ctx.lift_tail = lift_tail
         for l in range(nl):
             if head and l == nl - 2:
                 y = ops.mlp_head_fwd(h, Ps[l], bs[l], Ps[l + 1].reshape(-1), bs[l + 1])
@@ -64,7 +70,7 @@ class FusedChainFn(torch.autograd.Function):
                 h = y
                 break
             N, M = Ps[l].shape
-            want_z = acts[l] and need_grad
+            want_z = acts[l] and need_grad and not (lift_tail and l == 0)
             Xh = None
             if spec[l]:
                 Xh = ops.analysis(plan, 0, h)
@@ -83,7 +89,7 @@ class FusedChainFn(torch.autograd.Function):
                       for l in range(nl)]
         ctx.has_h = [t is not None for t in hs]
         saved = [t for t in hs if t is not None] + [t for t in Xhs if t is not None] + [t for t in zs if t is not None] \
-            + [t for t in Ws if t is not None] + Ps + ([bs[nl - 2]] if head else [])
+            + [t for t in Ws if t is not None] + Ps + ([bs[nl - 2]] if head else []) + ([bs[0]] if lift_tail else [])
         ctx.has_z = [t is not None for t in zs]
         ctx.save_for_backward(*saved)
         return h
@@ -99,6 +105,7 @@ class FusedChainFn(torch.autograd.Function):
         Ws = [next(it) if spec[l] else None for l in range(nl)]
         Ps = [next(it) for _ in range(nl)]
         head_b1 = next(it) if ctx.head else None
+        lift_b1 = next(it) if ctx.lift_tail else None
         B = hs[0].shape[0]
         gz = gy.contiguous().float()
         if acts[nl - 1]:
@@ -138,6 +145,12 @@ class FusedChainFn(torch.autograd.Function):
             if spec[l]:
                 gYh = ops.analysis(plan, 1, gz)
                 grads[3 * l] = ops.mix_bwd_weight(Xhs[l], gYh)
+            if ctx.lift_tail and l == 1:
+                # gz_0 = (P_1^T gz) gelu'(w1 x + b1) stays on chip; only its two pixel reductions leave
+                gw1, gb1 = ops.lift_tail_bwd(gz, Ps[1], Ps[0].reshape(-1), lift_b1, hs[0])
+                grads[1] = gw1.reshape(ctx.shapes[0][0])
+                grads[2] = gb1.reshape(ctx.shapes[0][1])
+                break
             # ---- data gradient (fused with GELU' of the previous layer) ----
             if l > 0 or ctx.needs_input_grad[0]:
                 gPhi = ops.coldft_inv(plan, 1, ops.mix_bwd_input(gYh, Ws[l])) if spec[l] else None

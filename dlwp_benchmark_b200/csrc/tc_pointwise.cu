@@ -109,6 +109,8 @@ struct TcPwParams {
 //      5 fused head forward:  y[b,p] = sum_n w2[n] GELU(D[p,n] + b1[n]) + b2     (the N-channel hidden never leaves the SM)
 //      6 fused head backward: recomputed D = z1;  gz1[b,n,p] = w2[n] gy[b,p] GELU'(z1) is written (y_out) and the pixel
 //        reductions gb1[n] = sum gz1, gw2[n] = sum gy GELU(z1), gb2 = sum gy leave through colsum_ws (N == 256)
+//      7 fused lifting-tail backward (1 input channel):  gz1[n,p] = D[p,n] GELU'(w1[n] x[p] + b1[n]) is never stored;
+//        only gb1[n] = sum_p gz1 and gw1[n] = sum_p gz1 x[p] leave, through colsum_ws (w2 = w1, bias = b1, gy = x)
 
 // sums of 16 per-lane values over the 32 lanes of a warp, transposing while reducing: 16 SHFL instead of 80.
 // Returns, in every lane, the total of column ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
@@ -209,7 +211,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         }
     }
     for (int idx = tid; idx < 256; idx += TP_THREADS) bias_s[idx] = (bias_epi && idx < p.N) ? __ldg(p.bias + idx) : 0.f;
-    if (EPI == 5 || EPI == 6)
+    if (EPI == 5 || EPI == 6 || EPI == 7)
         for (int idx = tid; idx < 256; idx += TP_THREADS) w2_s[idx] = idx < p.N ? __ldg(p.w2 + idx) : 0.f;
     if (spectral) {
         // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
@@ -526,6 +528,30 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 if (lane == 0) tc::mbar_arrive(tempty_bar + a);
                 continue;
             }
+            if constexpr (EPI == 7) {
+                const float xv = in_range ? __ldg(p.gy + (int64_t)b * HW + pp) : 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c0 = c_begin + 16 * ci;
+                    uint32_t r[16];
+                    tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+                    tc::tmem_ld_wait();
+                    float s0[16], s1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float z = fmaf(w2_s[c0 + j], xv, bias_s[c0 + j]);
+                        const float gzv = in_range ? __uint_as_float(r[j]) * gelu_grad_f(z) : 0.f;
+                        s0[j] = gzv;
+                        s1[j] = gzv * xv;
+                    }
+                    hsum[ci] += warp_colsum16(s0, lane);
+                    hsum[4 + ci] += warp_colsum16(s1, lane);
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+                continue;
+            }
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 const int nv = min(16, c_end - c0);
                 const int64_t off0 = ((int64_t)b * p.N + c0) * HW + pp;
@@ -594,7 +620,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty_bar + a);
         }
-        if (EPI == 6) {
+        if (EPI == 6 || EPI == 7) {
             // flush the per-warp column sums: row = (CTA, lane quarter); each cpart owns 64 of the 256 columns
             const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
             float* row = p.colsum_ws + (size_t)(blockIdx.x * 4 + quarter) * 512;
@@ -618,18 +644,35 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// out[0][n] = gb1, out[1][n] = gw2 (n < 256), gb2 = sum(gy): fixed-order sums over the (CTA, quarter) rows
+// out[0][n] = gb1, out[1][n] = gw2 (n < 256), gb2 = sum(gy): fixed-order sums over the (CTA, quarter) rows.
+// 32 consecutive outputs x 8 row lanes per block (coalesced partial reads), shared-memory tree at the end.
 __global__ void __launch_bounds__(256) head_colsum_reduce_kernel(const float* __restrict__ ws, int rows, float* __restrict__ gb1,
                                                                  float* __restrict__ gw2, float* __restrict__ gb2, int N) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;      // 0..511
-    float acc = 0.f;
-    for (int r = 0; r < rows; ++r) acc += ws[(size_t)r * 512 + idx];
-    if (idx < 256) { if (idx < N) gb1[idx] = acc; }
-    else if (idx - 256 < N) gw2[idx - 256] = acc;
-    if (idx == 0 && gb2) {
+    __shared__ float part[8][33];
+    const int o = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    if (blockIdx.x == 16) {                              // gb2: the tail of the workspace
         float g = 0.f;
-        for (int r = 0; r < rows; ++r) g += ws[(size_t)rows * 512 + r];
-        *gb2 = g;
+        for (int r = threadIdx.x; r < rows; r += 256) g += ws[(size_t)rows * 512 + r];
+        part[rl][o] = g;
+        __syncthreads();
+        if (threadIdx.x == 0 && gb2) {
+            float t = 0.f;
+            for (int a = 0; a < 8; ++a)
+                for (int c = 0; c < 32; ++c) t += part[a][c];
+            *gb2 = t;
+        }
+        return;
+    }
+    const int idx = blockIdx.x * 32 + o;                 // 0..511
+    float acc = 0.f;
+    for (int r = rl; r < rows; r += 8) acc += ws[(size_t)r * 512 + idx];
+    part[rl][o] = acc;
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int a = 1; a < 8; ++a) acc += part[a][o];
+        if (idx < 256) { if (idx < N) gb1[idx] = acc; }
+        else if (idx - 256 < N) gw2[idx - 256] = acc;
     }
 }
 
@@ -731,9 +774,9 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
 // ---------------------------------------------------------------------------------------------
 // fused pointwise MLP head (projection of the FNO: C -> N=256 -> 1 channel)
 // ---------------------------------------------------------------------------------------------
-static int tp_head_launch(int epi, const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
-                          const float* gy, float* out, float* ws, int B, int M, int N, int64_t HW, cudaStream_t st,
-                          unsigned* grid_out) {
+static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn, int64_t w_sm, const float* b1,
+                          const float* w2, const float* b2, const float* gy, float* out, float* ws, int B, int M, int N,
+                          int64_t HW, cudaStream_t st, unsigned* grid_out) {
     SB_REQUIRE(g_tc_mode != 0, "mlp_head: the fused head runs on the tcgen05 path (tc mode 1 or 3)");
     SB_REQUIRE(M % 8 == 0 && (M <= 32 || M % 32 == 0), "mlp_head: in-channels %d not supported (multiple of 8; of 32 above 32)", M);
     SB_REQUIRE(N == 256, "mlp_head: hidden width must be 256 (got %d)", N);
@@ -741,7 +784,7 @@ static int tp_head_launch(int epi, const float* h, const float* W1, const float*
     const int passes = g_tc_mode;
     TcPwParams p;
     memset(&p, 0, sizeof(p));
-    p.Wp = W1; p.w_sn = M; p.w_sm = 1; p.bias = b1; p.y_out = out; p.B = B; p.M = M; p.N = N; p.HW = HW;
+    p.Wp = W1; p.w_sn = w_sn; p.w_sm = w_sm; p.bias = b1; p.y_out = out; p.B = B; p.M = M; p.N = N; p.HW = HW;
     p.KC = M < 32 ? M : 32;
     p.nkc = M / p.KC;
     p.idesc = tc::make_idesc_tf32(128, N, 1, 0);
@@ -776,8 +819,9 @@ static int tp_head_launch(int epi, const float* h, const float* W1, const float*
                                            (int)smem));                                                                \
         tc_pointwise_kernel<PS, EP><<<grid, TP_THREADS, smem, st>>>(tmap, p);                                          \
     } while (0)
-    if (epi == 5) { if (passes == 3) TP_HEAD(3, 5); else TP_HEAD(1, 5); }
-    else          { if (passes == 3) TP_HEAD(3, 6); else TP_HEAD(1, 6); }
+    if (epi == 5)      { if (passes == 3) TP_HEAD(3, 5); else TP_HEAD(1, 5); }
+    else if (epi == 6) { if (passes == 3) TP_HEAD(3, 6); else TP_HEAD(1, 6); }
+    else               { if (passes == 3) TP_HEAD(3, 7); else TP_HEAD(1, 7); }
 #undef TP_HEAD
     SB_LAUNCH_CHECK();
     return 0;
@@ -798,7 +842,7 @@ extern "C" int sb200_mlp_head_fwd(const float* h, const float* W1, const float* 
     SB_REQUIRE(h && W1 && b1 && w2 && y, "mlp_head_fwd: NULL argument");
     if (B <= 0) return 0;
     unsigned grid;
-    return tp_head_launch(5, h, W1, b1, w2, b2, nullptr, y, nullptr, B, M, N, HW, (cudaStream_t)stream, &grid);
+    return tp_head_launch(5, h, W1, M, 1, b1, w2, b2, nullptr, y, nullptr, B, M, N, HW, (cudaStream_t)stream, &grid);
 }
 
 extern "C" int64_t sb200_mlp_head_bwd_workspace(void) { return (int64_t)tp_sms() * 4 * 513; }
@@ -809,8 +853,25 @@ extern "C" int sb200_mlp_head_bwd(const float* h, const float* W1, const float* 
     SB_REQUIRE(h && W1 && b1 && w2 && gy && gz1 && gb1 && gw2 && workspace, "mlp_head_bwd: NULL argument");
     if (B <= 0) return 0;
     unsigned grid;
-    if (int rc = tp_head_launch(6, h, W1, b1, w2, nullptr, gy, gz1, workspace, B, M, N, HW, (cudaStream_t)stream, &grid)) return rc;
-    head_colsum_reduce_kernel<<<2, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw2, gb2, N);
+    if (int rc = tp_head_launch(6, h, W1, M, 1, b1, w2, nullptr, gy, gz1, workspace, B, M, N, HW, (cudaStream_t)stream, &grid)) return rc;
+    head_colsum_reduce_kernel<<<17, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw2, gb2, N);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Lifting tail backward for a 1-input-channel lifting MLP  x -> gelu(w1 x + b1) [256] -> W2 [C,256]:
+//   gz1[b,n,p] = (sum_c W2[c,n] g[b,c,p]) * gelu'(w1[n] x[b,p] + b1[n])  stays on chip; only
+//   gb1[n] = sum gz1 and gw1[n] = sum gz1 x leave.   g [B,C,HW], W2 [C,256] (row-major), x [B,HW].
+extern "C" int sb200_lift_tail_bwd(const float* g, const float* W2, const float* w1, const float* b1, const float* x,
+                                   float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW,
+                                   void* stream) {
+    SB_REQUIRE(g && W2 && w1 && b1 && x && gw1 && gb1 && workspace, "lift_tail_bwd: NULL argument");
+    if (B <= 0) return 0;
+    unsigned grid;
+    // out channel n of the transposed product reads W2[c, n]: stride 1 over n, N over the contraction index c
+    if (int rc = tp_head_launch(7, g, W2, 1, N, b1, w1, nullptr, x, nullptr, workspace, B, C, N, HW, (cudaStream_t)stream, &grid))
+        return rc;
+    head_colsum_reduce_kernel<<<17, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw1, nullptr, N);
     SB_LAUNCH_CHECK();
     return 0;
 }

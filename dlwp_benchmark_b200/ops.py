@@ -247,3 +247,19 @@ def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True):
     _lib.check(lib.sb200_mlp_head_bwd(_p(h), _p(W1), _p(b1), _p(w2), _p(gy), _p(gz1), _p(gb1), _p(gw2), _p(gb2), _p(ws),
                                       B, M, N, H * W, _stream()), "mlp_head_bwd")
     return gz1, gb1, gw2, gb2
+
+
+def lift_tail_bwd(g, W2, w1, b1, x):
+    """Backward of the first lifting layer for a 1-channel input: returns (gw1 [256], gb1 [256]).
+    g [B,C,H,W] gradient wrt the lifting output, W2 [C,256], w1/b1 [256], x [B,1,H,W]."""
+    for t, n in ((g, "g"), (W2, "W2"), (w1, "w1"), (b1, "b1"), (x, "x")):
+        _req(t, n)
+    B, C, H, W = g.shape
+    N = W2.shape[1]
+    lib = _lib.load()
+    gw1 = torch.empty(N, device=g.device, dtype=torch.float32)
+    gb1 = torch.empty(N, device=g.device, dtype=torch.float32)
+    ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=g.device, dtype=torch.float32)
+    _lib.check(lib.sb200_lift_tail_bwd(_p(g), _p(W2), _p(w1), _p(b1), _p(x), _p(gw1), _p(gb1), _p(ws), B, C, N, H * W,
+                                       _stream()), "lift_tail_bwd")
+    return gw1, gb1

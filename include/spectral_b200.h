@@ -113,6 +113,15 @@ int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const f
                        float* gz1, float* gb1, float* gw2, float* gb2, float* workspace, int B, int M, int N,
                        int64_t HW, void* stream);
 
+/* Backward of the first lifting layer when the model has ONE input channel (neuralop FNO.lifting =
+ * MLP(in_channels=1, hidden=256, out=C); src/nsbench/configs/model/fno.yaml): with g = gradient wrt the lifting
+ * output [B,C,HW],
+ *      gz1[b,n,p] = (sum_c W2[c,n] g[b,c,p]) * gelu'(w1[n] x[b,p] + b1[n])      (recomputed from x, never stored)
+ *      gb1[n] = sum_{b,p} gz1,     gw1[n] = sum_{b,p} gz1 x[b,p]
+ * Same restrictions and workspace as sb200_mlp_head_bwd (N == 256, C % 8 == 0, ...). */
+int sb200_lift_tail_bwd(const float* g, const float* W2, const float* w1, const float* b1, const float* x,
+                        float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW, void* stream);
+
 /* Strided complex GEMM   C[m,n] = sum_k opA(A[m,k]) * opB(B[k,n])   (complex64, strides in complex elements).
  * m and k may be two-level composite indices: m -> (m / M2, m % M2) addressed with (s?m1, s?m2), likewise k
  * with K2 (M2 = 1 / K2 = 1: plain index using the *2 stride).  This expresses every mode product, core /

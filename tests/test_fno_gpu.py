@@ -482,3 +482,22 @@ def test_model_with_fused_head_vs_oracle():
     assert rel_l2(yc, yo) < TOL
     for k, p in m.named_parameters():
         assert rel_l2(p.grad, leaves[k].grad) < 2e-5, k
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 64, 64), (3, 32, 16, 32), (1, 16, 8, 16)])
+def test_lift_tail_bwd(B, C, H, W):
+    """sb200_lift_tail_bwd: gradients of (w1, b1) of a 1-input-channel lifting MLP with gz1 kept on chip."""
+    N = 256
+    x = _rand(B, 1, H, W, seed=1)
+    w1 = _rand(N, seed=2)
+    b1 = _rand(N, seed=3, scale=0.3)
+    W2 = _rand(C, N, seed=4, scale=N ** -0.5)
+    g = _rand(B, C, H, W, seed=5)
+    w1o, b1o = w1.double().requires_grad_(True), b1.double().requires_grad_(True)
+    h1 = torch.nn.functional.gelu(w1o.view(1, -1, 1, 1) * x.double() + b1o.view(1, -1, 1, 1))
+    out = torch.einsum("cn,bnhw->bchw", W2.double(), h1)
+    out.backward(g.double())
+    d = lambda t: t.to(DEV).contiguous()
+    gw1, gb1 = ops.lift_tail_bwd(d(g), d(W2), d(w1), d(b1), d(x))
+    assert rel_l2(gw1, w1o.grad) < 2e-5
+    assert rel_l2(gb1, b1o.grad) < 2e-5
