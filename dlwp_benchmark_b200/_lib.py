@@ -38,6 +38,8 @@ SIGNATURES = {
     "sb200_mlp_head_bwd_workspace": (_i64, []),
     "sb200_mlp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "sb200_lift_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_lift_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_lift_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "sb200_cgemm_workspace": (_i64, [_vp, _i]),
     "sb200_cgemm_grouped": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb200_cgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -63,7 +63,20 @@ class FusedChainFn(torch.autograd.Function):
                      and tuple(Ps[0].shape) == (256, 1) and bs[0] is not None and Ps[1].shape[1] == 256
                      and ops.mlp_head_supported(Ps[1].shape[0], 256, 1, H * Wd))
         ctx.lift_tail = lift_tail
+        # ... and when the shapes allow, the whole lifting MLP runs with its hidden tensor generated on chip
+        lift_gen = (nl >= 2 and not spec[0] and not spec[1] and acts[0] and not acts[1] and tuple(Ps[0].shape) == (256, 1)
+                    and bs[0] is not None and Ps[1].shape[1] == 256 and ops.lift_supported(Ps[1].shape[0], 256, H * Wd)
+                    and (lift_tail or not need_grad))
+        ctx.lift_gen = lift_gen
         for l in range(nl):
+            if lift_gen and l == 0:
+                hs.append(h); Xhs.append(None); zs.append(None)          # x itself is all the backward needs
+                continue
+            if lift_gen and l == 1:
+                y = ops.lift_fwd(x, Ps[0].reshape(-1), bs[0], Ps[1], bs[1])
+                hs.append(None); Xhs.append(None); zs.append(None)
+                h = y
+                continue
             if head and l == nl - 2:
                 y = ops.mlp_head_fwd(h, Ps[l], bs[l], Ps[l + 1].reshape(-1), bs[l + 1])
                 hs += [h, None]; Xhs += [None, None]; zs += [None, None]
@@ -132,7 +145,9 @@ class FusedChainFn(torch.autograd.Function):
                 grads[3 * l + 2] = bias_known.reshape(ctx.shapes[l][1])
                 has_b = False
             # ---- weight gradients ----
-            if N <= SMALL_W and N <= M:
+            if ctx.lift_gen and l == 1:
+                gP, gb = ops.lift_wgrad(gz, hs[0], Ps[0].reshape(-1), lift_b1, want_bias=has_b)
+            elif N <= SMALL_W and N <= M:
                 gP, gb, _ = ops.wgrad_small(gz, hs[l], False, has_b, False)
             elif M <= SMALL_W:
                 gP, _, gb = ops.wgrad_small(hs[l], gz, True, False, has_b)

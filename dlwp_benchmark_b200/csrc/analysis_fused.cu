@@ -18,7 +18,11 @@
 #include "tc_common.cuh"
 
 constexpr int AF_ROWS = 256;                 // image rows per group
-constexpr int AF_RTHREADS = 128;             // row-stage threads (2 rows each)
+#ifndef AF_RTHREADS_V
+#define AF_RTHREADS_V 256
+#endif
+constexpr int AF_RTHREADS = AF_RTHREADS_V;   // row-stage threads
+constexpr int AF_RPT = AF_ROWS / AF_RTHREADS; // image rows per row-stage thread
 constexpr int AF_CTHREADS = 160;             // column-stage threads
 constexpr int AF_THREADS = AF_RTHREADS + AF_CTHREADS;
 
@@ -105,18 +109,20 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
             tc::mbar_wait(xfull + b, par);
             tc::mbar_wait(tempty + b, par ^ 1);
             const uint8_t* xb = xbuf + (uint32_t)b * xbuf_bytes;
-            float2 are[2][MXE / 2], aim[2][MXE / 2];       // (k, k+1) pairs
-            float carry[2] = {0.f, 0.f};
+            float2 are[AF_RPT][MXE / 2], aim[AF_RPT][MXE / 2];       // (k, k+1) pairs
+            float carry[AF_RPT];
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < AF_RPT; ++q) carry[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < AF_RPT; ++q)
 #pragma unroll
                 for (int k = 0; k < MXE / 2; ++k) { are[q][k] = make_float2(0.f, 0.f); aim[q][k] = make_float2(0.f, 0.f); }
 #pragma unroll 1
             for (int c = 0; c < nch / 2; ++c) {
                 const int cm = nch - 1 - c;
-                float e[2][4], o[2][4];
+                float e[AF_RPT][4], o[AF_RPT][4];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < AF_RPT; ++q) {
                     const int r = tid + q * AF_RTHREADS;
                     const uint8_t* rowp = xb + (uint32_t)r * 128;
                     const float4 xa = af_lds128(rowp + (uint32_t)(c >> 3) * half_bytes + (uint32_t)(((c & 7) ^ (r & 7)) << 4));
@@ -142,7 +148,7 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
 #pragma unroll
                     for (int k = 0; k < MXE / 2; ++k)
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
+                        for (int q = 0; q < AF_RPT; ++q) {
                             are[q][k] = ffma2(make_float2(e[q][j], e[q][j]), tw[k], are[q][k]);
                             aim[q][k] = ffma2(make_float2(o[q][j], o[q][j]), tw[MXE / 2 + k], aim[q][k]);
                         }
@@ -153,11 +159,11 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
 #pragma unroll
                 for (int k = 0; k < MXE / 2; ++k)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) are[q][k] = ffma2(make_float2(carry[q], carry[q]), twp[k], are[q][k]);
+                    for (int q = 0; q < AF_RPT; ++q) are[q][k] = ffma2(make_float2(carry[q], carry[q]), twp[k], are[q][k]);
             }
             float2* Tb = Tbuf + (size_t)b * AF_ROWS * MX;
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < AF_RPT; ++q)
 #pragma unroll
                 for (int k = 0; k < MX; ++k) {
                     const float re = (k & 1) ? are[q][k / 2].y : are[q][k / 2].x;

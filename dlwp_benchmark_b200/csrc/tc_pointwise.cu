@@ -137,7 +137,9 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     return d;
 }
-template <int PASSES, int EPI>
+// ASRC: 0 = activation tiles arrive by TMA | 1 = generated on chip: A[m, px] = GELU(w1[m] x[b, px] + b1[m]), the hidden
+//       layer of a 1-input-channel lifting MLP (w1 = p.w2, b1 = p.b2, x = p.gy): the 256-channel tensor never exists in HBM
+template <int PASSES, int EPI, int ASRC = 0>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -213,6 +215,11 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     for (int idx = tid; idx < 256; idx += TP_THREADS) bias_s[idx] = (bias_epi && idx < p.N) ? __ldg(p.bias + idx) : 0.f;
     if (EPI == 5 || EPI == 6 || EPI == 7)
         for (int idx = tid; idx < 256; idx += TP_THREADS) w2_s[idx] = idx < p.N ? __ldg(p.w2 + idx) : 0.f;
+    if (ASRC == 1)
+        for (int idx = tid; idx < 256; idx += TP_THREADS) {
+            w2_s[idx] = idx < p.M ? __ldg(p.w2 + idx) : 0.f;
+            red_s[idx] = idx < p.M ? __ldg(p.b2 + idx) : 0.f;
+        }
     if (spectral) {
         // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
         for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
@@ -251,7 +258,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && nkc) {
+        if (lane == 0 && nkc && ASRC == 0) {
             uint32_t s = 0, ph = 0;                                 // ring position / phase
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const uint32_t tile = first + it * stride;
@@ -307,7 +314,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     }
                 }
                 for (int kc = 0; kc < nkc; ++kc) {
-                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
+                    tc::mbar_wait(((PASSES == 3 || ASRC == 1) ? split_bar : full_bar) + s, ph);
                     tc::tc_fence_after_sync();
                     uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + s * a_stage_bytes), a_lbo);
                     uint32_t al = ah + (a_bytes >> 4);
@@ -410,7 +417,51 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(phi_bar + (it & 1));
             }
-            if (PASSES == 3) {
+            if (ASRC == 1) {
+                // generate the operand: thread -> (channel row k_local, 8-pixel chunk c8) of every 32-channel K chunk
+                const uint32_t tile = first + it * stride;
+                const uint32_t b = tile / tiles_per_b;
+                const int64_t px = (int64_t)(tile - b * tiles_per_b) * TP_PX + (wtid & 15) * 8;
+                float xv[8];
+                {
+                    const float* xs = p.gy + (int64_t)b * p.HW + px;
+                    if (px + 8 <= p.HW) {
+                        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xs)), x1 = __ldg(reinterpret_cast<const float4*>(xs) + 1);
+                        xv[0] = x0.x; xv[1] = x0.y; xv[2] = x0.z; xv[3] = x0.w; xv[4] = x1.x; xv[5] = x1.y; xv[6] = x1.z; xv[7] = x1.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) xv[j] = px + j < p.HW ? __ldg(xs + j) : 0.f;
+                    }
+                }
+                const int k_local = wtid >> 4, c8 = wtid & 15;
+                const uint32_t goff = tc::sw128b32_mnmajor_off(c8 * 8, k_local, (uint32_t)KC * 128u);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(empty_bar + sp_s, sp_ph ^ 1);          // MMAs that read this stage are done
+                    const int m = kc * KC + k_local;
+                    const float w = w2_s[m], bb = red_s[m];
+                    float hv[8], lv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float g = gelu_f(fmaf(w, xv[j], bb));
+                        hv[j] = tc::tf32_trunc(g);
+                        lv[j] = g - hv[j];
+                    }
+                    if (k_local < KC) {
+                        float4* dh = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + goff);
+                        dh[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                        dh[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                        if (PASSES == 3) {
+                            float4* dl = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + a_bytes + goff);
+                            dl[0] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+                            dl[1] = make_float4(lv[4], lv[5], lv[6], lv[7]);
+                        }
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
+                }
+            } else if (PASSES == 3) {
                 for (int kc = 0; kc < nkc; ++kc) {
                     tc::mbar_wait(full_bar + sp_s, sp_ph);
                     float4* ah = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes);
@@ -872,6 +923,57 @@ extern "C" int sb200_lift_tail_bwd(const float* g, const float* W2, const float*
     if (int rc = tp_head_launch(7, g, W2, 1, N, b1, w1, nullptr, x, nullptr, workspace, B, C, N, HW, (cudaStream_t)stream, &grid))
         return rc;
     head_colsum_reduce_kernel<<<17, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw1, nullptr, N);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Lifting MLP forward for ONE input channel (neuralop FNO.lifting = MLP(1 -> 256 -> C)):
+//      y[b,c,p] = sum_n W2[c,n] gelu(w1[n] x[b,p] + b1[n]) + b2[c]
+// the hidden operand is generated tile by tile in shared memory (ASRC = 1), so it never reaches HBM.
+extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, float* y,
+                              int B, int N, int C, int64_t HW, void* stream) {
+    SB_REQUIRE(x && w1 && b1 && W2 && y, "lift_fwd: NULL argument");
+    SB_REQUIRE(g_tc_mode != 0, "lift_fwd: runs on the tcgen05 path (tc mode 1 or 3)");
+    SB_REQUIRE(N == 256, "lift_fwd: hidden width must be 256 (got %d)", N);
+    SB_REQUIRE(C % 16 == 0 && C >= 16 && C <= 256, "lift_fwd: output channels %d not supported", C);
+    SB_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "lift_fwd: layout");
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int passes = g_tc_mode;
+    TcPwParams p;
+    memset(&p, 0, sizeof(p));
+    p.Wp = W2; p.w_sn = N; p.w_sm = 1; p.bias = b2; p.y_out = y; p.B = B; p.M = N; p.N = C; p.HW = HW;
+    p.KC = 32; p.nkc = N / 32;
+    p.idesc = tc::make_idesc_tf32(128, C, 1, 0);
+    p.idesc_spec = tc::make_idesc_tf32(128, C, 0, 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * C)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.ntiles = (HW + TP_PX - 1) / TP_PX * B;
+    p.w2 = w1; p.b2 = b1; p.gy = x;
+    const size_t mult = passes == 3 ? 2 : 1;
+    const size_t a_stage = (size_t)p.KC * 512 * mult;
+    const size_t b_bytes = ((((size_t)(N / 32) * C * 128 + 1023) & ~(size_t)1023) * mult);
+    const size_t fixed = 1024 + b_bytes + 512 + 1024 + 2048 + 1024 + 4096;
+    int stages = 6;
+    while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
+    SB_REQUIRE(fixed + stages * a_stage <= 227 * 1024, "lift_fwd: shared memory does not fit (C=%d)", C);
+    p.stages = stages;
+    const size_t smem = fixed + stages * a_stage;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const int sms = tp_sms();
+    const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
+    int tl = 0;
+    while ((1 << (tl + 1)) * C <= TP_WTHREADS) ++tl;
+    p.tpr_log2 = tl;
+    if (passes == 3) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_pointwise_kernel<3, 0, 1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
+    } else {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_pointwise_kernel<1, 0, 1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
+    }
     SB_LAUNCH_CHECK();
     return 0;
 }

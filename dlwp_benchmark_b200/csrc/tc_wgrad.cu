@@ -27,9 +27,12 @@ struct TcWgParams {
     int64_t items_per_b, nitems;
     float* ws;               // [grid][mblocks*128][Qc]
     uint32_t idesc, tmem_cols;
+    // ASRC = 1: the A side is generated on chip, P[n, px] = GELU(w1[n] x[b, px] + b1[n]) (hidden layer of a 1-input-channel
+    // lifting MLP), instead of being read from HBM
+    const float* gen_x; const float* gen_w1; const float* gen_b1;
 };
 
-template <int PASSES>
+template <int PASSES, int ASRC = 0>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapQ, const TcWgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -40,7 +43,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     const uint32_t p_chunk = (uint32_t)p.Pc * 128, q_chunk = (uint32_t)p.Qc * 128;
     const uint32_t ones_bytes = (uint32_t)(p.Qn - p.Qc) * 128;         // constant rows [1,1,...; 0...] behind the Q rows
     const uint32_t chunk_bytes = p_chunk + q_chunk + ones_bytes;       // [P rows | Q rows | ones], 128 B per row
-    const uint32_t tma_bytes = (uint32_t)CH * (p_chunk + q_chunk);
+    const uint32_t tma_bytes = (uint32_t)CH * (ASRC ? q_chunk : p_chunk + q_chunk);
     const uint32_t raw_bytes = (uint32_t)CH * chunk_bytes;
     const uint32_t stage_bytes = raw_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
     uint8_t* St = base;
@@ -106,7 +109,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                 uint8_t* dst = St + s * stage_bytes;
                 tc::mbar_expect_tx(full_bar + s, tma_bytes);
                 for (int j = 0; j < CH; ++j) {
-                    tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes, &tmapP, px0 + 32 * j, (int)b * p.Pc, full_bar + s);
+                    if (ASRC == 0)
+                        tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes, &tmapP, px0 + 32 * j, (int)b * p.Pc, full_bar + s);
                     tc::tma_load_2d(dst + (uint32_t)j * chunk_bytes + p_chunk, &tmapQ, px0 + 32 * j, (int)b * p.Qc, full_bar + s);
                 }
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -120,7 +124,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             const uint32_t mb_step = (128u * 128u) >> 4;
             uint32_t s = 0, ph = 0, ra = 0;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
-                tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
+                tc::mbar_wait(((PASSES == 3 || ASRC == 1) ? split_bar : full_bar) + s, ph);
                 tc::tc_fence_after_sync();
                 const uint32_t base_lo = tc::desc_lo(tc::smem_u32(St + s * stage_bytes), 16);
                 const uint32_t dacc = tmem_base + ra * (uint32_t)(p.mblocks * p.Qn);
@@ -156,7 +160,52 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     } else {
         const int wk = warp - 2;
         const int wtid = tid - 64;
-        if (PASSES == 3) {
+        if (ASRC == 1) {
+            // thread -> 16-byte piece (4 px) `piece` of rows (wtid >> 3) + 64 i of every 32-px chunk
+            const int piece = wtid & 7, row0 = wtid >> 3;
+            const uint32_t items_per_b = (uint32_t)p.items_per_b;
+            uint32_t s = 0, ph = 0;
+            for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
+                const uint32_t item = (uint32_t)i0 + q;
+                const uint32_t b = item / items_per_b;
+                const int64_t px0 = (int64_t)(item - b * items_per_b) * 32 * CH;
+                tc::mbar_wait(empty_bar + s, ph ^ 1);                 // MMAs that read this stage are done
+                uint8_t* sb = St + s * stage_bytes;
+                for (int j = 0; j < CH; ++j) {
+                    const int64_t px = px0 + 32 * j + piece * 4;
+                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (px + 4 <= p.HW) xv = __ldg(reinterpret_cast<const float4*>(p.gen_x + (int64_t)b * p.HW + px));
+                    for (int row = row0; row < p.Pc; row += 64) {
+                        const float w = __ldg(p.gen_w1 + row), bb = __ldg(p.gen_b1 + row);
+                        float4 g = make_float4(gelu_f(fmaf(w, xv.x, bb)), gelu_f(fmaf(w, xv.y, bb)), gelu_f(fmaf(w, xv.z, bb)),
+                                               gelu_f(fmaf(w, xv.w, bb)));
+                        if (px + 4 > p.HW) g = make_float4(0.f, 0.f, 0.f, 0.f);     // pixels outside the image contribute nothing
+                        const float4 h = make_float4(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y), tc::tf32_trunc(g.z), tc::tf32_trunc(g.w));
+                        const uint32_t off = (uint32_t)j * chunk_bytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((piece ^ (row & 7)) << 4));
+                        *reinterpret_cast<float4*>(sb + off) = h;
+                        if (PASSES == 3)
+                            *reinterpret_cast<float4*>(sb + raw_bytes + off) = make_float4(g.x - h.x, g.y - h.y, g.z - h.z, g.w - h.w);
+                    }
+                }
+                tc::mbar_wait(full_bar + s, ph);                       // Q side landed
+                if (PASSES == 3) {
+                    for (int j = 0; j < CH; ++j) {
+                        float4* ah = reinterpret_cast<float4*>(sb + (uint32_t)j * chunk_bytes + p_chunk);
+                        float4* al = reinterpret_cast<float4*>(sb + raw_bytes + (uint32_t)j * chunk_bytes + p_chunk);
+                        for (int idx = wtid; idx < (int)(q_chunk / 16); idx += 32 * TW_WORKER_WARPS) {
+                            const float4 v = ah[idx];
+                            const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                            ah[idx] = h;
+                            al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        }
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(split_bar + s);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+            }
+        } else if (PASSES == 3) {
             uint32_t s = 0, ph = 0;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
                 tc::mbar_wait(full_bar + s, ph);
@@ -294,18 +343,22 @@ int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
     return (int64_t)tw_num_sms() * mblocks * 128 * (Qc + 16) + (int64_t)B * Cout;
 }
 
-int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
-                             int64_t HW, float* workspace, cudaStream_t st, int* handled) {
+static int tw_launch(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin, int64_t HW,
+                     float* workspace, cudaStream_t st, int* handled, const float* gen_x, const float* gen_w1,
+                     const float* gen_b1) {
     *handled = 0;
+    const bool gen = gen_x != nullptr;
     const int passes = sb200_get_tc_mode();
     int Pc, Qc, tr;
     if (passes == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
-    if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return 0;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) || (!gen && (reinterpret_cast<uintptr_t>(x) & 15))) return 0;
+    if (gen && (tr != 1 || (reinterpret_cast<uintptr_t>(gen_x) & 15))) return 0;      // the generated tensor is the wide (A) side
     if ((int64_t)B * Pc >= (1LL << 31)) return 0;
     const float* Pt = tr ? x : g;
     const float* Qt = tr ? g : x;
 
     TcWgParams p;
+    p.gen_x = gen_x; p.gen_w1 = gen_w1; p.gen_b1 = gen_b1;
     p.Pc = Pc; p.Qc = Qc; p.mblocks = (Pc + 127) / 128; p.HW = HW;
     // bias gradient = sum over pixels of g: free from the MMA when g is the A side (ones-row appended to the B side)
     const bool bias_mma = passes == 3 && gbias != nullptr && tr == 0 && Qc + 16 <= 256 && p.mblocks * (Qc + 16) <= 512;
@@ -337,9 +390,19 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
     const unsigned grid = (unsigned)(p.nitems < sms ? p.nitems : sms);
 
     CUtensorMap tmP, tmQ;
-    if (int rc = sb200_make_tmap_2d_f32(&tmP, Pt, (uint64_t)HW, (uint64_t)B * Pc, (uint64_t)HW * 4, 32, (uint32_t)Pc, 1)) return rc;
     if (int rc = sb200_make_tmap_2d_f32(&tmQ, Qt, (uint64_t)HW, (uint64_t)B * Qc, (uint64_t)HW * 4, 32, (uint32_t)Qc, 1)) return rc;
-    if (passes == 3) {
+    if (gen) {
+        tmP = tmQ;     // unused by the kernel
+        if (passes == 3) {
+            SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_wgrad_kernel<3, 1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+        } else {
+            SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_wgrad_kernel<1, 1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+        }
+    } else if (int rc = sb200_make_tmap_2d_f32(&tmP, Pt, (uint64_t)HW, (uint64_t)B * Pc, (uint64_t)HW * 4, 32, (uint32_t)Pc, 1)) {
+        return rc;
+    } else if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_wgrad_kernel<3><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
     } else {
@@ -360,5 +423,26 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
         SB_LAUNCH_CHECK();
     }
     *handled = 1;
+    return 0;
+}
+
+int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
+                             int64_t HW, float* workspace, cudaStream_t st, int* handled) {
+    return tw_launch(g, x, gW, gbias, B, Cout, Cin, HW, workspace, st, handled, nullptr, nullptr, nullptr);
+}
+
+// Weight gradient of the second lifting layer for a 1-input-channel lifting MLP:
+//      gW2[c, n] = sum_{b,p} g[b,c,p] gelu(w1[n] x[b,p] + b1[n]),   gb2[c] = sum_{b,p} g[b,c,p]
+// the hidden activations are regenerated on chip (ASRC = 1) instead of being re-read from HBM.
+// workspace: sb200_pointwise_wgrad_workspace(B, C, 256, HW) floats.
+extern "C" int sb200_lift_wgrad(const float* g, const float* x, const float* w1, const float* b1, float* gW2, float* gb2,
+                                float* workspace, int B, int C, int N, int64_t HW, void* stream) {
+    SB_REQUIRE(g && x && w1 && b1 && gW2 && workspace, "lift_wgrad: NULL argument");
+    SB_REQUIRE(sb200_get_tc_mode() != 0, "lift_wgrad: runs on the tcgen05 path (tc mode 1 or 3)");
+    SB_REQUIRE(N > C, "lift_wgrad: the hidden width (%d) must exceed the output channels (%d)", N, C);
+    if (B <= 0) return 0;
+    int handled = 0;
+    if (int rc = tw_launch(g, nullptr, gW2, gb2, B, C, N, HW, workspace, (cudaStream_t)stream, &handled, x, w1, b1)) return rc;
+    SB_REQUIRE(handled, "lift_wgrad: shape not covered by the tcgen05 kernel (C=%d, N=%d, HW=%lld)", C, N, (long long)HW);
     return 0;
 }

@@ -263,3 +263,35 @@ def lift_tail_bwd(g, W2, w1, b1, x):
     _lib.check(lib.sb200_lift_tail_bwd(_p(g), _p(W2), _p(w1), _p(b1), _p(x), _p(gw1), _p(gb1), _p(ws), B, C, N, H * W,
                                        _stream()), "lift_tail_bwd")
     return gw1, gb1
+
+
+def lift_supported(C: int, N: int, HW: int) -> bool:
+    """Shapes the generated-operand lifting kernels cover (1 input channel, hidden 256)."""
+    return (N == 256 and C % 16 == 0 and 16 <= C < N and HW % 4 == 0 and _lib.load().sb200_get_tc_mode() != 0)
+
+
+def lift_fwd(x, w1, b1, W2, b2):
+    """y = W2 gelu(w1 x + b1) + b2 for x [B,1,H,W]; w1/b1 [256], W2 [C,256], b2 [C] or None -> y [B,C,H,W]."""
+    for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (W2, "W2")):
+        _req(t, n)
+    B, _, H, W = x.shape
+    C, N = W2.shape
+    y = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_lift_fwd(_p(x), _p(w1), _p(b1), _p(W2), _p(b2), _p(y), B, N, C, H * W, _stream()),
+               "lift_fwd")
+    return y
+
+
+def lift_wgrad(g, x, w1, b1, want_bias: bool = True):
+    """(gW2 [C,256], gb2 [C] or None) with the hidden activations regenerated from x on chip."""
+    for t, n in ((g, "g"), (x, "x"), (w1, "w1"), (b1, "b1")):
+        _req(t, n)
+    B, C, H, W = g.shape
+    N = w1.numel()
+    lib = _lib.load()
+    ws = torch.empty(lib.sb200_pointwise_wgrad_workspace(B, C, N, H * W), device=g.device, dtype=torch.float32)
+    gW2 = torch.empty(C, N, device=g.device, dtype=torch.float32)
+    gb2 = torch.empty(C, device=g.device, dtype=torch.float32) if want_bias else None
+    _lib.check(lib.sb200_lift_wgrad(_p(g), _p(x), _p(w1), _p(b1), _p(gW2), _p(gb2), _p(ws), B, C, N, H * W, _stream()),
+               "lift_wgrad")
+    return gW2, gb2

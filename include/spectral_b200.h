@@ -122,6 +122,18 @@ int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const f
 int sb200_lift_tail_bwd(const float* g, const float* W2, const float* w1, const float* b1, const float* x,
                         float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW, void* stream);
 
+/* Lifting MLP of a ONE-input-channel model, forward:   y[b,c,p] = sum_n W2[c,n] gelu(w1[n] x[b,p] + b1[n]) + b2[c]
+ * (neuralop FNO.lifting = MLP(1 -> 256 -> C)).  The 256-channel hidden operand is generated tile by tile in
+ * shared memory and consumed by tcgen05.mma: it never exists in HBM.  x [B,HW], W2 [C,256], y [B,C,HW];
+ * N == 256, C % 16 == 0, HW % 4 == 0, tc mode != 0. */
+int sb200_lift_fwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, float* y,
+                   int B, int N, int C, int64_t HW, void* stream);
+/* ... and the weight gradient of its second layer with the hidden activations regenerated on chip:
+ *      gW2[c,n] = sum_{b,p} g[b,c,p] gelu(w1[n] x[b,p] + b1[n]),   gb2[c] = sum_{b,p} g[b,c,p]   (gb2 may be NULL)
+ * workspace: sb200_pointwise_wgrad_workspace(B, C, N, HW) floats. */
+int sb200_lift_wgrad(const float* g, const float* x, const float* w1, const float* b1, float* gW2, float* gb2,
+                     float* workspace, int B, int C, int N, int64_t HW, void* stream);
+
 /* Strided complex GEMM   C[m,n] = sum_k opA(A[m,k]) * opB(B[k,n])   (complex64, strides in complex elements).
  * m and k may be two-level composite indices: m -> (m / M2, m % M2) addressed with (s?m1, s?m2), likewise k
  * with K2 (M2 = 1 / K2 = 1: plain index using the *2 stride).  This expresses every mode product, core /

@@ -501,3 +501,25 @@ def test_lift_tail_bwd(B, C, H, W):
     gw1, gb1 = ops.lift_tail_bwd(d(g), d(W2), d(w1), d(b1), d(x))
     assert rel_l2(gw1, w1o.grad) < 2e-5
     assert rel_l2(gb1, b1o.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 64, 64), (3, 32, 16, 32), (1, 16, 8, 16), (2, 64, 12, 20)])
+def test_lift_fwd_and_wgrad_generated_operand(B, C, H, W):
+    """sb200_lift_fwd / sb200_lift_wgrad: the 256-channel hidden tensor is generated on chip, never stored."""
+    N = 256
+    x = _rand(B, 1, H, W, seed=1)
+    w1 = _rand(N, seed=2)
+    b1 = _rand(N, seed=3, scale=0.3)
+    W2 = _rand(C, N, seed=4, scale=N ** -0.5)
+    b2 = _rand(C, seed=6)
+    g = _rand(B, C, H, W, seed=5)
+    W2o, b2o = W2.double().requires_grad_(True), b2.double().requires_grad_(True)
+    h1 = torch.nn.functional.gelu(w1.double().view(1, -1, 1, 1) * x.double() + b1.double().view(1, -1, 1, 1))
+    out = torch.einsum("cn,bnhw->bchw", W2o, h1) + b2o.view(1, -1, 1, 1)
+    out.backward(g.double())
+    d = lambda t: t.to(DEV).contiguous()
+    y = ops.lift_fwd(d(x), d(w1), d(b1), d(W2), d(b2))
+    assert rel_l2(y, out) < TOL
+    gW2, gb2 = ops.lift_wgrad(d(g), d(x), d(w1), d(b1))
+    assert rel_l2(gW2, W2o.grad) < 2e-5
+    assert rel_l2(gb2, b2o.grad) < 2e-5
