@@ -19,6 +19,8 @@ template <int KG, int CPT>
 __global__ void __launch_bounds__(128)
 cl_rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab /*[W][Mx]*/,
                      float2* __restrict__ T, int W, int Mx, int C) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float2 ts[CLR_WC][KG];
     const int64_t row = blockIdx.x;
     const int c0 = (blockIdx.y * 128 + threadIdx.x) * CPT;
@@ -77,7 +79,7 @@ template <int KG, int CPT>
 static int launch_cl_rowdft(const float* x, const float2* tab, float2* T, int64_t rows, int W, int Mx, int C,
                             cudaStream_t st) {
     dim3 grid((unsigned)rows, (unsigned)((C / CPT + 127) / 128));
-    cl_rowdft_fwd_kernel<KG, CPT><<<grid, 128, 0, st>>>(x, tab, T, W, Mx, C);
+    sb_launch(cl_rowdft_fwd_kernel<KG, CPT>, grid, 128, 0, st, x, tab, T, W, Mx, C);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -107,6 +109,8 @@ template <int KG, int CPT>
 __global__ void __launch_bounds__(128)
 cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__ tab /*[Mx][W]*/,
                       const float* __restrict__ resid, float* __restrict__ y, int W, int Mx, int C, int accumulate) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ float2 tsm[];     // [KG][W]
     const int64_t row = blockIdx.x;
     const int c0 = (blockIdx.y * 128 + threadIdx.x) * CPT;
@@ -167,7 +171,7 @@ static int launch_cl_rowidft(const float2* Phi, const float2* tab, const float* 
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(cl_rowidft_res_kernel<KG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)rows, (unsigned)((C / CPT + 127) / 128), 1);
-    cl_rowidft_res_kernel<KG, CPT><<<grid, 128, smem, st>>>(Phi, tab, resid, y, W, Mx, C, 0);
+    sb_launch(cl_rowidft_res_kernel<KG, CPT>, grid, 128, smem, st, Phi, tab, resid, y, W, Mx, C, 0);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -202,6 +206,8 @@ constexpr int CLC_IC = 32;
 __global__ void __launch_bounds__(128)
 cl_coldft_kernel(const float2* __restrict__ in, const float2* __restrict__ tab /*[J][I]*/, float2* __restrict__ out,
                  int I, int J, int Mx, int C) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float2 ts[CLC_JG][CLC_IC + 1];
     const int b = blockIdx.x / Mx, kx = blockIdx.x % Mx;
     const int c = blockIdx.y * 128 + threadIdx.x;
@@ -238,7 +244,7 @@ cl_coldft_kernel(const float2* __restrict__ in, const float2* __restrict__ tab /
 static int cl_coldft(const float2* in, const float2* tab, float2* out, int B, int I, int J, int Mx, int C, cudaStream_t st) {
     SB_REQUIRE((int64_t)B * Mx < (1LL << 31), "cl_coldft: too many columns");
     dim3 grid((unsigned)(B * Mx), (unsigned)((C + 127) / 128), (unsigned)((J + CLC_JG - 1) / CLC_JG));
-    cl_coldft_kernel<<<grid, 128, 0, st>>>(in, tab, out, I, J, Mx, C);
+    sb_launch(cl_coldft_kernel, grid, 128, 0, st, in, tab, out, I, J, Mx, C);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -288,6 +294,8 @@ constexpr int BL_TOK = 64, BL_KC = 16, BL_OT = 32;
 
 __global__ void __launch_bounds__(256)
 blocklinear_kernel(const BlParams p) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float2 Xs[BL_TOK][BL_KC + 1];
     __shared__ __align__(16) float Wrs[BL_KC][BL_OT];
     __shared__ __align__(16) float Wis[BL_KC][BL_OT];
@@ -360,7 +368,7 @@ static int launch_blocklinear(const BlParams& p, cudaStream_t st) {
     if (p.ntok <= 0) return 0;
     SB_REQUIRE(ceil_div64(p.ntok, BL_TOK) < (1LL << 31), "blocklinear: too many tokens");
     dim3 grid((unsigned)ceil_div64(p.ntok, BL_TOK), (unsigned)p.nb, (unsigned)((p.No + BL_OT - 1) / BL_OT));
-    blocklinear_kernel<<<grid, 256, 0, st>>>(p);
+    sb_launch(blocklinear_kernel, grid, 256, 0, st, p);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -401,6 +409,8 @@ __global__ void __launch_bounds__(256)
 blocklinear_wgrad_kernel(const float2* __restrict__ a, const float2* __restrict__ g, const float2* __restrict__ mask_src,
                          int mask_kind, float* __restrict__ ws, int64_t ntok, int64_t chunk_tok, int nb, int Ni, int No,
                          int o_tiles) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ __align__(16) float2 As[BW_T][32];
     __shared__ __align__(16) float2 Gs[BW_T][32];
     const int tid = threadIdx.x;
@@ -487,6 +497,8 @@ blocklinear_wgrad_kernel(const float2* __restrict__ a, const float2* __restrict_
 __global__ void __launch_bounds__(256)
 chunk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out0, int64_t n0, float* __restrict__ out1,
                     int64_t n1, int nchunks) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t E = n0 + n1;
     if (e >= E) return;
@@ -524,13 +536,13 @@ extern "C" int sb200_afno_blocklinear_wgrad(const float* a, const float* gout, c
     bw_chunking(ntok, nb, &ct, &nc);
     const int i_tiles = (Ni + 31) / 32, o_tiles = (No + 31) / 32;
     dim3 grid(nc, nb, i_tiles * o_tiles);
-    blocklinear_wgrad_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(a),
+    sb_launch(blocklinear_wgrad_kernel, grid, 256, 0, st, reinterpret_cast<const float2*>(a),
                                                    reinterpret_cast<const float2*>(gout),
                                                    reinterpret_cast<const float2*>(fwd_out), mask_kind, workspace, ntok,
                                                    ct, nb, Ni, No, o_tiles);
     SB_LAUNCH_CHECK();
     const int64_t n0 = 2 * (int64_t)nb * Ni * No, n1 = 2 * (int64_t)nb * No;
-    chunk_reduce_kernel<<<(unsigned)ceil_div64(n0 + n1, 256), 256, 0, st>>>(workspace, gw, n0, gb, n1, nc);
+    sb_launch(chunk_reduce_kernel, (unsigned)ceil_div64(n0 + n1, 256), 256, 0, st, workspace, gw, n0, gb, n1, nc);
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -40,6 +40,7 @@ __device__ __forceinline__ float4 af_lds128(const uint8_t* p) { return *reinterp
 template <int MX>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams p) {
+    sb_pdl_launch();
     constexpr int MXE = (MX + 1) & ~1;                   // MX rounded up to even: accumulators are fp32x2 pairs over k
     constexpr int TWS = 2 * MXE;                         // floats per row-twiddle record [C0..C(MX-1), 0?, S0..S(MX-1), 0?]
     static_assert(TWS % 4 == 0, "row-twiddle records are read as float4");
@@ -83,6 +84,7 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
         ctw[idx] = k < My ? __ldg(p.colF + (size_t)k * H + y) : make_float2(0.f, 0.f);
     }
     __syncthreads();
+    sb_pdl_wait();          // the twiddle tables above are immutable plan data; x is the preceding kernel's output
 
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_groups = first < p.ngroups ? (p.ngroups - first + stride - 1) / stride : 0;
@@ -267,7 +269,7 @@ int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh,
     case MXV:                                                                                                           \
         SB_CHECK_CUDA(cudaFuncSetAttribute(analysis_fused_kernel<MXV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                            (int)smem));                                                                  \
-        analysis_fused_kernel<MXV><<<grid, AF_THREADS, smem, st>>>(tmap, p);                                             \
+        sb_launch(analysis_fused_kernel<MXV>, grid, AF_THREADS, smem, st, tmap, p);                                             \
         break;
     switch (Mx) {
         AF_LAUNCH(5) AF_LAUNCH(7) AF_LAUNCH(9) AF_LAUNCH(13) AF_LAUNCH(17)

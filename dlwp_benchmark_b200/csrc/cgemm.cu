@@ -44,6 +44,8 @@ __device__ __forceinline__ long long cg_off2(int idx, int inner, long long s1, l
 
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(CG_THREADS) cgemm_kernel(const CgParams p) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     static_assert((BM / TM) * (BN / TN) == CG_THREADS, "thread tiling must cover the block tile");
     constexpr int LA = BM * CG_BK / CG_THREADS, LB = BN * CG_BK / CG_THREADS;
     static_assert(LA >= 1 && LB >= 1, "tile too small");
@@ -176,6 +178,8 @@ constexpr int CS_MAXK = 64;
 
 template <int NP>
 __global__ void __launch_bounds__(CS_THREADS) cskinny_kernel(const CgParams p) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ __align__(16) float4 Bs[CS_MAXK * NP];
     const int g = blockIdx.y;
     const float2* __restrict__ Ag = p.A[g];
@@ -259,6 +263,8 @@ struct CgOut { float2* C[CG_MAXG]; };
 __global__ void __launch_bounds__(256) cgemm_reduce_kernel(const float2* __restrict__ ws, const CgOut out, int M, int N,
                                                            int splits, int M2, long long sCm1, long long sCm2,
                                                            long long sCn) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float2 part[8][32];
     const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const long long MN = (long long)M * N;
@@ -359,25 +365,25 @@ extern "C" int sb200_cgemm_grouped(const sb200_cgemm_desc* d, int ngroups, const
     }
     if (skinny) {
         dim3 sgrid((unsigned)((d->M + 2 * CS_THREADS - 1) / (2 * CS_THREADS)), (unsigned)ngroups);
-        if (d->N <= 8) cskinny_kernel<8><<<sgrid, CS_THREADS, 0, st>>>(p);
-        else if (d->N <= 16) cskinny_kernel<16><<<sgrid, CS_THREADS, 0, st>>>(p);
-        else cskinny_kernel<32><<<sgrid, CS_THREADS, 0, st>>>(p);
+        if (d->N <= 8) sb_launch(cskinny_kernel<8>, sgrid, CS_THREADS, 0, st, p);
+        else if (d->N <= 16) sb_launch(cskinny_kernel<16>, sgrid, CS_THREADS, 0, st, p);
+        else sb_launch(cskinny_kernel<32>, sgrid, CS_THREADS, 0, st, p);
         SB_LAUNCH_CHECK();
         return 0;
     }
     const CgShape t = cg_pick(d->M, d->N);
     dim3 grid((unsigned)((d->M + t.bm - 1) / t.bm), (unsigned)((d->N + t.bn - 1) / t.bn), (unsigned)(p.splits * ngroups));
     SB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "cgemm: grid too large");
-    if (t.bm == 16) cgemm_kernel<16, 16, 1, 1><<<grid, CG_THREADS, 0, st>>>(p);
-    else if (t.bm == 32) cgemm_kernel<32, 32, 2, 2><<<grid, CG_THREADS, 0, st>>>(p);
-    else if (t.bm == 256) cgemm_kernel<256, 16, 4, 4><<<grid, CG_THREADS, 0, st>>>(p);
-    else if (t.bm == 128) cgemm_kernel<128, 32, 4, 4><<<grid, CG_THREADS, 0, st>>>(p);
-    else cgemm_kernel<64, 64, 4, 4><<<grid, CG_THREADS, 0, st>>>(p);
+    if (t.bm == 16) sb_launch(cgemm_kernel<16, 16, 1, 1>, grid, CG_THREADS, 0, st, p);
+    else if (t.bm == 32) sb_launch(cgemm_kernel<32, 32, 2, 2>, grid, CG_THREADS, 0, st, p);
+    else if (t.bm == 256) sb_launch(cgemm_kernel<256, 16, 4, 4>, grid, CG_THREADS, 0, st, p);
+    else if (t.bm == 128) sb_launch(cgemm_kernel<128, 32, 4, 4>, grid, CG_THREADS, 0, st, p);
+    else sb_launch(cgemm_kernel<64, 64, 4, 4>, grid, CG_THREADS, 0, st, p);
     SB_LAUNCH_CHECK();
     if (p.partial) {
         const long long MN = (long long)d->M * d->N;
         dim3 rgrid((unsigned)((MN + 31) / 32), (unsigned)ngroups);
-        cgemm_reduce_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const float2*>(workspace), out, d->M, d->N, p.splits,
+        sb_launch(cgemm_reduce_kernel, rgrid, 256, 0, st, reinterpret_cast<const float2*>(workspace), out, d->M, d->N, p.splits,
                                                    d->M2, d->sCm1, d->sCm2, d->sCn);
         SB_LAUNCH_CHECK();
     }

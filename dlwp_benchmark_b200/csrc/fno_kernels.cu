@@ -20,6 +20,8 @@ template <int KPT>
 __global__ void __launch_bounds__(256)
 rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab, float2* __restrict__ T,
                   int64_t R, int W, int Mx, int vec_ok) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float xs[RD_ROWS][RD_XC + 1];
     __shared__ float2 ts[RD_XC][4 * KPT];
     const int tid = threadIdx.x;
@@ -100,7 +102,7 @@ extern "C" int sb200_rowdft_fwd(sb200_plan_t p, int pass, const float* x, float*
     dim3 grid((unsigned)ceil_div64(rows, RD_ROWS)), block(256);
     const float2* tab = p->rowF[pass];
     float2* To = reinterpret_cast<float2*>(T);
-#define RD_CASE(K) case K: rowdft_fwd_kernel<K><<<grid, block, 0, st>>>(x, tab, To, rows, W, Mx, vec_ok); break;
+#define RD_CASE(K) case K: sb_launch(rowdft_fwd_kernel<K>, grid, block, 0, st, x, tab, To, rows, W, Mx, vec_ok); break;
     switch (kpt) {
         RD_CASE(1) RD_CASE(2) RD_CASE(3) RD_CASE(4) RD_CASE(5) RD_CASE(6) RD_CASE(7) RD_CASE(8)
         default: SB_REQUIRE(false, "rowdft_fwd: internal kpt=%d", kpt);
@@ -118,6 +120,8 @@ constexpr int CF_HC = 16;
 __global__ void __launch_bounds__(1024)
 coldft_fwd_kernel(const float2* __restrict__ T, const float2* __restrict__ CF, float2* __restrict__ Xh,
                   int64_t nimg, int H, int My, int Mx, int IPB, int KGB) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ float2 sm[];
     float2* Ts = sm;                                  // [IPB][HC][Mx]
     float2* Cs = sm + (size_t)IPB * CF_HC * Mx;       // [KGB*4][HC+1]
@@ -172,6 +176,8 @@ coldft_fwd_kernel(const float2* __restrict__ T, const float2* __restrict__ CF, f
 __global__ void __launch_bounds__(1024)
 coldft_inv_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
                   int64_t nimg, int H, int My, int Mx, int IPB, int YGB) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ float2 sm[];
     float2* Ys = sm;                                  // [IPB][My][Mx]
     float2* Cs = sm + (size_t)IPB * My * Mx;          // [YGB*4][My+1]
@@ -223,6 +229,8 @@ template <int MYP>
 __global__ void __launch_bounds__(128)
 coldft_inv2_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
                    int64_t nitems, int H, int My, int Mx, int yseg) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ __align__(16) float2 tw[];          // [yseg][MYP] twiddles of this block's rows
     const int y0 = blockIdx.y * yseg;
     const int ny = min(yseg, H - y0);
@@ -271,7 +279,7 @@ static int coldft_inv2_launch(const float2* Yh, const float2* CI, float2* Phi, i
     const size_t smem = (size_t)yseg * MYP * sizeof(float2);
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(coldft_inv2_kernel<MYP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coldft_inv2_kernel<MYP><<<grid, 128, smem, st>>>(Yh, CI, Phi, nitems, H, My, Mx, yseg);
+    sb_launch(coldft_inv2_kernel<MYP>, grid, 128, smem, st, Yh, CI, Phi, nitems, H, My, Mx, yseg);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -301,7 +309,7 @@ extern "C" int sb200_coldft_fwd(sb200_plan_t p, int pass, const float* T, float*
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(coldft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div64(nimg, IPB), (unsigned)(((My + 3) / 4 + KGB - 1) / KGB));
-    coldft_fwd_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
+    sb_launch(coldft_fwd_kernel, grid, threads, smem, (cudaStream_t)stream, 
         reinterpret_cast<const float2*>(T), p->colF[pass], reinterpret_cast<float2*>(Xh), nimg, H, My, Mx, IPB, KGB);
     SB_LAUNCH_CHECK();
     return 0;
@@ -329,7 +337,7 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(coldft_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div64(nimg, IPB), (unsigned)(((H + 3) / 4 + YGB - 1) / YGB));
-    coldft_inv_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
+    sb_launch(coldft_inv_kernel, grid, threads, smem, (cudaStream_t)stream, 
         reinterpret_cast<const float2*>(Yh), p->colI[pass], reinterpret_cast<float2*>(Phi), nimg, H, My, Mx, IPB, YGB);
     SB_LAUNCH_CHECK();
     return 0;
@@ -379,6 +387,8 @@ modes_gemm2_kernel(const float2* __restrict__ A, int64_t sAr, int64_t sAp,
                    const float2* __restrict__ B, int64_t sBr, int64_t sBq,
                    float2* __restrict__ out, int64_t sOp, int64_t sOq,
                    int P, int Q, int R, int K, int conjA, int conjB) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     constexpr int STAGE_FLOATS = 4 * MG_RC * 4 * MG2_PS, OUT_FLOATS = 2 * 4 * MG2_OPLANE;
     __shared__ __align__(16) float smem[STAGE_FLOATS > OUT_FLOATS ? STAGE_FLOATS : OUT_FLOATS];
     float (*As_re)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem);
@@ -473,6 +483,8 @@ modes_gemm_kernel(const float2* __restrict__ A, int64_t sAr, int64_t sAp,
                   const float2* __restrict__ B, int64_t sBr, int64_t sBq,
                   float2* __restrict__ out, int64_t sOp, int64_t sOq,
                   int P, int Q, int R, int K, int conjA, int conjB) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     constexpr int KB = 4 * KT;
     __shared__ __align__(16) float2 As[MG_RC][32][KB];
     __shared__ __align__(16) float2 Bs[MG_RC][32][KB];
@@ -560,7 +572,7 @@ extern "C" int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp, const 
     float2* O2 = reinterpret_cast<float2*>(out);
     if (getenv("SB200_MODES_GEMM_V1") == nullptr) {
         dim3 grid((K + 3) / 4, pb, qb);
-        modes_gemm2_kernel<<<grid, 256, 0, st>>>(A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
+        sb_launch(modes_gemm2_kernel, grid, 256, 0, st, A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
         SB_LAUNCH_CHECK();
         return 0;
     }
@@ -568,10 +580,10 @@ extern "C" int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp, const 
     const int64_t blocks8 = (int64_t)((K + 7) / 8) * pb * qb;
     if (blocks8 >= 2 * 148) {
         dim3 grid((K + 7) / 8, pb, qb);
-        modes_gemm_kernel<2><<<grid, 256, 0, st>>>(A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
+        sb_launch(modes_gemm_kernel<2>, grid, 256, 0, st, A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
     } else {
         dim3 grid((K + 3) / 4, pb, qb);
-        modes_gemm_kernel<1><<<grid, 256, 0, st>>>(A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
+        sb_launch(modes_gemm_kernel<1>, grid, 256, 0, st, A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
     }
     SB_LAUNCH_CHECK();
     return 0;

@@ -13,6 +13,8 @@ constexpr int PW_MC = 16;    // input-channel chunk
 
 __global__ void __launch_bounds__(128)
 rowidft_pointwise_kernel(const PwParams p) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int K2 = 2 * p.Mx;
     float* As = smem;                               // [PW_MC][PW_PX]
@@ -191,7 +193,7 @@ extern "C" int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float*
     const int64_t tiles = (HW + PW_PX - 1) / PW_PX * B;
     SB_REQUIRE(tiles < (1LL << 31), "rowidft_pointwise: too many tiles");
     dim3 grid((unsigned)tiles, (unsigned)((N + PW_N - 1) / PW_N));
-    rowidft_pointwise_kernel<<<grid, 128, smem, st>>>(p);
+    sb_launch(rowidft_pointwise_kernel, grid, 128, smem, st, p);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(256)
 pointwise_wgrad_partial_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ ws,
                                float* __restrict__ wsb, int B, int Cout, int Cin, int64_t HW, int64_t chunk_px,
                                int chunks_per_b, int i_tiles) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ __align__(16) float Gs[WG_PC][WG_LD];
     __shared__ __align__(16) float Xs[WG_PC][WG_LD];
     __shared__ float red[64][65];
@@ -306,6 +310,8 @@ pointwise_wgrad_partial_kernel(const float* __restrict__ g, const float* __restr
 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t E, int nchunks) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= E) return;
     float s = 0.f;
@@ -354,13 +360,13 @@ extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, 
     float* wsb = workspace + (int64_t)nchunks * Cout * Cin;
     const int o_tiles = (Cout + 63) / 64, i_tiles = (Cin + 63) / 64;
     dim3 grid(nchunks, o_tiles * i_tiles);
-    pointwise_wgrad_partial_kernel<<<grid, 256, 0, st>>>(g, x, ws, wsb, B, Cout, Cin, HW, px, cpb, i_tiles);
+    sb_launch(pointwise_wgrad_partial_kernel, grid, 256, 0, st, g, x, ws, wsb, B, Cout, Cin, HW, px, cpb, i_tiles);
     SB_LAUNCH_CHECK();
     const int64_t E = (int64_t)Cout * Cin;
-    wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(ws, gW, E, nchunks);
+    sb_launch(wgrad_reduce_kernel, (unsigned)ceil_div64(E, 256), 256, 0, st, ws, gW, E, nchunks);
     SB_LAUNCH_CHECK();
     if (gbias) {
-        wgrad_reduce_kernel<<<(unsigned)ceil_div64(Cout, 256), 256, 0, st>>>(wsb, gbias, Cout, nchunks);
+        sb_launch(wgrad_reduce_kernel, (unsigned)ceil_div64(Cout, 256), 256, 0, st, wsb, gbias, Cout, nchunks);
         SB_LAUNCH_CHECK();
     }
     return 0;
@@ -375,6 +381,8 @@ __global__ void __launch_bounds__(256)
 pointwise_small_n_kernel(const float* __restrict__ A, const float* __restrict__ Wp, const float* __restrict__ bias,
                          float* __restrict__ z_out, float* __restrict__ y_out, int M, int N, int64_t HW,
                          int apply_act) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     extern __shared__ float wsm[];      // [NT][M]
     const int b = blockIdx.y;
     for (int idx = threadIdx.x; idx < NT * M; idx += 256) {
@@ -423,10 +431,10 @@ extern "C" int sb200_pointwise_small_n(const float* A, const float* Wp, const fl
     const size_t smem = (size_t)NT * M * sizeof(float);
     SB_REQUIRE(smem <= 48 * 1024, "pointwise_small_n: M=%d too large", M);
     switch (NT) {
-        case 1: pointwise_small_n_kernel<1><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
-        case 2: pointwise_small_n_kernel<2><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
-        case 4: pointwise_small_n_kernel<4><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
-        default: pointwise_small_n_kernel<8><<<grid, 256, smem, st>>>(A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        case 1: sb_launch(pointwise_small_n_kernel<1>, grid, 256, smem, st, A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        case 2: sb_launch(pointwise_small_n_kernel<2>, grid, 256, smem, st, A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        case 4: sb_launch(pointwise_small_n_kernel<4>, grid, 256, smem, st, A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
+        default: sb_launch(pointwise_small_n_kernel<8>, grid, 256, smem, st, A, Wp, bias, z_out, y_out, M, N, HW, apply_act); break;
     }
     SB_LAUNCH_CHECK();
     return 0;
@@ -442,6 +450,8 @@ __global__ void __launch_bounds__(256)
 pointwise_small_m_kernel(const float* __restrict__ A, const float* __restrict__ Wp, int64_t w_sn, int64_t w_sm,
                          const float* __restrict__ bias, const float* __restrict__ zprev, float* __restrict__ z_out,
                          float* __restrict__ y_out, int M, int N, int64_t HW, int mode, int apply_act) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float wsm[32][MT + 1];
     const int b = blockIdx.y, n0 = blockIdx.z * 32;
     for (int idx = threadIdx.x; idx < 32 * MT; idx += 256) {
@@ -481,7 +491,7 @@ pointwise_small_m_kernel(const float* __restrict__ A, const float* __restrict__ 
 static int launch_small_m(const PwParams& p, cudaStream_t st) {
     const int64_t HW = (int64_t)p.H * p.W;
     dim3 grid((unsigned)ceil_div64(HW, 1024), (unsigned)p.B, (unsigned)((p.N + 31) / 32));
-#define SM_CASE(MT) pointwise_small_m_kernel<MT><<<grid, 256, 0, st>>>(p.A, p.Wp, p.w_sn, p.w_sm, p.bias, p.zprev, p.z_out, \
+#define SM_CASE(MT) sb_launch(pointwise_small_m_kernel<MT>, grid, 256, 0, st, p.A, p.Wp, p.w_sn, p.w_sm, p.bias, p.zprev, p.z_out, \
                                                                       p.y_out, p.M, p.N, HW, p.mode, p.apply_act)
     if (p.M <= 1) SM_CASE(1);
     else if (p.M <= 2) SM_CASE(2);
@@ -503,6 +513,8 @@ template <int ST>
 __global__ void __launch_bounds__(256)
 wgrad_small_partial_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ ws,
                            int S, int L, int64_t HW, int64_t chunk_px, int chunks_per_b) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x;
     const int b = chunk / chunks_per_b;
@@ -559,6 +571,8 @@ wgrad_small_partial_kernel(const float* __restrict__ small, const float* __restr
 __global__ void __launch_bounds__(256)
 wgrad_small_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out_dot, float* __restrict__ out_small,
                           float* __restrict__ out_big, int S, int L, int nchunks, int transpose) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t E = (int64_t)S * L + S + L;
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= E) return;
@@ -608,15 +622,15 @@ extern "C" int sb200_wgrad_small(const float* small, const float* big, float* ou
     SB_REQUIRE(grid.y <= 65535, "wgrad_small: L too large");
     const int ST = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : (S <= 8 ? 8 : 16)));
     switch (ST) {
-        case 1: wgrad_small_partial_kernel<1><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
-        case 2: wgrad_small_partial_kernel<2><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
-        case 4: wgrad_small_partial_kernel<4><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
-        case 8: wgrad_small_partial_kernel<8><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
-        default: wgrad_small_partial_kernel<16><<<grid, 256, 0, st>>>(small, big, workspace, S, L, HW, px, cpb); break;
+        case 1: sb_launch(wgrad_small_partial_kernel<1>, grid, 256, 0, st, small, big, workspace, S, L, HW, px, cpb); break;
+        case 2: sb_launch(wgrad_small_partial_kernel<2>, grid, 256, 0, st, small, big, workspace, S, L, HW, px, cpb); break;
+        case 4: sb_launch(wgrad_small_partial_kernel<4>, grid, 256, 0, st, small, big, workspace, S, L, HW, px, cpb); break;
+        case 8: sb_launch(wgrad_small_partial_kernel<8>, grid, 256, 0, st, small, big, workspace, S, L, HW, px, cpb); break;
+        default: sb_launch(wgrad_small_partial_kernel<16>, grid, 256, 0, st, small, big, workspace, S, L, HW, px, cpb); break;
     }
     SB_LAUNCH_CHECK();
     const int64_t E = (int64_t)S * L + S + L;
-    wgrad_small_reduce_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(workspace, out_dot, out_small, out_big, S,
+    sb_launch(wgrad_small_reduce_kernel, (unsigned)ceil_div64(E, 256), 256, 0, st, workspace, out_dot, out_small, out_big, S,
                                                                              L, nchunks, transpose);
     SB_LAUNCH_CHECK();
     return 0;
@@ -626,6 +640,8 @@ extern "C" int sb200_wgrad_small(const float* small, const float* big, float* ou
 // element-wise GELU helpers
 // ======================================================================================
 __global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int64_t n) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
@@ -637,6 +653,8 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z, float* __restrict__ gz,
                                 int64_t n) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
@@ -652,14 +670,14 @@ extern "C" int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream)
     if (n <= 0) return 0;
     SB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                "gelu_fwd: pointers must be 16-byte aligned");
-    gelu_fwd_kernel<<<(unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream>>>(z, y, n);
+    sb_launch(gelu_fwd_kernel, (unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream, z, y, n);
     SB_LAUNCH_CHECK();
     return 0;
 }
 extern "C" int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream) {
     SB_REQUIRE(gy && z && gz, "gelu_bwd: NULL argument");
     if (n <= 0) return 0;
-    gelu_bwd_kernel<<<(unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream>>>(gy, z, gz, n);
+    sb_launch(gelu_bwd_kernel, (unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream, gy, z, gz, n);
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -142,6 +142,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 template <int PASSES, int EPI, int ASRC = 0>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
+    sb_pdl_launch();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
     // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
@@ -201,6 +202,23 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         tc::tmem_alloc(tmem_slot, p.tmem_cols);
         tc::tmem_relinquish();
     }
+    if (spectral) {
+        // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
+        // (plan tables are immutable: staged BEFORE the grid-dependency wait, overlapping the previous kernel's tail)
+        for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
+            const int k = idx >> 7, px = idx & 127;
+            const float v = (p.bias_mma && k == p.K2) ? 1.0f : __ldg(p.E + idx);
+            const float hi = tc::tf32_trunc(v);
+            const uint32_t off = tc::sw32_kmajor_off(px, k, 4096u);
+            *reinterpret_cast<float*>(E_hi + off) = hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = v - hi;
+        }
+        for (int idx = tid; idx < p.V * p.Mx; idx += TP_THREADS) rot_s[idx] = __ldg(p.rot + idx);
+        // zero both Phi buffers once: the K padding columns are never written again
+        for (int idx = tid; idx < (int)(2 * phi_buf_bytes / 16); idx += TP_THREADS)
+            reinterpret_cast<float4*>(Phi_s)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    sb_pdl_wait();          // everything below may read what the preceding kernels wrote (weights, bias, activations)
     // resident weight tile: Wp[n, m] -> K-major 128B-swizzled rows, split into tf32 hi / lo
     if (nkc) {
         for (int idx = tid; idx < p.N * p.M; idx += TP_THREADS) {
@@ -220,31 +238,16 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             w2_s[idx] = idx < p.M ? __ldg(p.w2 + idx) : 0.f;
             red_s[idx] = idx < p.M ? __ldg(p.b2 + idx) : 0.f;
         }
-    if (spectral) {
-        // resident synthesis operand E[kk][px] -> K-major 32B-swizzled hi / lo; with bias_mma the spare row K2 is all ones
-        for (int idx = tid; idx < p.K2pad * 128; idx += TP_THREADS) {
-            const int k = idx >> 7, px = idx & 127;
-            const float v = (p.bias_mma && k == p.K2) ? 1.0f : __ldg(p.E + idx);
+    if (spectral && p.bias_mma) {
+        __syncthreads();
+        // Phi column K2 carries the bias (constant over tiles) in both buffers
+        for (int idx = tid; idx < 2 * p.N; idx += TP_THREADS) {
+            const int a = idx >= p.N, n = idx - a * p.N;
+            const float v = __ldg(p.bias + n);
             const float hi = tc::tf32_trunc(v);
-            const uint32_t off = tc::sw32_kmajor_off(px, k, 4096u);
-            *reinterpret_cast<float*>(E_hi + off) = hi;
-            if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = v - hi;
-        }
-        for (int idx = tid; idx < p.V * p.Mx; idx += TP_THREADS) rot_s[idx] = __ldg(p.rot + idx);
-        // zero both Phi buffers once: the K padding columns are never written again
-        for (int idx = tid; idx < (int)(2 * phi_buf_bytes / 16); idx += TP_THREADS)
-            reinterpret_cast<float4*>(Phi_s)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias_mma) {
-            __syncthreads();
-            // ... except column K2, which carries the bias (constant over tiles) in both buffers
-            for (int idx = tid; idx < 2 * p.N; idx += TP_THREADS) {
-                const int a = idx >= p.N, n = idx - a * p.N;
-                const float v = __ldg(p.bias + n);
-                const float hi = tc::tf32_trunc(v);
-                const uint32_t off = tc::sw32_kmajor_off(n, p.K2, phi_kstep);
-                *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + off) = hi;
-                if (PASSES == 3) *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + phi_bytes + off) = v - hi;
-            }
+            const uint32_t off = tc::sw32_kmajor_off(n, p.K2, phi_kstep);
+            *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + off) = hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + phi_bytes + off) = v - hi;
         }
     }
     tc::fence_proxy_async_smem();
@@ -699,6 +702,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
 // 32 consecutive outputs x 8 row lanes per block (coalesced partial reads), shared-memory tree at the end.
 __global__ void __launch_bounds__(256) head_colsum_reduce_kernel(const float* __restrict__ ws, int rows, float* __restrict__ gb1,
                                                                  float* __restrict__ gw2, float* __restrict__ gb2, int N) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     __shared__ float part[8][33];
     const int o = threadIdx.x & 31, rl = threadIdx.x >> 5;
     if (blockIdx.x == 16) {                              // gb2: the tail of the workspace
@@ -803,7 +808,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     do {                                                                                                               \
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)smem));                                                                \
-        tc_pointwise_kernel<PS, EP><<<grid, TP_THREADS, smem, st>>>(tmap, p);                                          \
+        sb_launch(tc_pointwise_kernel<PS, EP>, grid, TP_THREADS, smem, st, tmap, p);                                          \
     } while (0)
 #define TP_LAUNCH_EPI(PS)                                                                                              \
     switch (epi) {                                                                                                     \
@@ -868,7 +873,7 @@ static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn
     do {                                                                                                               \
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)smem));                                                                \
-        tc_pointwise_kernel<PS, EP><<<grid, TP_THREADS, smem, st>>>(tmap, p);                                          \
+        sb_launch(tc_pointwise_kernel<PS, EP>, grid, TP_THREADS, smem, st, tmap, p);                                          \
     } while (0)
     if (epi == 5)      { if (passes == 3) TP_HEAD(3, 5); else TP_HEAD(1, 5); }
     else if (epi == 6) { if (passes == 3) TP_HEAD(3, 6); else TP_HEAD(1, 6); }
@@ -905,7 +910,7 @@ extern "C" int sb200_mlp_head_bwd(const float* h, const float* W1, const float* 
     if (B <= 0) return 0;
     unsigned grid;
     if (int rc = tp_head_launch(6, h, W1, M, 1, b1, w2, nullptr, gy, gz1, workspace, B, M, N, HW, (cudaStream_t)stream, &grid)) return rc;
-    head_colsum_reduce_kernel<<<17, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw2, gb2, N);
+    sb_launch(head_colsum_reduce_kernel, 17, 256, 0, (cudaStream_t)stream, workspace, (int)grid * 4, gb1, gw2, gb2, N);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -922,7 +927,7 @@ extern "C" int sb200_lift_tail_bwd(const float* g, const float* W2, const float*
     // out channel n of the transposed product reads W2[c, n]: stride 1 over n, N over the contraction index c
     if (int rc = tp_head_launch(7, g, W2, 1, N, b1, w1, nullptr, x, nullptr, workspace, B, C, N, HW, (cudaStream_t)stream, &grid))
         return rc;
-    head_colsum_reduce_kernel<<<17, 256, 0, (cudaStream_t)stream>>>(workspace, (int)grid * 4, gb1, gw1, nullptr, N);
+    sb_launch(head_colsum_reduce_kernel, 17, 256, 0, (cudaStream_t)stream, workspace, (int)grid * 4, gb1, gw1, nullptr, N);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -969,10 +974,10 @@ extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, 
     p.tpr_log2 = tl;
     if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<3, 0, 1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
+        sb_launch(tc_pointwise_kernel<3, 0, 1>, grid, TP_THREADS, smem, st, tmap, p);
     } else {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_pointwise_kernel<1, 0, 1><<<grid, TP_THREADS, smem, st>>>(tmap, p);
+        sb_launch(tc_pointwise_kernel<1, 0, 1>, grid, TP_THREADS, smem, st, tmap, p);
     }
     SB_LAUNCH_CHECK();
     return 0;

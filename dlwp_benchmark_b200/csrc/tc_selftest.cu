@@ -6,6 +6,8 @@
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, float* __restrict__ D, int N, int K,
                    int a_layout_in, int use_mask, uint32_t* __restrict__ info) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int a_layout = a_layout_in & 15, b_sw32 = a_layout_in >> 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
@@ -100,7 +102,7 @@ extern "C" int sb200_tc_selftest(const float* A, const float* B, float* D, int N
     const size_t smem = 1024 + (size_t)((K + 31) / 32) * 128 * 128 +
                         (((size_t)((K + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) + 64;
     SB_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, a_layout, use_mask, info);
+    sb_launch(tc_selftest_kernel, 1, 128, smem, (cudaStream_t)stream, A, B, D, N, K, a_layout, use_mask, info);
     SB_LAUNCH_CHECK();
     return 0;
 }

@@ -35,6 +35,7 @@ struct TcWgParams {
 template <int PASSES, int ASRC = 0>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapQ, const TcWgParams p) {
+    sb_pdl_launch();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
     // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
@@ -90,6 +91,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    sb_pdl_wait();          // barriers, TMEM and the constant rows are set up; from here on global memory is touched
 
     // contiguous item range of this CTA
     const int64_t per = (p.nitems + gridDim.x - 1) / gridDim.x;
@@ -268,6 +270,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ gbias, int Pc, int Qc,
                        int Qn, int prow_pad, int nparts, int transpose) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int cols = Qn > Qc ? Qc + 1 : Qc;
@@ -288,6 +292,8 @@ tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, fl
 // per-channel sums: out[c] = sum_{b,p} g[b,c,p]   (one warp per (b,c) row, then a fixed-order sum over b)
 __global__ void __launch_bounds__(256)
 channel_rowsum_kernel(const float* __restrict__ g, float* __restrict__ part, int64_t rows, int64_t HW) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -303,6 +309,8 @@ channel_rowsum_kernel(const float* __restrict__ g, float* __restrict__ part, int
 }
 __global__ void __launch_bounds__(256)
 channel_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int C) {
+    sb_pdl_launch();
+    sb_pdl_wait();
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
@@ -395,31 +403,31 @@ static int tw_launch(const float* g, const float* x, float* gW, float* gbias, in
         tmP = tmQ;     // unused by the kernel
         if (passes == 3) {
             SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_wgrad_kernel<3, 1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+            sb_launch(tc_wgrad_kernel<3, 1>, grid, TW_THREADS, smem, st, tmP, tmQ, p);
         } else {
             SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_wgrad_kernel<1, 1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+            sb_launch(tc_wgrad_kernel<1, 1>, grid, TW_THREADS, smem, st, tmP, tmQ, p);
         }
     } else if (int rc = sb200_make_tmap_2d_f32(&tmP, Pt, (uint64_t)HW, (uint64_t)B * Pc, (uint64_t)HW * 4, 32, (uint32_t)Pc, 1)) {
         return rc;
     } else if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_wgrad_kernel<3><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+        sb_launch(tc_wgrad_kernel<3>, grid, TW_THREADS, smem, st, tmP, tmQ, p);
     } else {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_wgrad_kernel<1><<<grid, TW_THREADS, smem, st>>>(tmP, tmQ, p);
+        sb_launch(tc_wgrad_kernel<1>, grid, TW_THREADS, smem, st, tmP, tmQ, p);
     }
     SB_LAUNCH_CHECK();
     const int64_t E = (int64_t)Pc * (bias_mma ? Qc + 1 : Qc);
-    tc_wgrad_reduce_kernel<<<(unsigned)ceil_div64(E, 8), 256, 0, st>>>(workspace, gW, bias_mma ? gbias : nullptr, Pc, Qc, p.Qn,
+    sb_launch(tc_wgrad_reduce_kernel, (unsigned)ceil_div64(E, 8), 256, 0, st, workspace, gW, bias_mma ? gbias : nullptr, Pc, Qc, p.Qn,
                                                                        p.mblocks * 128, (int)grid, tr);
     SB_LAUNCH_CHECK();
     if (gbias && !bias_mma) {
         float* part = workspace + (int64_t)sms * p.mblocks * 128 * (Qc + 16);
         const int64_t rows = (int64_t)B * Cout;
-        channel_rowsum_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(g, part, rows, HW);
+        sb_launch(channel_rowsum_kernel, (unsigned)ceil_div64(rows, 8), 256, 0, st, g, part, rows, HW);
         SB_LAUNCH_CHECK();
-        channel_sum_final_kernel<<<(unsigned)((Cout + 255) / 256), 256, 0, st>>>(part, gbias, B, Cout);
+        sb_launch(channel_sum_final_kernel, (unsigned)((Cout + 255) / 256), 256, 0, st, part, gbias, B, Cout);
         SB_LAUNCH_CHECK();
     }
     *handled = 1;
