@@ -249,6 +249,8 @@ def run_b200(args, wl, rank, world, local_rank):
 
     from dlwp_benchmark_b200 import _lib
     lib = _lib.load()
+    if args.tc_mode is not None:
+        lib.sb200_set_tc_mode(args.tc_mode)
     step_eager()                                   # also the first-touch of plans / workspaces
     torch.cuda.synchronize()
     n0 = lib.sb200_kernel_launches()
@@ -393,6 +395,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [wl["H"], wl["W"]],
                        "parallelism": f"dp{world}", "step": "fwd+MSE+bwd+Adam(fused)" + ("+allreduce" if world > 1 else ""),
                        "cuda_graph": bool(use_graph), "graph_scope": graph_mode,
+                       "tc_mode": int(lib.sb200_get_tc_mode()),
                        "l2": "per-step working set (activations of 4 layers + 256-ch lifting/projection, >1 GB) exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
@@ -415,6 +418,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tc-mode", type=int, default=int(os.environ["SB200_TC_MODE"]) if os.environ.get("SB200_TC_MODE") else None,
+                    help="0 = CUDA-core fp32, 1 = single-pass TF32 (parity ~1e-3), 3 = 3xTF32 (parity <= 1e-5; library default)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     args = ap.parse_args()

@@ -25,8 +25,6 @@ SIGNATURES = {
     "sb200_device_arch": (_i, []),
     "sb200_set_tc_mode": (_i, [_i]),
     "sb200_get_tc_mode": (_i, []),
-    "sb200_set_pdl": (_i, [_i]),
-    "sb200_get_pdl": (_i, []),
     "sb200_tc_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sb200_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _d, _d]),
     "sb200_plan_destroy": (_i, [_vp]),

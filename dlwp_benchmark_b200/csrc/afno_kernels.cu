@@ -19,8 +19,6 @@ template <int KG, int CPT>
 __global__ void __launch_bounds__(128)
 cl_rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab /*[W][Mx]*/,
                      float2* __restrict__ T, int W, int Mx, int C) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float2 ts[CLR_WC][KG];
     const int64_t row = blockIdx.x;
     const int c0 = (blockIdx.y * 128 + threadIdx.x) * CPT;
@@ -109,8 +107,6 @@ template <int KG, int CPT>
 __global__ void __launch_bounds__(128)
 cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__ tab /*[Mx][W]*/,
                       const float* __restrict__ resid, float* __restrict__ y, int W, int Mx, int C, int accumulate) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ float2 tsm[];     // [KG][W]
     const int64_t row = blockIdx.x;
     const int c0 = (blockIdx.y * 128 + threadIdx.x) * CPT;
@@ -206,8 +202,6 @@ constexpr int CLC_IC = 32;
 __global__ void __launch_bounds__(128)
 cl_coldft_kernel(const float2* __restrict__ in, const float2* __restrict__ tab /*[J][I]*/, float2* __restrict__ out,
                  int I, int J, int Mx, int C) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float2 ts[CLC_JG][CLC_IC + 1];
     const int b = blockIdx.x / Mx, kx = blockIdx.x % Mx;
     const int c = blockIdx.y * 128 + threadIdx.x;
@@ -294,8 +288,6 @@ constexpr int BL_TOK = 64, BL_KC = 16, BL_OT = 32;
 
 __global__ void __launch_bounds__(256)
 blocklinear_kernel(const BlParams p) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float2 Xs[BL_TOK][BL_KC + 1];
     __shared__ __align__(16) float Wrs[BL_KC][BL_OT];
     __shared__ __align__(16) float Wis[BL_KC][BL_OT];
@@ -409,8 +401,6 @@ __global__ void __launch_bounds__(256)
 blocklinear_wgrad_kernel(const float2* __restrict__ a, const float2* __restrict__ g, const float2* __restrict__ mask_src,
                          int mask_kind, float* __restrict__ ws, int64_t ntok, int64_t chunk_tok, int nb, int Ni, int No,
                          int o_tiles) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ __align__(16) float2 As[BW_T][32];
     __shared__ __align__(16) float2 Gs[BW_T][32];
     const int tid = threadIdx.x;
@@ -497,8 +487,6 @@ blocklinear_wgrad_kernel(const float2* __restrict__ a, const float2* __restrict_
 __global__ void __launch_bounds__(256)
 chunk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out0, int64_t n0, float* __restrict__ out1,
                     int64_t n1, int nchunks) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t E = n0 + n1;
     if (e >= E) return;

@@ -40,7 +40,6 @@ __device__ __forceinline__ float4 af_lds128(const uint8_t* p) { return *reinterp
 template <int MX>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams p) {
-    sb_pdl_launch();
     constexpr int MXE = (MX + 1) & ~1;                   // MX rounded up to even: accumulators are fp32x2 pairs over k
     constexpr int TWS = 2 * MXE;                         // floats per row-twiddle record [C0..C(MX-1), 0?, S0..S(MX-1), 0?]
     static_assert(TWS % 4 == 0, "row-twiddle records are read as float4");
@@ -84,7 +83,6 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
         ctw[idx] = k < My ? __ldg(p.colF + (size_t)k * H + y) : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    sb_pdl_wait();          // the twiddle tables above are immutable plan data; x is the preceding kernel's output
 
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_groups = first < p.ngroups ? (p.ngroups - first + stride - 1) / stride : 0;

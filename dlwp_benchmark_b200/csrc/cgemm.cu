@@ -44,8 +44,6 @@ __device__ __forceinline__ long long cg_off2(int idx, int inner, long long s1, l
 
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(CG_THREADS) cgemm_kernel(const CgParams p) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     static_assert((BM / TM) * (BN / TN) == CG_THREADS, "thread tiling must cover the block tile");
     constexpr int LA = BM * CG_BK / CG_THREADS, LB = BN * CG_BK / CG_THREADS;
     static_assert(LA >= 1 && LB >= 1, "tile too small");
@@ -178,8 +176,6 @@ constexpr int CS_MAXK = 64;
 
 template <int NP>
 __global__ void __launch_bounds__(CS_THREADS) cskinny_kernel(const CgParams p) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ __align__(16) float4 Bs[CS_MAXK * NP];
     const int g = blockIdx.y;
     const float2* __restrict__ Ag = p.A[g];
@@ -263,8 +259,6 @@ struct CgOut { float2* C[CG_MAXG]; };
 __global__ void __launch_bounds__(256) cgemm_reduce_kernel(const float2* __restrict__ ws, const CgOut out, int M, int N,
                                                            int splits, int M2, long long sCm1, long long sCm2,
                                                            long long sCn) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float2 part[8][32];
     const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const long long MN = (long long)M * N;

@@ -65,21 +65,12 @@ extern unsigned long long g_sb200_launches;
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// ---- programmatic dependent launch (PDL) --------------------------------------------------------
-// Every kernel of the library is launched through sb_launch().  With PDL on (sb200_set_pdl, default on) the
-// launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so on a stream / in a captured graph the
-// next kernel's CTAs are scheduled as soon as every CTA of this one has executed sb_pdl_launch() and an SM has
-// room, instead of after the whole grid has drained.  Contract every kernel follows:
-//   * sb_pdl_launch() first (nothing is promised to the dependents by it: they do their own wait);
-//   * sb_pdl_wait() before the first access to ANY global memory other than immutable plan tables
-//     (it returns once the preceding kernel has completed and its writes are visible; transitively all earlier
-//     work is complete too, because that kernel waited the same way);
-//   * code above the wait may only touch shared memory, barriers, TMEM, tensor-map prefetch, plan tables.
-extern int g_sb200_pdl;
-
-__device__ __forceinline__ void sb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void sb_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
+// Every kernel of the library is launched through sb_launch() (one place to add launch attributes).
+// Programmatic dependent launch was tried here (session 5) and removed: the kernels read their inputs through the
+// non-coherent path (__ldg / const __restrict__ -> LDG.E.CONSTANT), which is only legal for data that is read-only for
+// the whole lifetime of the grid; with PDL a grid's lifetime starts before its producer has finished, the L1
+// invalidation of its launch happens too early, and stale lines were observed (wrong results in 2 parity tests).
+// It also measured 8 % slower on the cfg2 train step (early-resident CTAs of the next kernels crowd the SMs).
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline void sb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -88,11 +79,8 @@ static inline void sb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = g_sb200_pdl ? 1 : 0;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in SB_LAUNCH_CHECK
 }
 #endif

@@ -20,8 +20,6 @@ template <int KPT>
 __global__ void __launch_bounds__(256)
 rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab, float2* __restrict__ T,
                   int64_t R, int W, int Mx, int vec_ok) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float xs[RD_ROWS][RD_XC + 1];
     __shared__ float2 ts[RD_XC][4 * KPT];
     const int tid = threadIdx.x;
@@ -120,8 +118,6 @@ constexpr int CF_HC = 16;
 __global__ void __launch_bounds__(1024)
 coldft_fwd_kernel(const float2* __restrict__ T, const float2* __restrict__ CF, float2* __restrict__ Xh,
                   int64_t nimg, int H, int My, int Mx, int IPB, int KGB) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ float2 sm[];
     float2* Ts = sm;                                  // [IPB][HC][Mx]
     float2* Cs = sm + (size_t)IPB * CF_HC * Mx;       // [KGB*4][HC+1]
@@ -176,8 +172,6 @@ coldft_fwd_kernel(const float2* __restrict__ T, const float2* __restrict__ CF, f
 __global__ void __launch_bounds__(1024)
 coldft_inv_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
                   int64_t nimg, int H, int My, int Mx, int IPB, int YGB) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ float2 sm[];
     float2* Ys = sm;                                  // [IPB][My][Mx]
     float2* Cs = sm + (size_t)IPB * My * Mx;          // [YGB*4][My+1]
@@ -229,8 +223,6 @@ template <int MYP>
 __global__ void __launch_bounds__(128)
 coldft_inv2_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
                    int64_t nitems, int H, int My, int Mx, int yseg) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ __align__(16) float2 tw[];          // [yseg][MYP] twiddles of this block's rows
     const int y0 = blockIdx.y * yseg;
     const int ny = min(yseg, H - y0);
@@ -387,8 +379,6 @@ modes_gemm2_kernel(const float2* __restrict__ A, int64_t sAr, int64_t sAp,
                    const float2* __restrict__ B, int64_t sBr, int64_t sBq,
                    float2* __restrict__ out, int64_t sOp, int64_t sOq,
                    int P, int Q, int R, int K, int conjA, int conjB) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     constexpr int STAGE_FLOATS = 4 * MG_RC * 4 * MG2_PS, OUT_FLOATS = 2 * 4 * MG2_OPLANE;
     __shared__ __align__(16) float smem[STAGE_FLOATS > OUT_FLOATS ? STAGE_FLOATS : OUT_FLOATS];
     float (*As_re)[4][MG2_PS] = reinterpret_cast<float (*)[4][MG2_PS]>(smem);
@@ -483,8 +473,6 @@ modes_gemm_kernel(const float2* __restrict__ A, int64_t sAr, int64_t sAp,
                   const float2* __restrict__ B, int64_t sBr, int64_t sBq,
                   float2* __restrict__ out, int64_t sOp, int64_t sOq,
                   int P, int Q, int R, int K, int conjA, int conjB) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     constexpr int KB = 4 * KT;
     __shared__ __align__(16) float2 As[MG_RC][32][KB];
     __shared__ __align__(16) float2 Bs[MG_RC][32][KB];

@@ -19,18 +19,6 @@ void sb200_set_error(const char* fmt, ...) {
 extern "C" const char* sb200_last_error(void) { return g_err; }
 unsigned long long g_sb200_launches = 0;
 extern "C" int64_t sb200_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_sb200_launches, __ATOMIC_RELAXED); }
-// programmatic dependent launch: on unless SB200_PDL=0 in the environment or sb200_set_pdl(0)
-static int pdl_default() {
-    const char* e = getenv("SB200_PDL");
-    return (e && e[0] == '0') ? 0 : 1;
-}
-int g_sb200_pdl = pdl_default();
-extern "C" int sb200_set_pdl(int on) {
-    const int prev = g_sb200_pdl;
-    g_sb200_pdl = on ? 1 : 0;
-    return prev;
-}
-extern "C" int sb200_get_pdl(void) { return g_sb200_pdl; }
 extern "C" int sb200_version(void) { return 10000 * 0 + 100 * 1 + 0; }
 
 extern "C" int sb200_device_arch(void) {

@@ -13,8 +13,6 @@ constexpr int PW_MC = 16;    // input-channel chunk
 
 __global__ void __launch_bounds__(128)
 rowidft_pointwise_kernel(const PwParams p) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int K2 = 2 * p.Mx;
     float* As = smem;                               // [PW_MC][PW_PX]
@@ -208,8 +206,6 @@ __global__ void __launch_bounds__(256)
 pointwise_wgrad_partial_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ ws,
                                float* __restrict__ wsb, int B, int Cout, int Cin, int64_t HW, int64_t chunk_px,
                                int chunks_per_b, int i_tiles) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ __align__(16) float Gs[WG_PC][WG_LD];
     __shared__ __align__(16) float Xs[WG_PC][WG_LD];
     __shared__ float red[64][65];
@@ -310,8 +306,6 @@ pointwise_wgrad_partial_kernel(const float* __restrict__ g, const float* __restr
 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t E, int nchunks) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= E) return;
     float s = 0.f;
@@ -381,8 +375,6 @@ __global__ void __launch_bounds__(256)
 pointwise_small_n_kernel(const float* __restrict__ A, const float* __restrict__ Wp, const float* __restrict__ bias,
                          float* __restrict__ z_out, float* __restrict__ y_out, int M, int N, int64_t HW,
                          int apply_act) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     extern __shared__ float wsm[];      // [NT][M]
     const int b = blockIdx.y;
     for (int idx = threadIdx.x; idx < NT * M; idx += 256) {
@@ -450,8 +442,6 @@ __global__ void __launch_bounds__(256)
 pointwise_small_m_kernel(const float* __restrict__ A, const float* __restrict__ Wp, int64_t w_sn, int64_t w_sm,
                          const float* __restrict__ bias, const float* __restrict__ zprev, float* __restrict__ z_out,
                          float* __restrict__ y_out, int M, int N, int64_t HW, int mode, int apply_act) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float wsm[32][MT + 1];
     const int b = blockIdx.y, n0 = blockIdx.z * 32;
     for (int idx = threadIdx.x; idx < 32 * MT; idx += 256) {
@@ -513,8 +503,6 @@ template <int ST>
 __global__ void __launch_bounds__(256)
 wgrad_small_partial_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ ws,
                            int S, int L, int64_t HW, int64_t chunk_px, int chunks_per_b) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x;
     const int b = chunk / chunks_per_b;
@@ -571,8 +559,6 @@ wgrad_small_partial_kernel(const float* __restrict__ small, const float* __restr
 __global__ void __launch_bounds__(256)
 wgrad_small_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out_dot, float* __restrict__ out_small,
                           float* __restrict__ out_big, int S, int L, int nchunks, int transpose) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t E = (int64_t)S * L + S + L;
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= E) return;
@@ -640,8 +626,6 @@ extern "C" int sb200_wgrad_small(const float* small, const float* big, float* ou
 // element-wise GELU helpers
 // ======================================================================================
 __global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int64_t n) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
@@ -653,8 +637,6 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z, float* __restrict__ gz,
                                 int64_t n) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(z + i));

@@ -142,7 +142,6 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 template <int PASSES, int EPI, int ASRC = 0>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
-    sb_pdl_launch();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
     // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
@@ -218,7 +217,6 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         for (int idx = tid; idx < (int)(2 * phi_buf_bytes / 16); idx += TP_THREADS)
             reinterpret_cast<float4*>(Phi_s)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    sb_pdl_wait();          // everything below may read what the preceding kernels wrote (weights, bias, activations)
     // resident weight tile: Wp[n, m] -> K-major 128B-swizzled rows, split into tf32 hi / lo
     if (nkc) {
         for (int idx = tid; idx < p.N * p.M; idx += TP_THREADS) {
@@ -357,37 +355,79 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         const int64_t HW = p.HW;
         const uint64_t hw_bytes = (uint64_t)p.HW * 4;
 
+        // Division-free tile cursors: tile(it) = first + it * stride -> (sample b, tile t inside the sample).  The loop
+        // below keeps three of them (epilogue tile it, staged tile it + 1, prefetched tile it + 2) and advances by adds.
+        struct Cur { uint32_t b, t; };
+        const uint32_t adv_q = stride / tiles_per_b, adv_r = stride - adv_q * tiles_per_b;
+        auto advance = [&](Cur c) {
+            c.b += adv_q; c.t += adv_r;
+            if (c.t >= tiles_per_b) { c.t -= tiles_per_b; ++c.b; }
+            return c;
+        };
+        Cur cur_e; cur_e.b = first / tiles_per_b; cur_e.t = first - cur_e.b * tiles_per_b;
+        Cur cur_p = cur_e, cur_f = cur_e;                   // set properly before the loop
+
         // Phi elements of the first staging round are fetched one tile ahead (registers), so that their global-load
         // latency is hidden behind the epilogue of the previous tile
         float2 fpre[4];
         // tile -> (sample b, first image row y0, 128-px segment v of the row); V == 1: a tile is R whole rows
         const uint32_t Vseg = (uint32_t)p.V, Rrows = (uint32_t)p.R;
-        auto phi_src = [&](uint32_t it, uint32_t& v) -> const float2* {
-            const uint32_t tile = first + it * stride;
-            const uint32_t b = tile / tiles_per_b;
-            const uint32_t t_in = tile - b * tiles_per_b;
+        const bool v_pow2 = (Vseg & (Vseg - 1)) == 0;
+        const uint32_t v_log2 = 31u - (uint32_t)__clz((int)Vseg);
+        auto phi_src = [&](Cur c, uint32_t& v) -> const float2* {
             uint32_t y0;
-            if (Vseg == 1) { y0 = t_in * Rrows; v = 0; }
-            else { y0 = t_in / Vseg; v = t_in - y0 * Vseg; }
-            return p.Phi + ((size_t)(b * (uint32_t)p.N + (uint32_t)n_st) * (uint32_t)p.H + y0) * (uint32_t)p.Mx;   // R*Mx contiguous complex
+            if (Vseg == 1) { y0 = c.t * Rrows; v = 0; }
+            else { y0 = v_pow2 ? (c.t >> v_log2) : (c.t / Vseg); v = c.t - y0 * Vseg; }
+            return p.Phi + ((size_t)(c.b * (uint32_t)p.N + (uint32_t)n_st) * (uint32_t)p.H + y0) * (uint32_t)p.Mx;   // R*Mx contiguous complex
         };
-        auto prefetch_phi = [&](uint32_t it) {
+        // tile-invariant staging slots of this thread: element rem = sub + u * tpr of its channel goes to byte offset
+        // st_off[u] (kk = 2*rem: k-step rem/4, 16-byte half (rem/2)&1 XOR swizzle bit, 8-byte slot rem&1)
+        const bool one_round = per_n <= 4 * tpr;
+        uint32_t st_off[4];
+        bool st_ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rem = sub + u * tpr;
+            st_ok[u] = st_active && rem < per_n;
+            st_off[u] = (uint32_t)n_st * 32u + (uint32_t)(rem >> 2) * phi_kstep +
+                        (uint32_t)(((((rem >> 1) & 1) ^ ((n_st >> 2) & 1)) << 4) | ((rem & 1) << 3));
+        }
+        auto prefetch_phi = [&](Cur c) {
             if (st_active) {
                 uint32_t v;
-                const float2* src = phi_src(it, v);
+                const float2* src = phi_src(c, v);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rem = sub + u * tpr;
-                    fpre[u] = rem < per_n ? __ldg(src + rem) : make_float2(0.f, 0.f);
-                }
+                for (int u = 0; u < 4; ++u) fpre[u] = st_ok[u] ? __ldg(src + sub + u * tpr) : make_float2(0.f, 0.f);
             }
         };
-        auto prepare_tile = [&](uint32_t it) {
+        auto prepare_tile = [&](uint32_t it, Cur c) {
             if (spectral) {
-                uint8_t* ph = Phi_s + (it & 1) * phi_buf_bytes + (uint32_t)n_st * 32u;
-                if (st_active) {
+                uint8_t* pbuf = Phi_s + (it & 1) * phi_buf_bytes;
+                if (st_active && one_round) {
+                    // every element of this thread is already in registers (fpre): rotate (V > 1), split, store
+                    const float2* rt = rot_s;
+                    if (Vseg > 1) {
+                        uint32_t v;
+                        (void)phi_src(c, v);
+                        rt = rot_s + v * p.Mx;                                                     // V > 1 implies R == 1: kx = rem
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (st_ok[u]) {
+                            float2 g = fpre[u];
+                            if (Vseg > 1) {
+                                const float2 cr = rt[sub + u * tpr];
+                                g = make_float2(fpre[u].x * cr.x - fpre[u].y * cr.y, fpre[u].x * cr.y + fpre[u].y * cr.x);
+                            }
+                            const float2 h = make_float2(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y));
+                            *reinterpret_cast<float2*>(pbuf + st_off[u]) = h;
+                            if (PASSES == 3) *reinterpret_cast<float2*>(pbuf + phi_bytes + st_off[u]) = make_float2(g.x - h.x, g.y - h.y);
+                        }
+                    }
+                } else if (st_active) {
+                    uint8_t* ph = pbuf + (uint32_t)n_st * 32u;
                     uint32_t v;
-                    const float2* src = phi_src(it, v);
+                    const float2* src = phi_src(c, v);
                     const float2* rt = rot_s + v * p.Mx;                                           // V > 1 implies R == 1: kx = rem
                     for (int r0 = sub; r0 < per_n; r0 += 4 * tpr) {
                         float2 f[4];
@@ -403,8 +443,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                             if (rem < per_n) {
                                 float2 g = f[u];
                                 if (p.V > 1) {
-                                    const float2 c = rt[rem];
-                                    g = make_float2(f[u].x * c.x - f[u].y * c.y, f[u].x * c.y + f[u].y * c.x);
+                                    const float2 cr = rt[rem];
+                                    g = make_float2(f[u].x * cr.x - f[u].y * cr.y, f[u].x * cr.y + f[u].y * cr.x);
                                 }
                                 // kk = 2*rem: k-step rem/4, 16-byte half (rem/2)&1 XOR swizzle bit, 8-byte slot rem&1
                                 const uint32_t off = (uint32_t)(rem >> 2) * phi_kstep +
@@ -422,9 +462,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             }
             if (ASRC == 1) {
                 // generate the operand: thread -> (channel row k_local, 8-pixel chunk c8) of every 32-channel K chunk
-                const uint32_t tile = first + it * stride;
-                const uint32_t b = tile / tiles_per_b;
-                const int64_t px = (int64_t)(tile - b * tiles_per_b) * TP_PX + (wtid & 15) * 8;
+                const uint32_t b = c.b;
+                const int64_t px = (int64_t)c.t * TP_PX + (wtid & 15) * 8;
                 float xv[8];
                 {
                     const float* xs = p.gy + (int64_t)b * p.HW + px;
@@ -485,14 +524,16 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
 
         float hsum[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // EPI 6: column sums (gb1 x4 | gw2 x4) and sum(gy)
         if (my_tiles > 0) {
-            prefetch_phi(0);
-            prepare_tile(0);
-            if (my_tiles > 1) prefetch_phi(1);
+            prefetch_phi(cur_e);
+            prepare_tile(0, cur_e);
+            cur_p = advance(cur_e);
+            if (my_tiles > 1) prefetch_phi(cur_p);
+            cur_f = advance(cur_p);
         }
         for (uint32_t it = 0; it < my_tiles; ++it) {
-            const uint32_t tile = first + it * stride;
-            const uint32_t b = tile / tiles_per_b;
-            const uint32_t p_base = (tile - b * tiles_per_b) * TP_PX;
+            // cur_e = tile it (epilogue), cur_p = tile it + 1 (staged now), cur_f = tile it + 2 (prefetched now)
+            const uint32_t b = cur_e.b;
+            const uint32_t p_base = cur_e.t * TP_PX;
             const int64_t pp = (int64_t)p_base + quarter * 32 + lane;
             const bool in_range = pp < HW;
             float zp[16];
@@ -507,9 +548,10 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 }
             }
             if (it + 1 < my_tiles) {
-                prepare_tile(it + 1);
-                if (it + 2 < my_tiles) prefetch_phi(it + 2);
+                prepare_tile(it + 1, cur_p);
+                if (it + 2 < my_tiles) prefetch_phi(cur_f);
             }
+            cur_e = cur_p; cur_p = cur_f; cur_f = advance(cur_f);
             const uint32_t a = it & 1;
             const uint32_t tround = it >> 1;
             tc::mbar_wait(tfull_bar + a, tround & 1);
@@ -702,8 +744,6 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
 // 32 consecutive outputs x 8 row lanes per block (coalesced partial reads), shared-memory tree at the end.
 __global__ void __launch_bounds__(256) head_colsum_reduce_kernel(const float* __restrict__ ws, int rows, float* __restrict__ gb1,
                                                                  float* __restrict__ gw2, float* __restrict__ gb2, int N) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     __shared__ float part[8][33];
     const int o = threadIdx.x & 31, rl = threadIdx.x >> 5;
     if (blockIdx.x == 16) {                              // gb2: the tail of the workspace
@@ -778,7 +818,12 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     const size_t phi_bytes = has_spec ? ((((size_t)(p.K2pad / 8) * N * 32 + 1023) & ~(size_t)1023) * mult * 2) : 0;
     const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512 + 1024 + 2048;   // + barriers, bias_s, rot_s
     int stages = has_pw ? 6 : 1;
-    while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
+    static const size_t ring_budget = []() {                       // bytes the ring may grow to (SB200_TP_SMEM_KB: experiments)
+        const char* e = getenv("SB200_TP_SMEM_KB");
+        const int kb = e ? atoi(e) : 0;
+        return (size_t)((kb >= 64 && kb <= 227) ? kb : 224) * 1024;
+    }();
+    while (stages > 2 && fixed + stages * a_stage > ring_budget) --stages;
     if (fixed + stages * a_stage > 227 * 1024) {
         stages = 1;
         if (fixed + stages * a_stage > 227 * 1024) return 0;           // does not fit: CUDA-core kernel

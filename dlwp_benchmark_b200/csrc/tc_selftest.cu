@@ -6,8 +6,6 @@
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, float* __restrict__ D, int N, int K,
                    int a_layout_in, int use_mask, uint32_t* __restrict__ info) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int a_layout = a_layout_in & 15, b_sw32 = a_layout_in >> 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address

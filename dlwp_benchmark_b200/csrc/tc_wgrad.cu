@@ -35,7 +35,6 @@ struct TcWgParams {
 template <int PASSES, int ASRC = 0>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapQ, const TcWgParams p) {
-    sb_pdl_launch();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET from the __shared__ array, so every derived pointer keeps the shared address
     // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
@@ -91,7 +90,6 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    sb_pdl_wait();          // barriers, TMEM and the constant rows are set up; from here on global memory is touched
 
     // contiguous item range of this CTA
     const int64_t per = (p.nitems + gridDim.x - 1) / gridDim.x;
@@ -270,8 +268,6 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ gbias, int Pc, int Qc,
                        int Qn, int prow_pad, int nparts, int transpose) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int cols = Qn > Qc ? Qc + 1 : Qc;
@@ -292,8 +288,6 @@ tc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, fl
 // per-channel sums: out[c] = sum_{b,p} g[b,c,p]   (one warp per (b,c) row, then a fixed-order sum over b)
 __global__ void __launch_bounds__(256)
 channel_rowsum_kernel(const float* __restrict__ g, float* __restrict__ part, int64_t rows, int64_t HW) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -309,8 +303,6 @@ channel_rowsum_kernel(const float* __restrict__ g, float* __restrict__ part, int
 }
 __global__ void __launch_bounds__(256)
 channel_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int C) {
-    sb_pdl_launch();
-    sb_pdl_wait();
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;

@@ -47,13 +47,6 @@ int sb200_device_arch(void);
 int sb200_set_tc_mode(int mode);
 int sb200_get_tc_mode(void);
 
-/* Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) on every kernel launch of the
- * library: 1 = on (default; SB200_PDL=0 in the environment turns it off), 0 = plain stream-ordered launches.
- * Results are identical either way; it only lets kernel N+1's prologue overlap kernel N's tail. Returns the
- * previous setting. Process-global. */
-int sb200_set_pdl(int on);
-int sb200_get_pdl(void);
-
 /* Bring-up self-test of the tcgen05 path: D[128,N] = A[128,K] * B[N,K]^T (tf32, single pass) with A staged
  * K-major (a_layout 0) or MN-major (1; 2 = MN-major with LBO/SBO swapped) in 128B-swizzled shared memory.
  * info[0..5] receives the TMEM base address, the instruction descriptor and the first A/B descriptors. */
