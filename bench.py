@@ -40,6 +40,14 @@ WORKLOADS = {
                   n_modes=(16, 16), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=64, W=64, batch=64, rank=0.0),
     "cfg3": dict(desc="FNO2D 256x256 in1 width64 modes32 L4 batch64/GPU (BASELINE configs[2])",
                  n_modes=(32, 32), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=256, W=256, batch=64, rank=0.0),
+    # the two below are not train-step lines of the FNO metric: they have their own metric names
+    "cfg4": dict(desc="FourCastNet AFNO2D filter stack: 8 layers x AFNO2D(embed 256, 8 blocks) on 32x64 tokens, batch 16/GPU "
+                      "(BASELINE configs[3]; LayerNorm / token MLP of the FourCastNet block are SURVEY rows f3, not built)",
+                 kind="afno", embed=256, nb=8, depth=8, H=32, W=64, batch=16),
+    "cfg5": dict(desc="FNO2D closed-loop rollout 128x128 in1 width64 modes32 L4, 512 initial conditions/GPU x 100 steps "
+                      "(BASELINE configs[4])",
+                 kind="rollout", n_modes=(32, 32), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=128, W=128,
+                 batch=512, rank=0.0, rollout_steps=100),
 }
 
 
@@ -206,6 +214,214 @@ def kernel_rooflines(wl, peak_gbs, reps=10):
     return out
 
 
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic(kernel_substr, approx_read_bytes=None):
+    """dram read+write bytes per launch of a kernel from the committed `ncu --set full` capture of this workload
+    (profiles/r01_cfg2_ncu_full_s5.json); None when the capture has no such kernel."""
+    path = os.path.join(ROOT, "profiles", "r01_cfg2_ncu_full_s5.json")
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    best = None
+    for name, rows in table.items():
+        if kernel_substr not in name:
+            continue
+        for r in rows:
+            if best is None or (approx_read_bytes is not None and
+                                abs(r["dram_read_bytes"] - approx_read_bytes) < abs(best["dram_read_bytes"] - approx_read_bytes)):
+                best = r
+    return None if best is None else int(best["dram_read_bytes"] + best["dram_write_bytes"])
+
+
+def _timed(step, steps, warmup, world, local_rank, dist):
+    """W warm-up steps, then K steps bracketed by barrier + synchronize; returns (seconds, clocks)."""
+    import torch
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3, cs.summary()
+
+
+# ----------------------------------------------------------------------------------------
+# cfg4: AFNO2D filter stack (train step), cfg5: closed-loop rollout (inference)
+# ----------------------------------------------------------------------------------------
+def run_afno(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import dlwp_benchmark_b200 as pkg
+    from dlwp_benchmark_b200 import _lib
+    from dlwp_benchmark_b200.ddp import GradSync
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    model = torch.nn.Sequential(*[pkg.AFNO2D(wl["embed"], num_blocks=wl["nb"]) for _ in range(wl["depth"])]).to(dev)
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    sync = GradSync(params, world) if world > 1 else None
+    B, H, W, C = wl["batch"], wl["H"], wl["W"], wl["embed"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    hx = torch.randn(B, H, W, C, generator=g).pin_memory()
+    hy = torch.randn(B, H, W, C, generator=g).pin_memory()
+    x, y = hx.to(dev), hy.to(dev)
+    loss_buf = torch.zeros((), device=dev)
+    hloss = torch.zeros((), pin_memory=True)
+    lib = _lib.load()
+
+    def step_eager():
+        if sync:
+            sync.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(x), y)
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+        if sync:
+            sync.allreduce()
+        opt.step()
+
+    step_eager(); torch.cuda.synchronize()
+    n0 = lib.sb200_kernel_launches()
+    step_eager(); torch.cuda.synchronize()
+    launches = int(lib.sb200_kernel_launches() - n0)
+    step = step_eager
+    if not args.no_graph and sync is None:
+        s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+        opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = torch.nn.functional.mse_loss(model(x), y)
+            loss.backward()
+            loss_buf.copy_(loss.detach())
+            opt.step()
+        step = graph.replay
+    t_dev, clocks = _timed(step, args.steps, args.warmup, world, local_rank, dist)
+
+    def step_e2e():
+        x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
+        step()
+        hloss.copy_(loss_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e2e, _ = _timed(step_e2e, args.steps, 3, world, local_rank, dist)
+    tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+    if rank == 0:
+        peak, peak_src = _peak()
+        P = B * H * W * C
+        alg = 20 * P * wl["depth"]        # per layer: fwd 8P (read x, write y) + bwd 12P (read gy, x for the masks/weights, write gx)
+        line = {"metric": "AFNO2D filter stack train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev,
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [H, W], "parallelism": f"dp{world}",
+                           "step": "fwd+MSE+bwd+Adam(fused)", "cuda_graph": step is not step_eager,
+                           "l2": "working set (8 layers x saved spectra + activations, ~0.6 GB) exceeds the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
+                        "h2d_bytes_per_step": 2 * P * 4 * world, "d2h_bytes_per_step": 4 * world,
+                        "ms_per_step": t_e2e / args.steps * 1e3},
+                "gpu_launches": launches * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "AFNO2D layer (all kernels of one layer, fwd+bwd)",
+                             "achieved": alg / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (t_dev / args.steps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "alg_bytes": alg, "note": "whole-step time over 20*P bytes per layer (includes Adam and the loss)"},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rollout(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import dlwp_benchmark_b200 as pkg
+    from dlwp_benchmark_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(wl).to(dev).eval()
+    B, R = wl["batch"], wl["rollout_steps"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    hx = torch.randn(B, wl["cin"], wl["H"], wl["W"], generator=g).pin_memory()
+    x0 = hx.to(dev)
+    out = torch.empty(B, R, wl["cout"], wl["H"], wl["W"], device=dev)
+    hlast = torch.empty(B, wl["cout"], wl["H"], wl["W"]).pin_memory()
+    eng = pkg.Rollout(model, graph=not args.no_graph)
+    lib = _lib.load()
+    eng(x0, 2)                                                    # capture + first replay
+    torch.cuda.synchronize()
+    n0 = lib.sb200_kernel_launches()
+    pkg.Rollout(model, graph=False)(x0, 1)
+    torch.cuda.synchronize()
+    launches = int(lib.sb200_kernel_launches() - n0)            # library kernels per model step
+    t_dev, clocks = _timed(lambda: eng(x0, R, out), args.steps, args.warmup, world, local_rank, dist)
+
+    def step_e2e():
+        x0.copy_(hx, non_blocking=True)
+        eng(x0, R, out)
+        hlast.copy_(out[:, -1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e2e, _ = _timed(step_e2e, args.steps, 1, world, local_rank, dist)
+    tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+    if rank == 0:
+        peak, peak_src = _peak()
+        C, L = wl["hidden"], wl["L"]
+        P = B * C * wl["H"] * wl["W"]
+        M = wl["n_modes"][0] * (wl["n_modes"][1] // 2 + 1)
+        alg = L * (8 * P + 8 * C * C * M + 4 * C * C) + 2 * 4 * P          # SURVEY 8(d) fwd bytes per layer + lifting out / projection in
+        per_model_step = t_dev / args.steps / R
+        line = {"metric": "FNO2D closed-loop rollout IC-steps/s", "value": B * world * R * args.steps / t_dev,
+                "unit": "IC-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "global_ics": B * world, "rollout_steps": R, "grid": [wl["H"], wl["W"]],
+                           "parallelism": f"ic-shard x{world} (no collective)", "step": "one 100-step closed-loop rollout",
+                           "cuda_graph": not args.no_graph, "ms_per_model_step": per_model_step * 1e3,
+                           "l2": "one activation tensor is 2.1 GB, far beyond the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": B * world * R * args.steps / t_e2e, "unit": "IC-steps/s",
+                        "h2d_bytes_per_step": hx.numel() * 4 * world, "d2h_bytes_per_step": hlast.numel() * 4 * world,
+                        "ms_per_step": t_e2e / args.steps * 1e3, "note": "initial conditions H2D, last frame D2H per rollout"},
+                "gpu_launches": launches * R * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "one model step (all kernels, forward only)",
+                             "achieved": alg / per_model_step / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / per_model_step / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "alg_bytes": alg},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------
@@ -356,11 +572,7 @@ def run_b200(args, wl, rank, world, local_rank):
     t_dev, t_e2e = tt.tolist()
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = _peak()
         roof = None
         log('e2e done; per-kernel rooflines')
         try:
@@ -374,8 +586,16 @@ def run_b200(args, wl, rank, world, local_rank):
                         "rowidft_pointwise(bwd)": L - 1, "pointwise_wgrad": L}
             share = {k: v["ms"] * per_step.get(k, 1) for k, v in kr.items()}
             top = max(share, key=share.get)
+            ncu_name = {"analysis": ("analysis_fused", None), "modes_gemm(mix_fwd)": ("modes_gemm2", None),
+                        "modes_gemm(wgrad)": ("modes_gemm2", None), "coldft_inv": ("coldft_inv2", None),
+                        "rowidft_pointwise(fwd)": ("tc_pointwise_kernel<3, 1, 0>", None),
+                        "rowidft_pointwise(bwd)": ("tc_pointwise_kernel<3, 3, 0>", None),
+                        "pointwise_wgrad": ("tc_wgrad_kernel<3, 0>", 8 * wl["batch"] * wl["hidden"] * wl["H"] * wl["W"])}
+            traffic = _ncu_traffic(*ncu_name[top]) if args.workload == "cfg2" and top in ncu_name else None
             roof = {"bound": "hbm", "kernel": top, "achieved": kr[top]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kr[top]["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": kr[top]["frac"], "traffic": traffic,
+                    "traffic_source": "profiles/r01_cfg2_ncu_full_s5.json (ncu --set full, same shapes)" if traffic else None,
+                    "peak_source": peak_src,
                     "kernel_ms": kr[top]["ms"], "alg_bytes": kr[top]["alg_bytes"],
                     "all": {k: {"ms": round(v["ms"], 4), "frac": round(v["frac"], 4)} for k, v in kr.items()}}
         except Exception as ex:  # the roofline block must never take the headline number down
@@ -429,9 +649,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if wl.get("kind"):
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm covers the FNO train-step workloads"}))
+            return
         run_reference(args, wl, rank, world)
         return
-    run_b200(args, wl, rank, world, local_rank)
+    if wl.get("kind") == "afno":
+        run_afno(args, wl, rank, world, local_rank)
+    elif wl.get("kind") == "rollout":
+        run_rollout(args, wl, rank, world, local_rank)
+    else:
+        run_b200(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

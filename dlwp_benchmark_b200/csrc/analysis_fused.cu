@@ -33,6 +33,7 @@ struct AfParams {
     int64_t nimg;
     int H, W, My, G;
     int ngroups;
+    int nxb, ntb;            // depth of the x ring (TMA destinations) and of the T ring (row stage -> column stage)
 };
 
 __device__ __forceinline__ float4 af_lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
@@ -51,20 +52,21 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
     const int Myp = (My + 3) & ~3;
     const uint32_t half_bytes = AF_ROWS * 128;           // one 32-float column block of a group
     const uint32_t xbuf_bytes = (uint32_t)(W / 32) * half_bytes;
-    uint8_t* xbuf = base;                                                         // [2][W/32][256][128 B]
-    float2* Tbuf = reinterpret_cast<float2*>(xbuf + 2 * xbuf_bytes);              // [2][256][MX]
-    float* rtw = reinterpret_cast<float*>(Tbuf + 2 * AF_ROWS * MX);              // [W/2+1][TWS]
+    const int NXB = p.nxb, NTB = p.ntb;
+    uint8_t* xbuf = base;                                                         // [NXB][W/32][256][128 B]
+    float2* Tbuf = reinterpret_cast<float2*>(xbuf + (uint32_t)NXB * xbuf_bytes);  // [NTB][256][MX]
+    float* rtw = reinterpret_cast<float*>(Tbuf + NTB * AF_ROWS * MX);            // [W/2+1][TWS]
     float2* ctw = reinterpret_cast<float2*>(rtw + (W / 2 + 1) * TWS);            // [H][Myp]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ctw + (size_t)H * Myp);
-    uint64_t* xfull = bars;          // [2] TMA landed
-    uint64_t* tfull = bars + 2;      // [2] T written by the row warps
-    uint64_t* tempty = bars + 4;     // [2] T consumed by the column warps
+    uint64_t* xfull = bars;          // [NXB <= 4] TMA landed
+    uint64_t* tfull = bars + 4;      // [NTB <= 2] T written by the row warps
+    uint64_t* tempty = bars + 6;     // [NTB <= 2] T consumed by the column warps
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         tc::tma_prefetch_desc(&tmapX);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(xfull + i, 1);
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(xfull + i, 1);
             tc::mbar_init(tfull + i, AF_RTHREADS);
             tc::mbar_init(tempty + i, AF_CTHREADS);
         }
@@ -88,8 +90,7 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
     const int my_groups = first < p.ngroups ? (p.ngroups - first + stride - 1) / stride : 0;
     const int nhalf = W / 32;
 
-    auto issue = [&](int i) {    // TMA loads of local group i into buffer i & 1 (one thread)
-        const int b = i & 1;
+    auto issue = [&](int i, int b) {    // TMA loads of local group i into x buffer b (one thread)
         const int row0 = (first + i * stride) * AF_ROWS;
         tc::mbar_expect_tx(xfull + b, xbuf_bytes);
         for (int h = 0; h < nhalf; ++h)
@@ -98,16 +99,13 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
 
     if (tid < AF_RTHREADS) {
         // =========================== row stage ===========================
-        if (tid == 0) {
-            if (my_groups > 0) issue(0);
-            if (my_groups > 1) issue(1);
-        }
+        if (tid == 0)
+            for (int i = 0; i < NXB && i < my_groups; ++i) issue(i, i);
         const int nch = W / 4;
+        int b = 0, tb = 0;                  // x / T ring slots of group i
+        uint32_t xpar = 0, tpar = 0;        // their phase parities
         for (int i = 0; i < my_groups; ++i) {
-            const int b = i & 1;
-            const uint32_t par = (uint32_t)(i >> 1) & 1;
-            tc::mbar_wait(xfull + b, par);
-            tc::mbar_wait(tempty + b, par ^ 1);
+            tc::mbar_wait(xfull + b, xpar);
             const uint8_t* xb = xbuf + (uint32_t)b * xbuf_bytes;
             float2 are[AF_RPT][MXE / 2], aim[AF_RPT][MXE / 2];       // (k, k+1) pairs
             float carry[AF_RPT];
@@ -161,7 +159,8 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
 #pragma unroll
                     for (int q = 0; q < AF_RPT; ++q) are[q][k] = ffma2(make_float2(carry[q], carry[q]), twp[k], are[q][k]);
             }
-            float2* Tb = Tbuf + (size_t)b * AF_ROWS * MX;
+            tc::mbar_wait(tempty + tb, tpar ^ 1);        // the column warps are done with this T slot
+            float2* Tb = Tbuf + (size_t)tb * AF_ROWS * MX;
 #pragma unroll
             for (int q = 0; q < AF_RPT; ++q)
 #pragma unroll
@@ -170,21 +169,23 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
                     const float im = (k & 1) ? aim[q][k / 2].y : aim[q][k / 2].x;
                     Tb[(tid + q * AF_RTHREADS) * MX + k] = make_float2(re, im);
                 }
-            tc::mbar_arrive(tfull + b);
-            // every row thread is done reading xbuf[b]: refill it with group i + 2
+            tc::mbar_arrive(tfull + tb);
+            // every row thread is done reading xbuf[b]: refill it with group i + NXB
             asm volatile("bar.sync 1, %0;" ::"n"(AF_RTHREADS) : "memory");
-            if (tid == 0 && i + 2 < my_groups) issue(i + 2);
+            if (tid == 0 && i + NXB < my_groups) issue(i + NXB, b);
+            if (++b == NXB) { b = 0; xpar ^= 1; }
+            if (++tb == NTB) { tb = 0; tpar ^= 1; }
         }
     } else {
         // =========================== column stage ===========================
         const int ct = tid - AF_RTHREADS;
         const int kyq_n = Myp / 4;
         const int items = p.G * kyq_n * MX;
+        int tb = 0;
+        uint32_t tpar = 0;
         for (int i = 0; i < my_groups; ++i) {
-            const int b = i & 1;
-            const uint32_t par = (uint32_t)(i >> 1) & 1;
-            tc::mbar_wait(tfull + b, par);
-            const float2* Tb = Tbuf + (size_t)b * AF_ROWS * MX;
+            tc::mbar_wait(tfull + tb, tpar);
+            const float2* Tb = Tbuf + (size_t)tb * AF_ROWS * MX;
             const int64_t img0 = (int64_t)(first + i * stride) * p.G;
             for (int item = ct; item < items; item += AF_CTHREADS) {
                 const int kx = item % MX;
@@ -218,18 +219,35 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
                     }
                 }
             }
-            tc::mbar_arrive(tempty + b);
+            tc::mbar_arrive(tempty + tb);
+            if (++tb == NTB) { tb = 0; tpar ^= 1; }
         }
     }
 }
 
 static int g_af_sms = 0;
 
-static size_t af_smem_bytes(const sb200_plan_s* p) {
+static size_t af_smem_bytes(const sb200_plan_s* p, int nxb, int ntb) {
     const int Myp = (p->My + 3) & ~3;
     const int TWS = (2 * p->Mx + 3) / 4 * 4;
-    return 1024 + 2 * (size_t)(p->W / 32) * AF_ROWS * 128 + 2 * (size_t)AF_ROWS * p->Mx * 8 +
+    return 1024 + (size_t)nxb * (p->W / 32) * AF_ROWS * 128 + (size_t)ntb * AF_ROWS * p->Mx * 8 +
            (size_t)(p->W / 2 + 1) * TWS * 4 + (size_t)p->H * Myp * 8 + 64;
+}
+
+// ring depths (x ring = TMA destinations, T ring = row stage -> column stage).  Measured on B200 at cfg2 shapes
+// (session 5, L2-flushed): {2,2} 51.4 us, {3,1} 53.3 us, {2,1} 52.3 us -- the kernel is bound by the latency of its
+// FFMA stages, not by bytes in flight, so the second T slot is worth more than a third x buffer.
+// SB200_AF_RING=<nxb><ntb> overrides (experiments).
+static void af_ring(const sb200_plan_s* p, int* nxb, int* ntb) {
+    static const int env = getenv("SB200_AF_RING") ? atoi(getenv("SB200_AF_RING")) : 0;
+    if (env >= 11 && env / 10 <= 4 && env % 10 >= 1 && env % 10 <= 2 && af_smem_bytes(p, env / 10, env % 10) <= 227 * 1024) {
+        *nxb = env / 10; *ntb = env % 10;
+        return;
+    }
+    const int cand[][2] = {{2, 2}, {2, 1}, {1, 1}};
+    for (const auto& c : cand)
+        if (af_smem_bytes(p, c[0], c[1]) <= 227 * 1024) { *nxb = c[0]; *ntb = c[1]; return; }
+    *nxb = 0; *ntb = 0;
 }
 
 // geometry check shared by the scratch query and the launcher
@@ -239,7 +257,9 @@ static bool af_supported(const sb200_plan_s* p) {
     if (H < 8 || AF_ROWS % H != 0) return false;
     if (!(Mx == 5 || Mx == 7 || Mx == 9 || Mx == 13 || Mx == 17)) return false;
     if (Mx > W / 2 + 1) return false;
-    return af_smem_bytes(p) <= 227 * 1024;
+    int nxb, ntb;
+    af_ring(p, &nxb, &ntb);
+    return nxb > 0;
 }
 
 bool sb200_analysis_fused_supported(sb200_plan_t plan) { return af_supported(plan); }
@@ -254,7 +274,8 @@ int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh,
     p.rowF = plan->rowF[pass]; p.colF = plan->colF[pass]; p.Xh = reinterpret_cast<float2*>(Xh);
     p.nimg = nimg; p.H = H; p.W = W; p.My = My; p.G = AF_ROWS / H;
     p.ngroups = (int)((rows + AF_ROWS - 1) / AF_ROWS);
-    const size_t smem = af_smem_bytes(plan);
+    af_ring(plan, &p.nxb, &p.ntb);
+    const size_t smem = af_smem_bytes(plan, p.nxb, p.ntb);
     CUtensorMap tmap;
     if (int rc = sb200_make_tmap_2d_f32(&tmap, x, (uint64_t)W, (uint64_t)rows, (uint64_t)W * 4, 32, AF_ROWS, 1)) return rc;
     if (g_af_sms == 0) {

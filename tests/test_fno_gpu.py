@@ -252,6 +252,37 @@ def test_rollout_20_steps_vs_oracle():
     assert rel_l2(got[:, -1], ref[:, -1]) < 5e-5
 
 
+def test_rollout_engine_graph_and_sequence_forward():
+    """the captured-graph closed loop equals the eager loop and the oracle; the reference wrapper's
+    teacher-forcing loop (src/nsbench/models/fno/fno.py:29-43) is reproduced by sequence_forward."""
+    torch.manual_seed(7)
+    m = pkg.FNO(n_modes=(12, 12), hidden_channels=16, in_channels=1, out_channels=1, lifting_channels=32,
+                projection_channels=32, n_layers=4)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    x0 = _rand(3, 1, 32, 32, seed=12)
+    ref = so.rollout(sd, x0.double(), (12, 12), 4, 12)
+    m = m.to(DEV)
+    eng = pkg.Rollout(m, graph=True)
+    got = eng(x0.to(DEV), 12)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL
+    again = eng(x0.to(DEV), 12)                       # second call replays the captured step
+    assert torch.equal(got, again)
+    eager = pkg.Rollout(m, graph=False)(x0.to(DEV), 12)
+    assert rel_l2(eager, got) < 1e-6
+    # teacher forcing for 3 frames, closed loop for the remaining 3
+    xs = _rand(2, 6, 1, 32, 32, seed=13)
+    outs, x_t = [], None
+    for t in range(6):
+        x_t = xs[:, t].double() if t < 3 else x_t
+        x_t = so.fno_forward(sd, x_t, (12, 12), 4)
+        outs.append(x_t)
+    want = torch.stack(outs, dim=1)
+    with torch.no_grad():
+        seq = pkg.sequence_forward(m, xs.to(DEV), teacher_forcing_steps=3)
+    assert rel_l2(seq, want) < TOL
+
+
 def test_cfg2_shapes_vs_oracle():
     """BASELINE configs[1] shapes (64x64, width 64, 16 modes, batch 64): one block fwd+bwd against the
     fp64 CPU oracle."""
