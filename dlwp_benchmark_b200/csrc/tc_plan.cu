@@ -83,8 +83,3 @@ void sb200_tc_tables_destroy(sb200_plan_s* p) {
     free(t);
     p->tc = nullptr;
 }
-
-int sb200_tc_rowdft_fwd(sb200_plan_t, int, const float*, float*, int64_t, cudaStream_t, int* handled) {
-    *handled = 0;
-    return 0;
-}

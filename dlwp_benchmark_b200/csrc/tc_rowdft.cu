@@ -1,0 +1,262 @@
+// tcgen05 truncated real DFT along W (the row stage of the analysis for grids the fused small-grid kernel
+// does not cover: W = 128, 256, ...):
+//
+//      T[row, kx] = sum_x x[row, x] * rowF[x, kx]          rows = nimg * H,  kx < Mx  (complex, interleaved)
+//
+// as ONE dense GEMM against the precomputed twiddle matrix (SURVEY.md 8a / north_star (a)):
+//      D[128 rows, N] = A[128 rows, K = W] * B[N, K]^T,    N = 2*Mx rounded up to 16, n = 2*kx + {0: re, 1: im}
+//   A : the image rows as they lie in memory (the contraction index x is the contiguous one), TMA boxes
+//       {32 x, 128 rows} with the 128B swizzle = the K-major SW128 UMMA operand directly; a ring of K chunks
+//   B : the twiddles, resident in shared memory for the whole kernel (K-major SW128, tf32 hi / lo)
+//   D : fp32 in TMEM, double buffered, so the epilogue of tile t overlaps the MMAs of tile t + 1
+// replaces torch.fft.rfftn's row pass + the kx slice of neuralop SpectralConv.forward (and, with the pass-1
+// tables, the adjoint of irfftn's row pass).  3xTF32 operand split as in tc_pointwise.cu (parity <= 1e-5);
+// sb200_set_tc_mode(1) runs the single TF32 pass, mode 0 keeps the FFMA kernel (rowdft_fwd_kernel).
+//   warp 0     TMA producer (one lane)
+//   warp 1     MMA issuer (one lane)
+//   warps 2-17 workers: tf32 hi/lo split of the landed chunks of tile t + 1, then epilogue of tile t
+#include "common.cuh"
+#include "tc_common.cuh"
+
+extern "C" int sb200_get_tc_mode(void);
+
+namespace {
+
+constexpr int TR_ROWS = 128;
+constexpr int TR_WORKER_WARPS = 16;
+constexpr int TR_THREADS = 32 * (2 + TR_WORKER_WARPS);
+constexpr int TR_WTHREADS = 32 * TR_WORKER_WARPS;
+constexpr uint32_t TR_A_BYTES = TR_ROWS * 128;          // one K chunk: 128 rows x 32 fp32
+
+struct TcRdParams {
+    const float2* rowF;      // [W][Mx]
+    float2* T;               // [rows][Mx]
+    int64_t rows;
+    uint32_t ntiles;
+    int W, Mx, N, nkc, stages;
+    uint32_t idesc, tmem_cols;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(TR_THREADS, 1)
+tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S = p.stages, nkc = p.nkc, N = p.N;
+    const uint32_t b_chunk = (uint32_t)N * 128;                       // N rows x 128 B per K chunk (N % 8 == 0)
+    const uint32_t b_bytes = (uint32_t)nkc * b_chunk;
+    const uint32_t stage_bytes = TR_A_BYTES * (PASSES == 3 ? 2 : 1);  // [hi | lo]
+    uint8_t* B_hi = base;
+    uint8_t* B_lo = B_hi + b_bytes;
+    uint8_t* A_st = B_lo + (PASSES == 3 ? b_bytes : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(A_st + (uint32_t)S * stage_bytes);
+    uint64_t* split_bar = full_bar + S;
+    uint64_t* empty_bar = split_bar + S;
+    uint64_t* tfull_bar = empty_bar + S;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmapX);
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(full_bar + s, 1);
+            tc::mbar_init(split_bar + s, TR_WORKER_WARPS);
+            tc::mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(tfull_bar + a, 1);
+            tc::mbar_init(tempty_bar + a, TR_WORKER_WARPS);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    // resident twiddle operand: B[n, x] = rowF[x][n >> 1].{x, y}; rows n >= 2*Mx are zero
+    for (int idx = tid; idx < N * p.W; idx += TR_THREADS) {
+        const int x = idx / N, n = idx - x * N;                       // n fastest: a warp reads one table row
+        float v = 0.f;
+        if (n < 2 * p.Mx) {
+            const float2 t = __ldg(p.rowF + (size_t)x * p.Mx + (n >> 1));
+            v = (n & 1) ? t.y : t.x;
+        }
+        const float hi = tc::tf32_trunc(v);
+        const uint32_t off = (uint32_t)(x >> 5) * b_chunk + tc::sw128_kmajor_off(n, x & 31);
+        *reinterpret_cast<float*>(B_hi + off) = hi;
+        if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = v - hi;
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t first = blockIdx.x, stride = gridDim.x, ntiles = p.ntiles;
+    const uint32_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const int row0 = (int)((first + it * stride) * TR_ROWS);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(empty_bar + s, ph ^ 1);
+                    tc::mbar_expect_tx(full_bar + s, TR_A_BYTES);
+                    tc::tma_load_2d(A_st + s * stage_bytes, &tmapX, kc * 32, row0, full_bar + s);
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
+            const uint32_t bh_base = tc::desc_lo(tc::smem_u32(B_hi), 16), bl_base = tc::desc_lo(tc::smem_u32(B_lo), 16);
+            uint32_t s = 0, ph = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t a = it & 1, tround = it >> 1;
+                tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
+                tc::tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + a * (uint32_t)N;
+                uint32_t started = 0;
+                uint32_t boff = 0;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
+                    tc::tc_fence_after_sync();
+                    uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + s * stage_bytes), 16);
+                    uint32_t al = ah + (TR_A_BYTES >> 4);
+                    uint32_t bo = boff;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc::umma_tf32_lh(tmem_d, ah, hi32, bh_base + bo, hi32, p.idesc, started);
+                        started = 1;
+                        if (PASSES == 3) {
+                            tc::umma_tf32_lh(tmem_d, al, hi32, bh_base + bo, hi32, p.idesc, 1u);
+                            tc::umma_tf32_lh(tmem_d, ah, hi32, bl_base + bo, hi32, p.idesc, 1u);
+                        }
+                        ah += 32 >> 4; al += 32 >> 4; bo += 32 >> 4;
+                    }
+                    tc::umma_commit(empty_bar + s);
+                    boff += b_chunk >> 4;
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+                tc::umma_commit(tfull_bar + a);
+            }
+        }
+    } else {
+        const int wk = warp - 2, wtid = tid - 64;
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cpart = wk >> 2;                          // 16-column slice of the accumulator it drains
+        const bool drains = cpart * 16 < 2 * p.Mx;
+        const int kx0 = cpart * 8;
+        const int nkx = min(8, p.Mx - kx0);
+        uint32_t sp_s = 0, sp_ph = 0;
+        auto split_tile = [&]() {
+            if (PASSES == 3) {
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(full_bar + sp_s, sp_ph);
+                    float4* ah = reinterpret_cast<float4*>(A_st + sp_s * stage_bytes);
+                    float4* al = reinterpret_cast<float4*>(A_st + sp_s * stage_bytes + TR_A_BYTES);
+#pragma unroll
+                    for (int j = 0; j < (int)(TR_A_BYTES / 16) / TR_WTHREADS; ++j) {
+                        const int idx = wtid + j * TR_WTHREADS;
+                        const float4 v = ah[idx];
+                        const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
+                        ah[idx] = h;
+                        al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
+                }
+            }
+        };
+        if (my_tiles > 0) split_tile();
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            if (it + 1 < my_tiles) split_tile();
+            const uint32_t a = it & 1, tround = it >> 1;
+            tc::mbar_wait(tfull_bar + a, tround & 1);
+            tc::tc_fence_after_sync();
+            if (drains) {
+                uint32_t r[16];
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)N + (uint32_t)(cpart * 16), r);
+                tc::tmem_ld_wait();
+                const int64_t row = (int64_t)(first + it * stride) * TR_ROWS + quarter * 32 + lane;
+                if (row < p.rows) {
+                    float2* dst = p.T + row * p.Mx + kx0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nkx) dst[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                }
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int g_tr_sms = 0;
+
+}  // namespace
+
+int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, cudaStream_t st,
+                        int* handled) {
+    *handled = 0;
+    const int passes = sb200_get_tc_mode();
+    if (passes == 0) return 0;
+    static const bool disabled = getenv("SB200_TC_ROWDFT_OFF") != nullptr;      // experiments: force the FFMA kernel
+    if (disabled) return 0;
+    const int W = plan->W, Mx = plan->Mx;
+    if (W % 32 != 0 || W < 64 || W > 2048) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(T) & 7) != 0) return 0;
+    const int N = (2 * Mx + 15) / 16 * 16;
+    if (N > 64) return 0;
+    if (rows >= (1LL << 31) - TR_ROWS) return 0;
+
+    TcRdParams p;
+    p.rowF = plan->rowF[pass];
+    p.T = reinterpret_cast<float2*>(T);
+    p.rows = rows;
+    p.ntiles = (uint32_t)((rows + TR_ROWS - 1) / TR_ROWS);
+    p.W = W; p.Mx = Mx; p.N = N; p.nkc = W / 32;
+    p.idesc = tc::make_idesc_tf32(128, N, 0, 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * N)) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t mult = passes == 3 ? 2 : 1;
+    const size_t b_bytes = (size_t)p.nkc * N * 128 * mult;
+    const size_t a_stage = (size_t)TR_A_BYTES * mult;
+    const size_t fixed = 1024 + b_bytes + 512;
+    int stages = 8;
+    while (stages > 2 && fixed + stages * a_stage > 224 * 1024) --stages;
+    if (fixed + stages * a_stage > 227 * 1024) return 0;               // twiddle operand too large: FFMA kernel
+    p.stages = stages;
+    const size_t smem = fixed + stages * a_stage;
+
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, x, (uint64_t)W, (uint64_t)rows, (uint64_t)W * 4, 32, TR_ROWS, 1)) return rc;
+    if (g_tr_sms == 0) {
+        int dev = 0;
+        SB_CHECK_CUDA(cudaGetDevice(&dev));
+        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_tr_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = p.ntiles < (uint32_t)g_tr_sms ? p.ntiles : (unsigned)g_tr_sms;
+    if (passes == 3) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb_launch(tc_rowdft_kernel<3>, grid, TR_THREADS, smem, st, tmap, p);
+    } else {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb_launch(tc_rowdft_kernel<1>, grid, TR_THREADS, smem, st, tmap, p);
+    }
+    SB_LAUNCH_CHECK();
+    *handled = 1;
+    return 0;
+}

@@ -58,6 +58,38 @@ def test_analysis_stages(B, C, H, W, nm):
     assert rel_l2(torch.view_as_complex(Xh), ref) < TOL
 
 
+TC_ROWDFT_SHAPES = [
+    # B, C, H, W, n_modes        (rows = B*C*H; tiles of 128 rows)
+    (1, 3, 50, 64, (12, 12)),    # 150 rows: partial last tile, N = 16
+    (2, 5, 128, 128, (32, 32)),  # cfg5 grid, N = 48 (Mx = 17), 10 tiles
+    (1, 9, 256, 256, (32, 32)),  # cfg3 grid: 8 K chunks through a 3-stage ring
+    (3, 2, 64, 256, (16, 16)),   # N = 32 (Mx = 9)
+    (1, 1, 8, 256, (8, 60)),     # fewer rows than one tile, N = 64 (Mx = 31): 128 KB of twiddles, 2-stage ring
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(3, 1e-5), (1, 3e-3)])
+@pytest.mark.parametrize("pas", [0, 1])
+@pytest.mark.parametrize("B,C,H,W,nm", TC_ROWDFT_SHAPES)
+def test_tc_rowdft(B, C, H, W, nm, pas, mode, tol):
+    """tcgen05 row DFT (tc_rowdft.cu) against torch.fft (pass 0) and against the exact-fp32 FFMA kernel (both passes)."""
+    half = so.halve_last_mode(nm)
+    plan = fno_plan(DEV, H, W, half)
+    x = _rand(B, C, H, W, seed=21)
+    xg = x.to(DEV)
+    try:
+        _set_tc(0)
+        exact = ops.rowdft_fwd(plan, pas, xg)
+        _set_tc(mode)
+        T = ops.rowdft_fwd(plan, pas, xg)
+    finally:
+        _set_tc(3)
+    assert rel_l2(T, exact) < tol
+    if pas == 0:
+        refT = torch.fft.rfft(x.double(), dim=-1)[..., :plan.Mx]
+        assert rel_l2(torch.view_as_complex(T), refT) < tol
+
+
 ANALYSIS_SHAPES = STAGE_SHAPES + [
     (5, 3, 64, 64, (16, 16)),    # fused kernel, 15 images: partial last group (G = 4)
     (64, 8, 64, 64, (16, 16)),   # fused kernel, more groups than one wave per SM pair
