@@ -347,6 +347,9 @@ extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
     return nimg * p->H * p->Mx * 2;
 }
 
+int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, cudaStream_t st,
+                      int* handled);
+
 extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream) {
     SB_REQUIRE(p && x && Xh, "analysis: NULL argument");
     SB_REQUIRE(pass == 0 || pass == 1, "analysis: pass must be 0 or 1");
@@ -355,6 +358,8 @@ extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* X
     if (int rc = sb200_analysis_fused(p, pass, x, Xh, nimg, (cudaStream_t)stream, &handled)) return rc;
     if (handled) return 0;
     SB_REQUIRE(scratch != nullptr, "analysis: this grid needs sb200_analysis_scratch() floats of scratch");
+    if (int rc = sb200_tc_analysis(p, pass, x, Xh, nimg, scratch, (cudaStream_t)stream, &handled)) return rc;   // tc_rowdft.cu
+    if (handled) return 0;
     if (int rc = sb200_rowdft_fwd(p, pass, x, scratch, nimg * p->H, stream)) return rc;
     return sb200_coldft_fwd(p, pass, scratch, Xh, nimg, stream);
 }

@@ -12,6 +12,14 @@
 // replaces torch.fft.rfftn's row pass + the kx slice of neuralop SpectralConv.forward (and, with the pass-1
 // tables, the adjoint of irfftn's row pass).  3xTF32 operand split as in tc_pointwise.cu (parity <= 1e-5);
 // sb200_set_tc_mode(1) runs the single TF32 pass, mode 0 keeps the FFMA kernel (rowdft_fwd_kernel).
+// The same kernel also runs the column stage of the analysis (MODE 2) when the row stage leaves its result in the
+// planar, transposed layout T'[img][n = 2*kx + c][y] (MODE 1): then the column DFT is again "rows x K" against a
+// resident twiddle matrix, with rows = (img, kx, re|im), K = y and B[n' = 2*ky + c'][y] = (Re, Im) colF[ky][y]:
+//      D[(img,kx,0)][(ky,r)] = sum_y a*tr   D[(img,kx,0)][(ky,i)] = sum_y b*tr        (colF = a + i b, T = tr + i ti)
+//      D[(img,kx,1)][(ky,r)] = sum_y a*ti   D[(img,kx,1)][(ky,i)] = sum_y b*ti
+//      Xh[img][ky][kx] = (D00 - D11) + i (D10 + D01): the two rows are adjacent TMEM lanes, one SHFL in the epilogue.
+// The intermediate never takes the interleaved [.., Mx, 2] form, its stores are full 128-byte lines, and both
+// stages of the large-grid analysis run on the tensor cores.
 //   warp 0     TMA producer (one lane)
 //   warp 1     MMA issuer (one lane)
 //   warps 2-17 workers: tf32 hi/lo split of the landed chunks of tile t + 1, then epilogue of tile t
@@ -29,15 +37,18 @@ constexpr int TR_WTHREADS = 32 * TR_WORKER_WARPS;
 constexpr uint32_t TR_A_BYTES = TR_ROWS * 128;          // one K chunk: 128 rows x 32 fp32
 
 struct TcRdParams {
-    const float2* rowF;      // [W][Mx]
-    float2* T;               // [rows][Mx]
-    int64_t rows;
+    const float2* tab;       // MODE 0/1: rowF [K = W][Mx];  MODE 2: colF [My][K = H]
+    float* out;              // MODE 0: T [rows][Mx] complex | MODE 1: T' [img][2*Mx][H] | MODE 2: Xh [img][My][Mx] complex
+    int64_t rows;            // GEMM rows: images * H (MODE 0/1), images * 2*Mx (MODE 2)
     uint32_t ntiles;
-    int W, Mx, N, nkc, stages;
+    int K, Mx, My, H, N, nvalid, nkc, stages;     // nvalid = 2*Mx (MODE 0/1) or 2*My (MODE 2) meaningful accumulator columns
     uint32_t idesc, tmem_cols;
 };
 
-template <int PASSES>
+// MODE 0: row DFT, interleaved complex output (public sb200_rowdft_fwd)
+// MODE 1: row DFT, planar transposed output T' (first half of sb200_analysis)
+// MODE 2: column DFT from T' (second half of sb200_analysis)
+template <int PASSES, int MODE>
 __global__ void __launch_bounds__(TR_THREADS, 1)
 tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,12 +86,15 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
         tc::tmem_alloc(tmem_slot, p.tmem_cols);
         tc::tmem_relinquish();
     }
-    // resident twiddle operand: B[n, x] = rowF[x][n >> 1].{x, y}; rows n >= 2*Mx are zero
-    for (int idx = tid; idx < N * p.W; idx += TR_THREADS) {
-        const int x = idx / N, n = idx - x * N;                       // n fastest: a warp reads one table row
+    // resident twiddle operand B[n][k]; rows n >= nvalid are zero
+    //   MODE 0/1: B[n][x] = rowF[x][n >> 1].{x, y}        MODE 2: B[n][y] = colF[n >> 1][y].{x, y}
+    for (int idx = tid; idx < N * p.K; idx += TR_THREADS) {
+        int x, n;
+        if (MODE == 2) { n = idx / p.K; x = idx - n * p.K; }           // k fastest: a warp reads along one table row
+        else { x = idx / N; n = idx - x * N; }                         // n fastest: likewise
         float v = 0.f;
-        if (n < 2 * p.Mx) {
-            const float2 t = __ldg(p.rowF + (size_t)x * p.Mx + (n >> 1));
+        if (n < p.nvalid) {
+            const float2 t = MODE == 2 ? __ldg(p.tab + (size_t)(n >> 1) * p.K + x) : __ldg(p.tab + (size_t)x * p.Mx + (n >> 1));
             v = (n & 1) ? t.y : t.x;
         }
         const float hi = tc::tf32_trunc(v);
@@ -149,9 +163,9 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
         const int wk = warp - 2, wtid = tid - 64;
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
         const int cpart = wk >> 2;                          // 16-column slice of the accumulator it drains
-        const bool drains = cpart * 16 < 2 * p.Mx;
-        const int kx0 = cpart * 8;
-        const int nkx = min(8, p.Mx - kx0);
+        const bool drains = cpart * 16 < p.nvalid;
+        const int c0 = cpart * 16;                          // first accumulator column of this warp
+        const int npair = min(8, (p.nvalid - c0) >> 1);     // complex values (MODE 0) / ky values (MODE 2) in the slice
         uint32_t sp_s = 0, sp_ph = 0;
         auto split_tile = [&]() {
             if (PASSES == 3) {
@@ -185,11 +199,35 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
                 tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)N + (uint32_t)(cpart * 16), r);
                 tc::tmem_ld_wait();
                 const int64_t row = (int64_t)(first + it * stride) * TR_ROWS + quarter * 32 + lane;
-                if (row < p.rows) {
-                    float2* dst = p.T + row * p.Mx + kx0;
+                if (MODE == 0) {
+                    if (row < p.rows) {
+                        float2* dst = reinterpret_cast<float2*>(p.out) + row * p.Mx + (c0 >> 1);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nkx) dst[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        for (int j = 0; j < 8; ++j)
+                            if (j < npair) dst[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    }
+                } else if (MODE == 1) {
+                    // T'[img][n][y]: the 32 lanes of a warp are 32 consecutive y of one image (32 | H): full-line stores
+                    if (row < p.rows) {
+                        const int64_t img = row / p.H;
+                        const int y = (int)(row - img * p.H);
+                        float* dst = p.out + (img * p.nvalid + c0) * p.H + y;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.nvalid) dst[(int64_t)j * p.H] = __uint_as_float(r[j]);
+                    }
+                } else {
+                    // rows (img, kx, 0) and (img, kx, 1) are lanes 2l and 2l + 1 (2*Mx and the tile base are even)
+                    const int64_t img = row / (2 * p.Mx);
+                    const int n = (int)(row - img * (2 * p.Mx));
+                    const bool writer = !(lane & 1) && row < p.rows;
+                    float2* dst = reinterpret_cast<float2*>(p.out) + (img * p.My + (c0 >> 1)) * p.Mx + (n >> 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float own_r = __uint_as_float(r[2 * j]), own_i = __uint_as_float(r[2 * j + 1]);
+                        const float oth_r = __shfl_xor_sync(0xffffffffu, own_r, 1), oth_i = __shfl_xor_sync(0xffffffffu, own_i, 1);
+                        if (writer && j < npair) dst[(int64_t)j * p.Mx] = make_float2(own_r - oth_i, oth_r + own_i);
+                    }
                 }
             }
             tc::tc_fence_before_sync();
@@ -206,43 +244,41 @@ int g_tr_sms = 0;
 
 }  // namespace
 
-int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, cudaStream_t st,
-                        int* handled) {
-    *handled = 0;
-    const int passes = sb200_get_tc_mode();
-    if (passes == 0) return 0;
-    static const bool disabled = getenv("SB200_TC_ROWDFT_OFF") != nullptr;      // experiments: force the FFMA kernel
-    if (disabled) return 0;
-    const int W = plan->W, Mx = plan->Mx;
-    if (W % 32 != 0 || W < 64 || W > 2048) return 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(T) & 7) != 0) return 0;
-    const int N = (2 * Mx + 15) / 16 * 16;
-    if (N > 64) return 0;
-    if (rows >= (1LL << 31) - TR_ROWS) return 0;
-
-    TcRdParams p;
-    p.rowF = plan->rowF[pass];
-    p.T = reinterpret_cast<float2*>(T);
-    p.rows = rows;
-    p.ntiles = (uint32_t)((rows + TR_ROWS - 1) / TR_ROWS);
-    p.W = W; p.Mx = Mx; p.N = N; p.nkc = W / 32;
-    p.idesc = tc::make_idesc_tf32(128, N, 0, 0);
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * N)) cols <<= 1;
-    p.tmem_cols = cols;
+// geometry both stages need: K chunks of 32 fp32, twiddle operand + at least a 2-stage ring inside 227 KB
+static bool tr_fits(int K, int nvalid, int passes, int* N_out, int* stages_out, size_t* smem_out) {
+    if (K % 32 != 0 || K < 64 || K > 2048 || nvalid < 2 || (nvalid & 1)) return false;
+    const int N = (nvalid + 15) / 16 * 16;
+    if (N > 64) return false;
     const size_t mult = passes == 3 ? 2 : 1;
-    const size_t b_bytes = (size_t)p.nkc * N * 128 * mult;
+    const size_t b_bytes = (size_t)(K / 32) * N * 128 * mult;
     const size_t a_stage = (size_t)TR_A_BYTES * mult;
     const size_t fixed = 1024 + b_bytes + 512;
     int stages = 8;
     while (stages > 2 && fixed + stages * a_stage > 224 * 1024) --stages;
-    if (fixed + stages * a_stage > 227 * 1024) return 0;               // twiddle operand too large: FFMA kernel
-    p.stages = stages;
-    const size_t smem = fixed + stages * a_stage;
+    if (fixed + stages * a_stage > 227 * 1024) return false;
+    *N_out = N; *stages_out = stages; *smem_out = fixed + stages * a_stage;
+    return true;
+}
 
+template <int MODE>
+static int tr_launch(const float* in, const float2* tab, float* out, int64_t rows, int K, int nvalid, int Mx, int My, int H,
+                     int passes, cudaStream_t st) {
+    TcRdParams p;
+    size_t smem = 0;
+    if (!tr_fits(K, nvalid, passes, &p.N, &p.stages, &smem)) {
+        sb200_set_error("tc_rowdft: internal: geometry K=%d nvalid=%d not supported", K, nvalid);
+        return 2;
+    }
+    p.tab = tab; p.out = out; p.rows = rows;
+    p.ntiles = (uint32_t)((rows + TR_ROWS - 1) / TR_ROWS);
+    p.K = K; p.Mx = Mx; p.My = My; p.H = H; p.nvalid = nvalid; p.nkc = K / 32;
+    p.idesc = tc::make_idesc_tf32(128, p.N, 0, 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.N)) cols <<= 1;
+    p.tmem_cols = cols;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (int rc = sb200_make_tmap_2d_f32(&tmap, x, (uint64_t)W, (uint64_t)rows, (uint64_t)W * 4, 32, TR_ROWS, 1)) return rc;
+    if (int rc = sb200_make_tmap_2d_f32(&tmap, in, (uint64_t)K, (uint64_t)rows, (uint64_t)K * 4, 32, TR_ROWS, 1)) return rc;
     if (g_tr_sms == 0) {
         int dev = 0;
         SB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -250,13 +286,57 @@ int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, i
     }
     const unsigned grid = p.ntiles < (uint32_t)g_tr_sms ? p.ntiles : (unsigned)g_tr_sms;
     if (passes == 3) {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sb_launch(tc_rowdft_kernel<3>, grid, TR_THREADS, smem, st, tmap, p);
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb_launch(tc_rowdft_kernel<3, MODE>, grid, TR_THREADS, smem, st, tmap, p);
     } else {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sb_launch(tc_rowdft_kernel<1>, grid, TR_THREADS, smem, st, tmap, p);
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb_launch(tc_rowdft_kernel<1, MODE>, grid, TR_THREADS, smem, st, tmap, p);
     }
     SB_LAUNCH_CHECK();
+    return 0;
+}
+
+static bool tr_enabled() {
+    static const bool disabled = getenv("SB200_TC_ROWDFT_OFF") != nullptr;      // experiments: force the FFMA kernels
+    return !disabled && sb200_get_tc_mode() != 0;
+}
+
+// public row stage (sb200_rowdft_fwd): x [rows][W] -> T [rows][Mx] interleaved complex
+int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, cudaStream_t st,
+                        int* handled) {
+    *handled = 0;
+    if (!tr_enabled()) return 0;
+    const int passes = sb200_get_tc_mode();
+    int N, stages;
+    size_t smem;
+    if (!tr_fits(plan->W, 2 * plan->Mx, passes, &N, &stages, &smem)) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(T) & 7) != 0) return 0;
+    if (rows >= (1LL << 31) - TR_ROWS) return 0;
+    if (int rc = tr_launch<0>(x, plan->rowF[pass], T, rows, plan->W, 2 * plan->Mx, plan->Mx, plan->My, plan->H, passes, st))
+        return rc;
+    *handled = 1;
+    return 0;
+}
+
+// both stages of the analysis on the tensor cores: x [nimg][H][W] -> scratch T' [nimg][2*Mx][H] -> Xh [nimg][My][Mx];
+// scratch holds sb200_analysis_scratch() floats (the same 2*nimg*H*Mx as the interleaved intermediate)
+int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, cudaStream_t st,
+                      int* handled) {
+    *handled = 0;
+    if (!tr_enabled() || scratch == nullptr) return 0;
+    static const bool col_off = getenv("SB200_TC_COLDFT_OFF") != nullptr;       // experiments: tensor-core row stage only
+    if (col_off) return 0;
+    const int passes = sb200_get_tc_mode();
+    const int H = plan->H, W = plan->W, Mx = plan->Mx, My = plan->My;
+    int N, stages;
+    size_t smem;
+    if (!tr_fits(W, 2 * Mx, passes, &N, &stages, &smem) || !tr_fits(H, 2 * My, passes, &N, &stages, &smem)) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(scratch) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(Xh) & 7) != 0)
+        return 0;
+    if (nimg * H >= (1LL << 31) - TR_ROWS || nimg * 2 * Mx >= (1LL << 31) - TR_ROWS) return 0;
+    if (int rc = tr_launch<1>(x, plan->rowF[pass], scratch, nimg * H, W, 2 * Mx, Mx, My, H, passes, st)) return rc;
+    if (int rc = tr_launch<2>(scratch, plan->colF[pass], Xh, nimg * 2 * Mx, H, 2 * My, Mx, My, H, passes, st)) return rc;
     *handled = 1;
     return 0;
 }
