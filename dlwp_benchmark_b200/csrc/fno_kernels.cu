@@ -341,20 +341,34 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
 bool sb200_analysis_fused_supported(sb200_plan_t plan);                                              // analysis_fused.cu
 int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, cudaStream_t st, int* handled);
 
-extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
-    if (!p || nimg <= 0) return 0;
-    if (sb200_analysis_fused_supported(p)) return 0;
-    return nimg * p->H * p->Mx * 2;
+int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, cudaStream_t st,
+                      int* handled);   // tc_rowdft.cu
+
+// which path serves grids that both the fused FFMA kernel and the tensor-core two-stage path cover
+// (SB200_ANALYSIS_PREFER=tc|fused; experiments)
+static bool analysis_prefers_tc() {
+    static const int v = []() {
+        const char* e = getenv("SB200_ANALYSIS_PREFER");
+        return (e && e[0] == 't') ? 1 : 0;
+    }();
+    return v != 0;
 }
 
-int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, cudaStream_t st,
-                      int* handled);
+extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
+    if (!p || nimg <= 0) return 0;
+    if (sb200_analysis_fused_supported(p) && !analysis_prefers_tc()) return 0;
+    return nimg * p->H * p->Mx * 2;
+}
 
 extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream) {
     SB_REQUIRE(p && x && Xh, "analysis: NULL argument");
     SB_REQUIRE(pass == 0 || pass == 1, "analysis: pass must be 0 or 1");
     if (nimg <= 0) return 0;
     int handled = 0;
+    if (analysis_prefers_tc() && scratch != nullptr) {
+        if (int rc = sb200_tc_analysis(p, pass, x, Xh, nimg, scratch, (cudaStream_t)stream, &handled)) return rc;
+        if (handled) return 0;
+    }
     if (int rc = sb200_analysis_fused(p, pass, x, Xh, nimg, (cudaStream_t)stream, &handled)) return rc;
     if (handled) return 0;
     SB_REQUIRE(scratch != nullptr, "analysis: this grid needs sb200_analysis_scratch() floats of scratch");

@@ -35,6 +35,7 @@ constexpr int TR_WORKER_WARPS = 16;
 constexpr int TR_THREADS = 32 * (2 + TR_WORKER_WARPS);
 constexpr int TR_WTHREADS = 32 * TR_WORKER_WARPS;
 constexpr uint32_t TR_A_BYTES = TR_ROWS * 128;          // one K chunk: 128 rows x 32 fp32
+constexpr uint32_t TR_NLO = 2;                          // buffers for the tf32 "lo" part of a chunk
 
 struct TcRdParams {
     const float2* tab;       // MODE 0/1: rowF [K = W][Mx];  MODE 2: colF [My][K = H]
@@ -56,11 +57,15 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
     const int S = p.stages, nkc = p.nkc, N = p.N;
     const uint32_t b_chunk = (uint32_t)N * 128;                       // N rows x 128 B per K chunk (N % 8 == 0)
     const uint32_t b_bytes = (uint32_t)nkc * b_chunk;
-    const uint32_t stage_bytes = TR_A_BYTES * (PASSES == 3 ? 2 : 1);  // [hi | lo]
+    // The ring of TMA destinations (S stages; the landed fp32 chunk is truncated in place to its tf32 "hi" part) is
+    // decoupled from the tf32 "lo" parts, which only live from the split to the MMAs of the same chunk: TR_NLO buffers
+    // are enough, and the shared memory saved buys ring depth = bytes in flight (what the strided-row TMA stream needs).
+    const uint32_t stage_bytes = TR_A_BYTES;
     uint8_t* B_hi = base;
     uint8_t* B_lo = B_hi + b_bytes;
     uint8_t* A_st = B_lo + (PASSES == 3 ? b_bytes : 0);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(A_st + (uint32_t)S * stage_bytes);
+    uint8_t* A_lo = A_st + (uint32_t)S * stage_bytes;                 // [TR_NLO][16 KB]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(A_lo + (PASSES == 3 ? TR_NLO * TR_A_BYTES : 0));
     uint64_t* split_bar = full_bar + S;
     uint64_t* empty_bar = split_bar + S;
     uint64_t* tfull_bar = empty_bar + S;
@@ -128,7 +133,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
         if (lane == 0) {
             const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t bh_base = tc::desc_lo(tc::smem_u32(B_hi), 16), bl_base = tc::desc_lo(tc::smem_u32(B_lo), 16);
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, lo = 0;
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const uint32_t a = it & 1, tround = it >> 1;
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
@@ -140,7 +145,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
                     tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
                     tc::tc_fence_after_sync();
                     uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + s * stage_bytes), 16);
-                    uint32_t al = ah + (TR_A_BYTES >> 4);
+                    uint32_t al = tc::desc_lo(tc::smem_u32(A_lo + lo * TR_A_BYTES), 16);
                     uint32_t bo = boff;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
@@ -152,9 +157,10 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
                         }
                         ah += 32 >> 4; al += 32 >> 4; bo += 32 >> 4;
                     }
-                    tc::umma_commit(empty_bar + s);
+                    tc::umma_commit(empty_bar + s);                    // frees the stage AND the lo buffer of this chunk
                     boff += b_chunk >> 4;
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                    if (++lo == TR_NLO) lo = 0;
                 }
                 tc::umma_commit(tfull_bar + a);
             }
@@ -166,13 +172,21 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
         const bool drains = cpart * 16 < p.nvalid;
         const int c0 = cpart * 16;                          // first accumulator column of this warp
         const int npair = min(8, (p.nvalid - c0) >> 1);     // complex values (MODE 0) / ky values (MODE 2) in the slice
-        uint32_t sp_s = 0, sp_ph = 0;
+        uint32_t sp_s = 0, sp_ph = 0, sp_lo = 0;            // chunk g: stage, phase parity, lo buffer
+        uint32_t lag_s = 0, lag_ph = 0, g = 0;             // chunk g - TR_NLO, the previous user of that lo buffer
         auto split_tile = [&]() {
             if (PASSES == 3) {
                 for (int kc = 0; kc < nkc; ++kc) {
+                    if (g >= TR_NLO) {
+                        // lo[sp_lo] was last read by the MMAs of chunk g - TR_NLO; their commit is that chunk's empty phase.
+                        // (That barrier cannot have moved a further phase on: its next use is chunk g - TR_NLO + S > g.)
+                        tc::mbar_wait(empty_bar + lag_s, lag_ph);
+                        if (++lag_s == (uint32_t)S) { lag_s = 0; lag_ph ^= 1; }
+                    }
+                    ++g;
                     tc::mbar_wait(full_bar + sp_s, sp_ph);
                     float4* ah = reinterpret_cast<float4*>(A_st + sp_s * stage_bytes);
-                    float4* al = reinterpret_cast<float4*>(A_st + sp_s * stage_bytes + TR_A_BYTES);
+                    float4* al = reinterpret_cast<float4*>(A_lo + sp_lo * TR_A_BYTES);
 #pragma unroll
                     for (int j = 0; j < (int)(TR_A_BYTES / 16) / TR_WTHREADS; ++j) {
                         const int idx = wtid + j * TR_WTHREADS;
@@ -185,6 +199,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
                     if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
+                    if (++sp_lo == TR_NLO) sp_lo = 0;
                 }
             }
         };
@@ -251,8 +266,8 @@ static bool tr_fits(int K, int nvalid, int passes, int* N_out, int* stages_out, 
     if (N > 64) return false;
     const size_t mult = passes == 3 ? 2 : 1;
     const size_t b_bytes = (size_t)(K / 32) * N * 128 * mult;
-    const size_t a_stage = (size_t)TR_A_BYTES * mult;
-    const size_t fixed = 1024 + b_bytes + 512;
+    const size_t a_stage = (size_t)TR_A_BYTES;
+    const size_t fixed = 1024 + b_bytes + (passes == 3 ? TR_NLO * TR_A_BYTES : 0) + 512;
     int stages = 8;
     while (stages > 2 && fixed + stages * a_stage > 224 * 1024) --stages;
     if (fixed + stages * a_stage > 227 * 1024) return false;
