@@ -223,8 +223,8 @@ def _peak():
 
 def _ncu_traffic(kernel_substr, approx_read_bytes=None):
     """dram read+write bytes per launch of a kernel from the committed `ncu --set full` capture of this workload
-    (profiles/r01_cfg2_ncu_full_s5.json); None when the capture has no such kernel."""
-    path = os.path.join(ROOT, "profiles", "r01_cfg2_ncu_full_s5.json")
+    (profiles/r01_cfg2_ncu_full_s5f.json); None when the capture has no such kernel."""
+    path = os.path.join(ROOT, "profiles", "r01_cfg2_ncu_full_s5f.json")
     try:
         table = json.load(open(path))
     except Exception:
@@ -594,7 +594,7 @@ def run_b200(args, wl, rank, world, local_rank):
             traffic = _ncu_traffic(*ncu_name[top]) if args.workload == "cfg2" and top in ncu_name else None
             roof = {"bound": "hbm", "kernel": top, "achieved": kr[top]["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": kr[top]["frac"], "traffic": traffic,
-                    "traffic_source": "profiles/r01_cfg2_ncu_full_s5.json (ncu --set full, same shapes)" if traffic else None,
+                    "traffic_source": "profiles/r01_cfg2_ncu_full_s5f.json (ncu --set full, same shapes)" if traffic else None,
                     "peak_source": peak_src,
                     "kernel_ms": kr[top]["ms"], "alg_bytes": kr[top]["alg_bytes"],
                     "all": {k: {"ms": round(v["ms"], 4), "frac": round(v["frac"], 4)} for k, v in kr.items()}}
