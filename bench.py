@@ -214,6 +214,26 @@ def kernel_rooflines(wl, peak_gbs, reps=10):
     return out
 
 
+def _finish(world, graphs=()):
+    """End of a rank's work.  With N > 1 the process leaves through os._exit(0) instead of
+    dist.destroy_process_group(): tearing down an NCCL communicator that a CUDA graph captured blocks
+    (measured in session 5 at N = 2 and N = 8: every rank finished and rank 0 had printed its line, then all of
+    them sat in destroy_process_group until the launcher's timeout killed them).  The captured graphs are
+    released first, output is flushed, nothing is left to lose."""
+    import torch
+    torch.cuda.synchronize()
+    for g in graphs:
+        try:
+            if g is not None:
+                g.reset()
+        except Exception:  # noqa: BLE001
+            pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -304,6 +324,7 @@ def run_afno(args, wl, rank, world, local_rank):
     step_eager(); torch.cuda.synchronize()
     launches = int(lib.sb200_kernel_launches() - n0)
     step = step_eager
+    graph = None
     if not args.no_graph and sync is None:
         s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -352,8 +373,7 @@ def run_afno(args, wl, rank, world, local_rank):
                              "alg_bytes": alg, "note": "whole-step time over 20*P bytes per layer (includes Adam and the loss)"},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, (graph,))
 
 
 def run_rollout(args, wl, rank, world, local_rank):
@@ -418,8 +438,7 @@ def run_rollout(args, wl, rank, world, local_rank):
                              "alg_bytes": alg},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, (getattr(eng, "_graph", None),))
 
 
 # ----------------------------------------------------------------------------------------
@@ -626,8 +645,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, (graph,))
 
 
 def main():
