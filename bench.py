@@ -218,16 +218,8 @@ def _finish(world, graphs=()):
     """End of a rank's work.  With N > 1 the process leaves through os._exit(0) instead of
     dist.destroy_process_group(): tearing down an NCCL communicator that a CUDA graph captured blocks
     (measured in session 5 at N = 2 and N = 8: every rank finished and rank 0 had printed its line, then all of
-    them sat in destroy_process_group until the launcher's timeout killed them).  The captured graphs are
-    released first, output is flushed, nothing is left to lose."""
-    import torch
-    torch.cuda.synchronize()
-    for g in graphs:
-        try:
-            if g is not None:
-                g.reset()
-        except Exception:  # noqa: BLE001
-            pass
+    them sat in destroy_process_group until the launcher's timeout killed them).  Every collective of the run has
+    completed by the time a rank gets here and its output is flushed, so nothing is lost by not tearing down."""
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
