@@ -228,8 +228,12 @@ def _finish(world, graphs=()):
 
 def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    try:
+        v = float(json.load(open(peaks_path))["hbm_gbs"])
+        if v > 0:
+            return v, "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001  (absent or unreadable file: the recipe's stated fallback)
+        pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
