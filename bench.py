@@ -140,11 +140,19 @@ def cpu_oracle_rate(wl, sample_batch, steps, warmup):
     return sample_batch / med, med, torch.get_num_threads()
 
 
+def _cpu_sample(wl):
+    """Samples per CPU step: the full per-GPU batch on the 64x64 grids (about 10 s of CPU work for the whole
+    measurement on the GPU box's host cores), a bounded slice of it on the large grids."""
+    if wl["H"] * wl["W"] <= 64 * 64:
+        return wl["batch"]
+    return max(1, min(wl["batch"], 4 if wl["H"] * wl["W"] <= 128 * 128 else 2))
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    sample = max(1, min(wl["batch"], 8 if wl["H"] <= 64 else 1))
-    steps = max(1, min(args.steps, 5))
+    sample = _cpu_sample(wl)
+    steps = max(1, min(args.steps, 10))
     rate, med, cores = cpu_oracle_rate(wl, sample, steps, min(args.warmup, 2))
     line = {
         "impl": "reference", "metric": "FNO2D train samples/s (fwd+bwd)", "value": rate, "unit": "samples/s",
@@ -153,7 +161,7 @@ def run_reference(args, wl, rank, world):
         "config": {"workload": wl["desc"], "note": "reference path = oracle restatement (neuralop is not vendored "
                    "by the reference; parity unpinned) on host cores, bounded sample"},
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"batch {sample} of {wl['batch']}, fwd+MSE+bwd, median of {steps}"},
+                         "sample": f"batch {sample} of {wl['batch']}, fwd+MSE+bwd, median of {steps} steps"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -618,10 +626,11 @@ def run_b200(args, wl, rank, world, local_rank):
         cpu = None
         log('cpu baseline')
         if world == 1 and not args.skip_cpu:
-            sample = 8 if wl["H"] <= 64 else 1
-            rate, med, cores = cpu_oracle_rate(wl, sample, 5, 2)
+            sample = _cpu_sample(wl)
+            rate, med, cores = cpu_oracle_rate(wl, sample, 10, 2)
             cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": f"batch {sample} of {B}, fwd+MSE+bwd (no optimizer), median of 5, oracle restatement"}
+                   "sample": f"batch {sample} of {B}, fwd+MSE+bwd (no optimizer), median of 10 steps "
+                             f"({12 * med:.1f} s of CPU work), oracle restatement"}
         n_launch = launches_per_step
         line = {
             "metric": "FNO2D train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev, "unit": "samples/s",
