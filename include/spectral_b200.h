@@ -71,7 +71,8 @@ int sb200_plan_destroy(sb200_plan_t plan);
 
 /* ---- channels-first (FNO) stages -------------------------------------------------------
  * replaces torch.fft.rfftn + fftshift + slice (neuralop SpectralConv.forward) */
-/* x [rows, W] real  ->  T [rows, Mx] complex   (rows = B*C*H) */
+/* x [rows, W] real  ->  T [rows, Mx] complex   (rows = B*C*H).  With tc mode 1 / 3 and W a multiple of 32 (>= 64) this
+ * is a tcgen05 GEMM against the twiddle matrix (tc_rowdft.cu), else the fp32 FFMA kernel. */
 int sb200_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, void* stream);
 /* T [nimg, H, Mx] complex -> Xh [nimg, My, Mx] complex */
 int sb200_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, int64_t nimg, void* stream);
@@ -81,7 +82,9 @@ int sb200_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, i
 
 /* x [nimg, H, W] real -> Xh [nimg, My, Mx] complex: the two stages above in one call.  On small grids
  * (W in {32, 64}, H dividing 256) a single fused kernel keeps the row-transformed spectrum on chip and
- * `scratch` may be NULL; otherwise `scratch` must hold sb200_analysis_scratch(plan, nimg) floats.
+ * `scratch` may be NULL; otherwise `scratch` must hold sb200_analysis_scratch(plan, nimg) floats (16-byte aligned)
+ * and, for W and H multiples of 32 (>= 64) with 2*Mx, 2*My <= 64, both stages run as tcgen05 GEMMs with a planar
+ * transposed intermediate in `scratch` (layout private to the library).
  * replaces torch.fft.rfftn + fftshift + slice (pass 0) / the adjoint of irfftn (pass 1). */
 int64_t sb200_analysis_scratch(sb200_plan_t plan, int64_t nimg);
 int sb200_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream);
