@@ -121,3 +121,42 @@ def test_reference_wrappers_import_on_the_shim():
     t = mod.TFNO2DModule(n_modes=[12, 12], in_channels=1, hidden_channels=8, lifting_channels=16,
                          projection_channels=16, out_channels=1, n_layers=1, rank=0.5, context_size=2)
     assert "fno.fno_blocks.convs.weight.0.tensor" in t.state_dict()     # dense: the reference's own quirk
+
+
+def test_sequence_forward_is_the_reference_loop():
+    """sequence_forward == FNOModule.forward (src/nsbench/models/fno/fno.py:29-43): teacher forcing for the first
+    `teacher_forcing_steps` frames, closed loop afterwards, frames stacked on dim 1 (any callable model)."""
+    step = lambda x: 0.5 * x + 1.0
+    x = torch.randn(2, 7, 1, 4, 4)
+    for tf in (0, 1, 3, 7, 50):
+        outs, x_t = [], None
+        for t in range(x.shape[1]):                     # literal transcription of the reference loop
+            x_t = x[:, t] if t < tf else x_t
+            if x_t is None:                             # tf == 0: the reference would fail here too (x_t undefined)
+                break
+            x_t = step(x_t)
+            outs.append(x_t)
+        if tf == 0:
+            continue
+        want = torch.stack(outs, dim=1)
+        assert torch.equal(pkg.sequence_forward(step, x, teacher_forcing_steps=tf), want)
+
+
+def test_rollout_engine_has_no_cpu_path():
+    m = pkg.FNO(n_modes=(6, 6), hidden_channels=8, in_channels=1, out_channels=1, lifting_channels=16,
+                projection_channels=16, n_layers=2)
+    with pytest.raises(_lib.SpectralB200Error):
+        pkg.Rollout(m)(torch.randn(1, 1, 16, 16), 3)
+
+
+def test_bench_reads_traffic_from_the_committed_capture():
+    """bench.py fills roofline.traffic from profiles/: the file it names must exist and hold the kernels it looks up."""
+    import bench
+    for name, approx in (("analysis_fused", None), ("modes_gemm2", None), ("coldft_inv2", None),
+                         ("tc_pointwise_kernel<3, 1, 0>", None), ("tc_pointwise_kernel<3, 3, 0>", None),
+                         ("tc_wgrad_kernel<3, 0>", 8 * 64 * 64 * 64 * 64)):
+        t = bench._ncu_traffic(name, approx)
+        assert isinstance(t, int) and t > 0, name
+    # the skip-conv weight gradient reads g and x once each (2 x 67 MB), not the 336 MB of the projection-head launch
+    assert bench._ncu_traffic("tc_wgrad_kernel<3, 0>", 8 * 64 * 64 * 64 * 64) < 200e6
+    assert bench._cpu_sample(bench.WORKLOADS["cfg2"]) == 64 and bench._cpu_sample(bench.WORKLOADS["cfg3"]) == 2
