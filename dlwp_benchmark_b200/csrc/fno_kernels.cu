@@ -312,7 +312,8 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
     SB_REQUIRE(pass == 0 || pass == 1, "coldft_inv: pass must be 0 or 1");
     if (nimg <= 0) return 0;
     const int H = p->H, My = p->My, Mx = p->Mx;
-    if (My <= 32 && getenv("SB200_COLDFT_INV_V1") == nullptr) {
+    static const bool inv_v1 = getenv("SB200_COLDFT_INV_V1") != nullptr;          // experiments: first-generation kernel
+    if (My <= 32 && !inv_v1) {
         const float2* Y2 = reinterpret_cast<const float2*>(Yh);
         float2* P2 = reinterpret_cast<float2*>(Phi);
         cudaStream_t st = (cudaStream_t)stream;
@@ -577,7 +578,8 @@ extern "C" int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp, const 
     const float2* A2 = reinterpret_cast<const float2*>(A);
     const float2* B2 = reinterpret_cast<const float2*>(B);
     float2* O2 = reinterpret_cast<float2*>(out);
-    if (getenv("SB200_MODES_GEMM_V1") == nullptr) {
+    static const bool gemm_v1 = getenv("SB200_MODES_GEMM_V1") != nullptr;          // experiments: first-generation kernel
+    if (!gemm_v1) {
         dim3 grid((K + 3) / 4, pb, qb);
         sb_launch(modes_gemm2_kernel, grid, 256, 0, st, A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);
         SB_LAUNCH_CHECK();
