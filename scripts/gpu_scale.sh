@@ -4,7 +4,7 @@ O=gpurun_out; mkdir -p $O
 nvidia-smi -L | head -8
 timeout 300 python bench.py --gpus 1 --steps 30 --warmup 5 --skip-cpu --skip-roofline > $O/scale_n1.json 2> $O/scale_n1.err; cut -c1-260 $O/scale_n1.json
 for n in 2 8; do
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 30 --warmup 5 --skip-cpu --skip-roofline > $O/scale_n$n.json 2> $O/scale_n$n.err
+  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 30 --warmup 5 --skip-cpu --skip-roofline > $O/scale_n$n.json 2> $O/scale_n$n.err
   echo "n=$n rc=$?"; grep '^{"metric"' $O/scale_n$n.json | cut -c1-260; grep -i "capture failed\|error\|NVLS" $O/scale_n$n.err | head -5
 done
 python - <<PY
