@@ -114,30 +114,138 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle on host cores, bounded sample
 # ----------------------------------------------------------------------------------------
+def _oracle_step_fn(wl, sample_batch, device):
+    """One train step (fwd + MSE + bwd + Adam) of the oracle restatement of the reference path -- plain
+    torch.fft / einsum / conv2d, fp32 -- on ``device``.  Returns (step, sync)."""
+    import torch
+    from oracle import spectral_oracle as so
+    m = build_model(wl)
+    sd = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-3, **({"capturable": True} if device != "cpu" else {}))
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(sample_batch, wl["cin"], wl["H"], wl["W"], generator=g).to(device)
+    y = torch.randn(sample_batch, wl["cout"], wl["H"], wl["W"], generator=g).to(device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = so.fno_forward(sd, x, wl["n_modes"], wl["L"])
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        opt.step()
+        return loss
+    return step
+
+
 def cpu_oracle_rate(wl, sample_batch, steps, warmup):
-    """fwd + MSE + bwd of the oracle restatement (torch CPU, fp32, all host threads)."""
+    """fwd + MSE + bwd + Adam of the oracle restatement (torch CPU, fp32, all host threads); total time / steps."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = _oracle_step_fn(wl, sample_batch, "cpu")
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    per = (time.perf_counter() - t0) / steps
+    return sample_batch / per, per, torch.get_num_threads()
+
+
+def gpu_torch_rate(wl, batch, steps=10, warmup=3):
+    """COMPARISON ONLY (north_star: "cuFFT and torch.fft on the GPU are reported only as comparisons"): the same
+    oracle module -- torch.fft (cuFFT) + einsum + conv2d, fp32, TF32 off -- on this B200, eager and as a CUDA graph.
+    Nothing of this is on the product path."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {"what": "oracle restatement of the reference path (torch.fft/cuFFT + einsum + conv2d, fp32, allow_tf32=False) "
+                   "on the same GPU, fwd+MSE+bwd+Adam", "batch": batch}
+    try:
+        step = _oracle_step_fn(wl, batch, "cuda")
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / steps
+        t = timed(step)
+        out["eager"] = {"ms_per_step": t * 1e3, "samples_per_s": batch / t}
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            t = timed(g.replay)
+            out["cuda_graph"] = {"ms_per_step": t * 1e3, "samples_per_s": batch / t}
+            del g
+        except Exception as ex:  # noqa: BLE001
+            out["cuda_graph"] = {"error": repr(ex)[:200]}
+            torch.cuda.synchronize()
+    except Exception as ex:  # noqa: BLE001
+        out["error"] = repr(ex)[:200]
+    return out
+
+
+def cpu_rollout_rate(wl, n_ics=2, n_steps=3):
+    """cfg5 on the host cores: closed-loop rollout of the oracle FNO on a bounded sample (a few ICs x a few steps)."""
     import torch
     from oracle import spectral_oracle as so
     torch.set_num_threads(os.cpu_count() or 1)
     m = build_model(wl)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(sample_batch, wl["cin"], wl["H"], wl["W"], generator=g)
-    y = torch.randn(sample_batch, wl["cout"], wl["H"], wl["W"], generator=g)
-    times = []
-    for it in range(warmup + steps):
-        for v in sd.values():
-            v.grad = None
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x0 = torch.randn(n_ics, wl["cin"], wl["H"], wl["W"], generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        so.rollout(sd, x0, wl["n_modes"], wl["L"], 1)
         t0 = time.perf_counter()
-        out = so.fno_forward(sd, x, wl["n_modes"], wl["L"])
-        loss = torch.nn.functional.mse_loss(out, y)
-        loss.backward()
-        t1 = time.perf_counter()
-        if it >= warmup:
-            times.append(t1 - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return sample_batch / med, med, torch.get_num_threads()
+        so.rollout(sd, x0, wl["n_modes"], wl["L"], n_steps)
+        dt = time.perf_counter() - t0
+    return {"value": n_ics * n_steps / dt, "unit": "IC-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_ics} initial conditions x {n_steps} closed-loop steps of the oracle FNO ({dt:.1f} s of CPU work)"}
+
+
+def cpu_afno_rate(wl, steps=3):
+    """cfg4 on the host cores: fwd + MSE + bwd of a stack of AFNO2D filters, oracle/afno_oracle.py (pinned against the
+    reference class by tests/golden/afno2d_*.npz), full per-GPU batch."""
+    import torch
+    from oracle import afno_oracle as ao
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)
+    C, nb, bs = wl["embed"], wl["nb"], wl["embed"] // wl["nb"]
+    ps = [[(0.02 * torch.randn(*s, generator=g)).requires_grad_(True)
+           for s in ((2, nb, bs, bs), (2, nb, bs), (2, nb, bs, bs), (2, nb, bs))] for _ in range(wl["depth"])]
+    x = torch.randn(wl["batch"], wl["H"], wl["W"], C, generator=g)
+    y = torch.randn(wl["batch"], wl["H"], wl["W"], C, generator=g)
+
+    def step():
+        h = x
+        for w1, b1, w2, b2 in ps:
+            h = ao.afno2d_fft(h, w1, b1, w2, b2, nb)
+        torch.nn.functional.mse_loss(h, y).backward()
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": wl["batch"] / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"batch {wl['batch']}, {wl['depth']} AFNO2D filters fwd+MSE+bwd, {steps} steps after 1 warm-up "
+                      f"({(steps + 1) * dt:.1f} s of CPU work), oracle pinned to the reference class"}
+
+
+def _config(wl, world):
+    """The ``config`` object both arms print (identical keys and values: the driver compares them)."""
+    return {"workload": wl["desc"], "global_batch": wl["batch"] * world, "grid": [wl["H"], wl["W"]],
+            "parallelism": f"dp{world}", "step": "fwd+MSE+bwd+Adam" + ("+allreduce" if world > 1 else ""),
+            "l2": "per-step working set (activations of 4 layers + 256-ch lifting/projection, >1 GB) exceeds the 126 MB L2"}
 
 
 def _cpu_sample(wl):
@@ -152,16 +260,18 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     sample = _cpu_sample(wl)
-    steps = max(1, min(args.steps, 10))
-    rate, med, cores = cpu_oracle_rate(wl, sample, steps, min(args.warmup, 2))
+    steps, warmup = args.steps, args.warmup
+    rate, med, cores = cpu_oracle_rate(wl, sample, steps, warmup)
     line = {
         "impl": "reference", "metric": "FNO2D train samples/s (fwd+bwd)", "value": rate, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": med * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "reference path = oracle restatement (neuralop is not vendored "
-                   "by the reference; parity unpinned) on host cores, bounded sample"},
+        "config": _config(wl, world),
+        "note": "reference path = oracle restatement of neuralop@05c01c3 (not vendored by the reference, not "
+                "installable here: parity unpinned) on the box's host cores; rank 0 only, one GPU's batch per step",
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"batch {sample} of {wl['batch']}, fwd+MSE+bwd, median of {steps} steps"},
+                         "sample": f"batch {sample} of {wl['batch']} per step, fwd+MSE+bwd+Adam, {steps} steps after "
+                                   f"{warmup} warm-up"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,6 +315,31 @@ def kernel_rooflines(wl, peak_gbs, reps=10):
                                    tb + 8 * P + 4 * P),
         "pointwise_wgrad": (lambda: ops.pointwise_wgrad(g, x), 8 * P),
     }
+    # lifting (1 -> 256 -> C) and projection (C -> 256 -> 1) MLPs: SURVEY row f1, 256-channel hidden tensor on chip
+    LP = wl["lift"]
+    if wl["cin"] == 1 and wl["cout"] == 1 and LP == 256 and ops.lift_supported(C, LP, H * W) \
+            and ops.mlp_head_supported(C, LP, 1, H * W):
+        x1 = torch.randn(B, 1, H, W, device=dev)
+        g1 = torch.randn(B, 1, H, W, device=dev)
+        w1 = torch.randn(LP, device=dev) * 0.5
+        b1 = torch.randn(LP, device=dev) * 0.1
+        W2 = torch.randn(C, LP, device=dev) * 0.05
+        Wh = torch.randn(LP, C, device=dev) * 0.1
+        wo = torch.randn(LP, device=dev) * 0.05
+        bo = torch.zeros(1, device=dev)
+        P1 = B * H * W
+        gz1 = ops.mlp_head_bwd(x, Wh, b1, wo, g1)[0]
+        cases.update({
+            "lift_fwd": (lambda: ops.lift_fwd(x1, w1, b1, W2, bv), 4 * P1 + 4 * P),
+            "lift_wgrad": (lambda: ops.lift_wgrad(g, x1, w1, b1), 4 * P + 4 * P1),
+            "lift_tail_bwd": (lambda: ops.lift_tail_bwd(g, W2, w1, b1, x1), 4 * P + 4 * P1),
+            "mlp_head_fwd": (lambda: ops.mlp_head_fwd(x, Wh, b1, wo, bo), 4 * P + 4 * P1),
+            # the three kernels of the projection backward as they stand (gz1 [B,256,H,W] round-trips HBM):
+            "mlp_head_bwd(gz1 out)": (lambda: ops.mlp_head_bwd(x, Wh, b1, wo, g1), 4 * P + 4 * P1 + 4 * B * LP * H * W),
+            "head_dgrad(256->C)": (lambda: ops.rowidft_pointwise(plan, 1, None, gz1, Wh, 1, C, None, None, B, LP, C, 1,
+                                                                 False), 4 * B * LP * H * W + 4 * P),
+            "head_wgrad(256xC)": (lambda: ops.pointwise_wgrad(gz1, x, want_bias=False), 4 * B * LP * H * W + 4 * P),
+        })
     out = {}
     for name, (fn, nbytes) in cases.items():
         for _ in range(3):
@@ -223,15 +358,32 @@ def kernel_rooflines(wl, peak_gbs, reps=10):
 
 
 def _finish(world, graphs=()):
-    """End of a rank's work.  With N > 1 the process leaves through os._exit(0) instead of
-    dist.destroy_process_group(): tearing down an NCCL communicator that a CUDA graph captured blocks
-    (measured in session 5 at N = 2 and N = 8: every rank finished and rank 0 had printed its line, then all of
-    them sat in destroy_process_group until the launcher's timeout killed them).  Every collective of the run has
-    completed by the time a rank gets here and its output is flushed, so nothing is lost by not tearing down."""
+    """End of a rank's work: release the CUDA graphs that captured the NCCL communicator FIRST (destroying a
+    communicator that a live graph still references is what blocked in round 1), then a barrier and a normal
+    ``destroy_process_group()``.  A 45 s watchdog turns a teardown that still hangs into an exit instead of a burnt
+    GPU lease (it reports itself on stderr; every result has been printed and flushed by then)."""
     sys.stdout.flush()
     sys.stderr.flush()
-    if world > 1:
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    def _bail():
+        sys.stderr.write("[bench] destroy_process_group did not return within 45 s: leaving through os._exit\n")
+        sys.stderr.flush()
         os._exit(0)
+    wd = threading.Timer(45.0, _bail)
+    wd.daemon = True
+    wd.start()
+    torch.cuda.synchronize()
+    for g in graphs:
+        if g is not None:
+            g.reset()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    wd.cancel()
 
 
 def _peak():
@@ -245,10 +397,18 @@ def _peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_table_path(rel=False):
+    """newest committed per-kernel table of an `ncu --set full` capture of the cfg2 step (profiles/r*_cfg2_ncu_full*.json)"""
+    import glob
+    c = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_cfg2_ncu_full*.json")))
+    p = c[-1] if c else os.path.join(ROOT, "profiles", "r01_cfg2_ncu_full_s5f.json")
+    return os.path.relpath(p, ROOT) if rel else p
+
+
 def _ncu_traffic(kernel_substr, approx_read_bytes=None):
     """dram read+write bytes per launch of a kernel from the committed `ncu --set full` capture of this workload
     (profiles/r01_cfg2_ncu_full_s5f.json); None when the capture has no such kernel."""
-    path = os.path.join(ROOT, "profiles", "r01_cfg2_ncu_full_s5f.json")
+    path = _ncu_table_path()
     try:
         table = json.load(open(path))
     except Exception:
@@ -375,7 +535,7 @@ def run_afno(args, wl, rank, world, local_rank):
                              "achieved": alg / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / (t_dev / args.steps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "alg_bytes": alg, "note": "whole-step time over 20*P bytes per layer (includes Adam and the loss)"},
-                "cpu_baseline": None}
+                "cpu_baseline": cpu_afno_rate(wl) if (world == 1 and not args.skip_cpu) else None}
         print(json.dumps(line), flush=True)
     _finish(world, (graph,))
 
@@ -440,7 +600,7 @@ def run_rollout(args, wl, rank, world, local_rank):
                              "achieved": alg / per_model_step / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / per_model_step / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "alg_bytes": alg},
-                "cpu_baseline": None}
+                "cpu_baseline": cpu_rollout_rate(wl) if (world == 1 and not args.skip_cpu) else None}
         print(json.dumps(line), flush=True)
     _finish(world, (getattr(eng, "_graph", None),))
 
@@ -606,7 +766,7 @@ def run_b200(args, wl, rank, world, local_rank):
             L = wl["L"]
             per_step = {"analysis": 2 * L, "modes_gemm(mix_fwd)": 2 * L - 0,
                         "modes_gemm(wgrad)": L, "coldft_inv": 2 * L - 0, "rowidft_pointwise(fwd)": L,
-                        "rowidft_pointwise(bwd)": L - 1, "pointwise_wgrad": L}
+                        "rowidft_pointwise(bwd)": L, "pointwise_wgrad": L}            # every other entry: once per step
             share = {k: v["ms"] * per_step.get(k, 1) for k, v in kr.items()}
             top = max(share, key=share.get)
             ncu_name = {"analysis": ("analysis_fused", None), "modes_gemm(mix_fwd)": ("modes_gemm2", None),
@@ -614,33 +774,40 @@ def run_b200(args, wl, rank, world, local_rank):
                         "rowidft_pointwise(fwd)": ("tc_pointwise_kernel<3, 1, 0>", None),
                         "rowidft_pointwise(bwd)": ("tc_pointwise_kernel<3, 3, 0>", None),
                         "pointwise_wgrad": ("tc_wgrad_kernel<3, 0>", 8 * wl["batch"] * wl["hidden"] * wl["H"] * wl["W"])}
+            ncu_name.update({"lift_fwd": ("tc_pointwise_kernel<3, 0, 1>", None), "lift_wgrad": ("tc_wgrad_kernel<3, 1>", None),
+                             "lift_tail_bwd": ("tc_pointwise_kernel<3, 7, 0>", None),
+                             "mlp_head_fwd": ("tc_pointwise_kernel<3, 5, 0>", None),
+                             "mlp_head_bwd(gz1 out)": ("tc_pointwise_kernel<3, 6, 0>", None),
+                             "head_dgrad(256->C)": ("tc_pointwise_kernel<3, 4, 0>", None),
+                             "head_wgrad(256xC)": ("tc_wgrad_kernel<3, 0>", 4 * wl["batch"] * (wl["proj"] + wl["hidden"]) * wl["H"] * wl["W"])})
             traffic = _ncu_traffic(*ncu_name[top]) if args.workload == "cfg2" and top in ncu_name else None
             roof = {"bound": "hbm", "kernel": top, "achieved": kr[top]["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": kr[top]["frac"], "traffic": traffic,
-                    "traffic_source": "profiles/r01_cfg2_ncu_full_s5f.json (ncu --set full, same shapes)" if traffic else None,
+                    "traffic_source": (_ncu_table_path(rel=True) + " (ncu --set full, same shapes)") if traffic else None,
                     "peak_source": peak_src,
                     "kernel_ms": kr[top]["ms"], "alg_bytes": kr[top]["alg_bytes"],
                     "all": {k: {"ms": round(v["ms"], 4), "frac": round(v["frac"], 4)} for k, v in kr.items()}}
         except Exception as ex:  # the roofline block must never take the headline number down
             roof = {"bound": "hbm", "error": repr(ex)}
         cpu = None
-        log('cpu baseline')
+        gpu_cmp = None
         if world == 1 and not args.skip_cpu:
+            log('gpu torch.fft comparison')
+            gpu_cmp = gpu_torch_rate(wl, B)
+            log('cpu baseline')
             sample = _cpu_sample(wl)
             rate, med, cores = cpu_oracle_rate(wl, sample, 10, 2)
             cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": f"batch {sample} of {B}, fwd+MSE+bwd (no optimizer), median of 10 steps "
+                   "sample": f"batch {sample} of {B}, fwd+MSE+bwd+Adam, 10 steps after 2 warm-up "
                              f"({12 * med:.1f} s of CPU work), oracle restatement"}
         n_launch = launches_per_step
         line = {
             "metric": "FNO2D train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [wl["H"], wl["W"]],
-                       "parallelism": f"dp{world}", "step": "fwd+MSE+bwd+Adam(fused)" + ("+allreduce" if world > 1 else ""),
-                       "cuda_graph": bool(use_graph), "graph_scope": graph_mode,
-                       "tc_mode": int(lib.sb200_get_tc_mode()),
-                       "l2": "per-step working set (activations of 4 layers + 256-ch lifting/projection, >1 GB) exceeds the 126 MB L2"},
+            "config": _config(wl, world),
+            "run": {"cuda_graph": bool(use_graph), "graph_scope": graph_mode, "tc_mode": int(lib.sb200_get_tc_mode()),
+                    "optimizer": "Adam(fused, capturable)", "grad_sync": "GradSync(direct sinks, 1 AVG all-reduce)" if sync else None},
             "clocks": clocks,
             "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
                     "h2d_bytes_per_step": (hx.numel() + hy.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world,
@@ -648,6 +815,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "gpu_launches": n_launch * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_torch_baseline": gpu_cmp,
         }
         print(json.dumps(line), flush=True)
     _finish(world, (graph,))
@@ -656,7 +824,7 @@ def run_b200(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (b200 arm), 20 (reference arm)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -667,6 +835,8 @@ def main():
     ap.add_argument("--skip-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 20 if (args.impl == "reference" or args.workload in ("cfg3", "cfg5")) else 200
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

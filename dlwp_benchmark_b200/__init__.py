@@ -10,6 +10,6 @@ from .spectral_conv import SpectralConv  # noqa: F401
 from .fno import FNO, TFNO, FNOBlocks, MLP  # noqa: F401
 from .afno import AFNO2D  # noqa: F401
 from .shim import install_neuralop_shim, patch_fourcastnet  # noqa: F401
-from .rollout import Rollout, sequence_forward  # noqa: F401
+from .rollout import Rollout, sequence_forward, dlwp_sequence_forward, DLWPRollout  # noqa: F401
 
 __version__ = "0.1.0"

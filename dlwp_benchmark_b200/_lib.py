@@ -25,7 +25,6 @@ SIGNATURES = {
     "sb200_device_arch": (_i, []),
     "sb200_set_tc_mode": (_i, [_i]),
     "sb200_get_tc_mode": (_i, []),
-    "sb200_tc_selftest": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sb200_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _d, _d]),
     "sb200_plan_destroy": (_i, [_vp]),
     "sb200_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
@@ -59,6 +58,8 @@ SIGNATURES = {
     "sb200_afno_blocklinear_wgrad": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "sb200_gelu_fwd": (_i, [_vp, _vp, _i64, _vp]),
     "sb200_gelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "sb200_channel_sum_workspace": (_i64, [_i, _i]),
+    "sb200_channel_sum": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
 }
 
 
@@ -85,6 +86,24 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def on_tensor_device(fn):
+    """Decorator for ``autograd.Function.forward/backward``: run with the CUDA device of the first CUDA tensor
+    argument current, so that ``torch.cuda.current_stream()``, the plan cache, workspaces allocated with
+    ``torch.empty`` and the library's per-device lookups all refer to the tensor's device even when the caller's
+    current device is another one (the backward runs on an autograd engine thread)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        import torch
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapper
 
 
 def check(rc: int, what: str = ""):

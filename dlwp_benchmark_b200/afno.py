@@ -37,6 +37,10 @@ class AFNO2D(nn.Module):
             raise _lib.SpectralB200Error("AFNO2D (B200) got a CPU tensor: there is no CPU / torch.fft path")
         from .afno_fn import AFNO2DFn
         dtype = x.dtype
+        fp32_in = dtype == torch.float32
+        # fp32 input (every shipped config): the residual add is fused into the row-synthesis kernel.  Other dtypes:
+        # the reference casts the filter output first and adds the residual in the input dtype
+        # (fourcastnet.py:124-126) -- same order here, so the rounding is the reference's.
         y = AFNO2DFn.apply(x.float(), self.w1, self.b1, self.w2, self.b2, self.num_blocks,
-                           float(self.sparsity_threshold), float(self.hard_thresholding_fraction))
-        return y.type(dtype)
+                           float(self.sparsity_threshold), float(self.hard_thresholding_fraction), fp32_in)
+        return y if fp32_in else y.type(dtype) + x

@@ -43,7 +43,8 @@ def _bl_wgrad(a, gout, fwd_out, kind, ntok, nb, Ni, No):
 
 class AFNO2DFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, num_blocks, lam, frac):
+    @_lib.on_tensor_device
+    def forward(ctx, x, w1, b1, w2, b2, num_blocks, lam, frac, add_residual=True):
         _req(x.contiguous(), "x")
         x = x.contiguous()
         B, h, w, C = x.shape
@@ -64,13 +65,15 @@ class AFNO2DFn(torch.autograd.Function):
         Phi = torch.empty(B, h, Mx, C, 2, device=x.device, dtype=torch.float32)
         _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 0, _p(Yh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
         y = torch.empty_like(x)
-        _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 0, _p(Phi), _p(x), _p(y), B * h, C, _stream()),
-                   "cl_rowidft_res")
+        _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 0, _p(Phi), _p(x) if add_residual else None, _p(y), B * h, C,
+                                            _stream()), "cl_rowidft_res")
+        ctx.add_residual = bool(add_residual)
         ctx.plan, ctx.dims = plan, (B, h, w, C, nb, bs, bsf, ntok)
         ctx.save_for_backward(Xh, O1, Yh, w1c, w2c)
         return y
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, gy):
         Xh, O1, Yh, w1c, w2c = ctx.saved_tensors
         plan = ctx.plan
@@ -92,6 +95,6 @@ class AFNO2DFn(torch.autograd.Function):
             Phi = torch.empty(B, h, Mx, C, 2, device=dev, dtype=torch.float32)
             _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 1, _p(gXh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
             gx = torch.empty_like(gy)
-            _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 1, _p(Phi), _p(gy), _p(gx), B * h, C, _stream()),
-                       "cl_rowidft_res")
-        return gx, gw1, gb1, gw2, gb2, None, None, None
+            _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 1, _p(Phi), _p(gy) if ctx.add_residual else None, _p(gx),
+                                                B * h, C, _stream()), "cl_rowidft_res")
+        return gx, gw1, gb1, gw2, gb2, None, None, None, None

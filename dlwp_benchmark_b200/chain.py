@@ -33,17 +33,20 @@ SMALL_W = 16   # channel counts handled by the small weight-gradient kernel
 
 class FusedChainFn(torch.autograd.Function):
     """args: x, n_modes_halved, spec (tuple of bool per layer: has a spectral branch),
-    acts (tuple of bool per layer), then per layer (Wspec_l or None, Wp_l, b_l or None)."""
+    acts (tuple of bool per layer), grad_mode (``torch.is_grad_enabled()`` of the caller: inside ``forward`` autograd
+    has already switched it off, and ``needs_input_grad`` stays True under ``no_grad``), then per layer
+    (Wspec_l or None, Wp_l, b_l or None)."""
 
     @staticmethod
-    def forward(ctx, x, n_modes_halved, spec, acts, *params):
+    @_lib.on_tensor_device
+    def forward(ctx, x, n_modes_halved, spec, acts, grad_mode, *params):
         if not x.is_cuda:
             raise _lib.SpectralB200Error("FNO(B200) got a CPU tensor: there is no CPU / torch.fft path")
         x = x.contiguous().float()
         B, _, H, Wd = x.shape
         nl = len(spec)
         plan = fno_plan(x.device, H, Wd, n_modes_halved)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         Ws, Ps, bs = [], [], []
         for l in range(nl):
             w, p, b = params[3 * l:3 * l + 3]
@@ -97,7 +100,13 @@ class FusedChainFn(torch.autograd.Function):
                                              want_z=want_z)
             hs.append(h); Xhs.append(Xh); zs.append(z)
             h = y
+            if not need_grad:
+                hs.clear(); Xhs.clear(); zs.clear()         # inference: nothing is kept alive past its consumer
+        if not need_grad:
+            return h
         ctx.plan, ctx.nl, ctx.spec, ctx.acts = plan, nl, tuple(spec), tuple(acts)
+        # direct gradient destinations (ddp.GradSync(direct=True)): written by the backward kernels themselves
+        ctx.sinks = [ops.grad_sink(t) for t in params]
         ctx.shapes = [(params[3 * l + 1].shape, params[3 * l + 2].shape if params[3 * l + 2] is not None else None)
                       for l in range(nl)]
         ctx.has_h = [t is not None for t in hs]
@@ -108,6 +117,7 @@ class FusedChainFn(torch.autograd.Function):
         return h
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, gy):
         nl, spec, acts, plan = ctx.nl, ctx.spec, ctx.acts, ctx.plan
         sv = list(ctx.saved_tensors)
@@ -124,47 +134,55 @@ class FusedChainFn(torch.autograd.Function):
         if acts[nl - 1]:
             gz = ops.gelu_bwd(gz, zs[nl - 1])
         grads: List[Optional[torch.Tensor]] = [None] * (3 * nl)
+        sinks = ctx.sinks
+
+        def put(idx, t, shape):
+            """hand gradient ``t`` of parameter slot ``idx`` to autograd -- unless the kernel wrote it into its sink"""
+            if t is not None and sinks[idx] is None:
+                grads[idx] = t.reshape(shape)
+
         gx = None
         top = nl - 1
-        bias_known = None
+        bias_known = False
         if ctx.head:
             # stage 1 of the fused head backward: z1 recomputed on the tensor cores; gz1 = w2 gy gelu'(z1) and the
             # reductions for b1, w2, b2 come out of one kernel
-            l1 = nl - 2
-            gz, gb1, gw2, gb2 = ops.mlp_head_bwd(hs[l1], Ps[l1], head_b1, Ps[nl - 1].reshape(-1), gz,
-                                                 want_gb2=ctx.shapes[nl - 1][1] is not None)
-            grads[3 * (nl - 1) + 1] = gw2.reshape(ctx.shapes[nl - 1][0])
-            if gb2 is not None:
-                grads[3 * (nl - 1) + 2] = gb2.reshape(ctx.shapes[nl - 1][1])
-            bias_known = gb1
+            l1, l2 = nl - 2, nl - 1
+            gz, gb1, gw2, gb2 = ops.mlp_head_bwd(hs[l1], Ps[l1], head_b1, Ps[l2].reshape(-1), gz,
+                                                 want_gb2=ctx.shapes[l2][1] is not None, out_gb1=sinks[3 * l1 + 2],
+                                                 out_gw2=sinks[3 * l2 + 1], out_gb2=sinks[3 * l2 + 2])
+            put(3 * l2 + 1, gw2, ctx.shapes[l2][0])
+            put(3 * l2 + 2, gb2, ctx.shapes[l2][1])
+            put(3 * l1 + 2, gb1, ctx.shapes[l1][1])
+            bias_known = True
             top = l1
         for l in range(top, -1, -1):
             N, M = Ps[l].shape
-            has_b = ctx.shapes[l][1] is not None
-            if bias_known is not None and l == top:
-                grads[3 * l + 2] = bias_known.reshape(ctx.shapes[l][1])
-                has_b = False
+            has_b = ctx.shapes[l][1] is not None and not (bias_known and l == top)
+            sw, sb = sinks[3 * l + 1], (sinks[3 * l + 2] if has_b else None)
             # ---- weight gradients ----
             if ctx.lift_gen and l == 1:
-                gP, gb = ops.lift_wgrad(gz, hs[0], Ps[0].reshape(-1), lift_b1, want_bias=has_b)
+                gP, gb = ops.lift_wgrad(gz, hs[0], Ps[0].reshape(-1), lift_b1, want_bias=has_b, out_w=sw, out_b=sb)
             elif N <= SMALL_W and N <= M:
-                gP, gb, _ = ops.wgrad_small(gz, hs[l], False, has_b, False)
+                gP, gb, _ = ops.wgrad_small(gz, hs[l], False, has_b, False, out_dot=sw, out_small=sb)
             elif M <= SMALL_W:
-                gP, _, gb = ops.wgrad_small(hs[l], gz, True, False, has_b)
+                gP, _, gb = ops.wgrad_small(hs[l], gz, True, False, has_b, out_dot=sw, out_big=sb)
             else:
-                gP, gb = ops.pointwise_wgrad(gz, hs[l], want_bias=has_b)
-            grads[3 * l + 1] = gP.reshape(ctx.shapes[l][0])
+                gP, gb = ops.pointwise_wgrad(gz, hs[l], want_bias=has_b, out_w=sw, out_b=sb)
+            put(3 * l + 1, gP, ctx.shapes[l][0])
             if has_b:
-                grads[3 * l + 2] = gb.reshape(ctx.shapes[l][1])
+                put(3 * l + 2, gb, ctx.shapes[l][1])
             gYh = None
             if spec[l]:
                 gYh = ops.analysis(plan, 1, gz)
-                grads[3 * l] = ops.mix_bwd_weight(Xhs[l], gYh)
+                gW = ops.mix_bwd_weight(Xhs[l], gYh, out=sinks[3 * l])
+                put(3 * l, gW, gW.shape)
             if ctx.lift_tail and l == 1:
                 # gz_0 = (P_1^T gz) gelu'(w1 x + b1) stays on chip; only its two pixel reductions leave
-                gw1, gb1 = ops.lift_tail_bwd(gz, Ps[1], Ps[0].reshape(-1), lift_b1, hs[0])
-                grads[1] = gw1.reshape(ctx.shapes[0][0])
-                grads[2] = gb1.reshape(ctx.shapes[0][1])
+                gw1, gb1 = ops.lift_tail_bwd(gz, Ps[1], Ps[0].reshape(-1), lift_b1, hs[0], out_gw1=sinks[1],
+                                             out_gb1=sinks[2])
+                put(1, gw1, ctx.shapes[0][0])
+                put(2, gb1, ctx.shapes[0][1])
                 break
             # ---- data gradient (fused with GELU' of the previous layer) ----
             if l > 0 or ctx.needs_input_grad[0]:
@@ -175,4 +193,4 @@ class FusedChainFn(torch.autograd.Function):
                     gz = gprev
                 else:
                     gx = gprev
-        return (gx, None, None, None, *grads)
+        return (gx, None, None, None, None, *grads)

@@ -225,7 +225,6 @@ analysis_fused_kernel(const __grid_constant__ CUtensorMap tmapX, const AfParams 
     }
 }
 
-static int g_af_sms = 0;
 
 static size_t af_smem_bytes(const sb200_plan_s* p, int nxb, int ntb) {
     const int Myp = (p->My + 3) & ~3;
@@ -239,7 +238,7 @@ static size_t af_smem_bytes(const sb200_plan_s* p, int nxb, int ntb) {
 // FFMA stages, not by bytes in flight, so the second T slot is worth more than a third x buffer.
 // SB200_AF_RING=<nxb><ntb> overrides (experiments).
 static void af_ring(const sb200_plan_s* p, int* nxb, int* ntb) {
-    static const int env = getenv("SB200_AF_RING") ? atoi(getenv("SB200_AF_RING")) : 0;
+    static const int env = sb_env_int("SB200_AF_RING", 0);
     if (env >= 11 && env / 10 <= 4 && env % 10 >= 1 && env % 10 <= 2 && af_smem_bytes(p, env / 10, env % 10) <= 227 * 1024) {
         *nxb = env / 10; *ntb = env % 10;
         return;
@@ -278,12 +277,8 @@ int sb200_analysis_fused(sb200_plan_t plan, int pass, const float* x, float* Xh,
     const size_t smem = af_smem_bytes(plan, p.nxb, p.ntb);
     CUtensorMap tmap;
     if (int rc = sb200_make_tmap_2d_f32(&tmap, x, (uint64_t)W, (uint64_t)rows, (uint64_t)W * 4, 32, AF_ROWS, 1)) return rc;
-    if (g_af_sms == 0) {
-        int dev = 0;
-        SB_CHECK_CUDA(cudaGetDevice(&dev));
-        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_af_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const unsigned grid = (unsigned)(p.ngroups < g_af_sms ? p.ngroups : g_af_sms);
+    const int nsm = sb200_num_sms();
+    const unsigned grid = (unsigned)(p.ngroups < nsm ? p.ngroups : nsm);
 #define AF_LAUNCH(MXV)                                                                                                  \
     case MXV:                                                                                                           \
         SB_CHECK_CUDA(cudaFuncSetAttribute(analysis_fused_kernel<MXV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \

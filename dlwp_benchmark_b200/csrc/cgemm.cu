@@ -343,7 +343,7 @@ extern "C" int sb200_cgemm_grouped(const sb200_cgemm_desc* d, int ngroups, const
     p.conjA = d->conjA; p.conjB = d->conjB;
     p.a_kfast = (d->sAk2 == 1 && d->sAm2 != 1) ? 1 : 0;
     p.b_kfast = (d->sBk2 == 1 && d->sBn != 1) ? 1 : 0;
-    static const bool skinny_off = getenv("SB200_CGEMM_NOSKINNY") != nullptr;     // experiments: tiled kernel for every shape
+    static const bool skinny_off = sb_env_flag("SB200_CGEMM_NOSKINNY");     // experiments: tiled kernel for every shape
     const bool skinny = d->N <= 32 && d->K <= CS_MAXK && d->K2 == 1 && d->M >= 2048 && !skinny_off;
     p.splits = skinny ? 1 : cg_splits(d, ngroups, &p.kchunk);
     if (skinny) p.kchunk = d->K;

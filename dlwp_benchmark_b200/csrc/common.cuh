@@ -65,6 +65,23 @@ extern unsigned long long g_sb200_launches;
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// SM count of the CURRENT device (per-device cache; the library is used from one process per GPU, but nothing
+// stops a caller from driving several devices from one process).  Defined in plan.cu.
+int sb200_num_sms();
+
+// Experiment switches are compiled out of the shipped library: they exist only in bring-up builds
+// (make BRINGUP=1 -> -DSB200_BRINGUP); a production build always takes the default.
+static inline int sb_env_int(const char* name, int dflt) {
+#ifdef SB200_BRINGUP
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+static inline bool sb_env_flag(const char* name) { return sb_env_int(name, 0) != 0; }
+
 // Every kernel of the library is launched through sb_launch() (one place to add launch attributes).
 // Programmatic dependent launch was tried here (session 5) and removed: the kernels read their inputs through the
 // non-coherent path (__ldg / const __restrict__ -> LDG.E.CONSTANT), which is only legal for data that is read-only for

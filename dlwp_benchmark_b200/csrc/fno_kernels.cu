@@ -312,7 +312,7 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
     SB_REQUIRE(pass == 0 || pass == 1, "coldft_inv: pass must be 0 or 1");
     if (nimg <= 0) return 0;
     const int H = p->H, My = p->My, Mx = p->Mx;
-    static const bool inv_v1 = getenv("SB200_COLDFT_INV_V1") != nullptr;          // experiments: first-generation kernel
+    static const bool inv_v1 = sb_env_flag("SB200_COLDFT_INV_V1");          // experiments: first-generation kernel
     if (My <= 32 && !inv_v1) {
         const float2* Y2 = reinterpret_cast<const float2*>(Yh);
         float2* P2 = reinterpret_cast<float2*>(Phi);
@@ -346,13 +346,10 @@ int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, in
                       int* handled);   // tc_rowdft.cu
 
 // which path serves grids that both the fused FFMA kernel and the tensor-core two-stage path cover
-// (SB200_ANALYSIS_PREFER=tc|fused; experiments)
+// (SB200_ANALYSIS_PREFER_TC=1; bring-up builds only)
 static bool analysis_prefers_tc() {
-    static const int v = []() {
-        const char* e = getenv("SB200_ANALYSIS_PREFER");
-        return (e && e[0] == 't') ? 1 : 0;
-    }();
-    return v != 0;
+    static const bool v = sb_env_flag("SB200_ANALYSIS_PREFER_TC");
+    return v;
 }
 
 extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
@@ -578,7 +575,7 @@ extern "C" int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp, const 
     const float2* A2 = reinterpret_cast<const float2*>(A);
     const float2* B2 = reinterpret_cast<const float2*>(B);
     float2* O2 = reinterpret_cast<float2*>(out);
-    static const bool gemm_v1 = getenv("SB200_MODES_GEMM_V1") != nullptr;          // experiments: first-generation kernel
+    static const bool gemm_v1 = sb_env_flag("SB200_MODES_GEMM_V1");          // experiments: first-generation kernel
     if (!gemm_v1) {
         dim3 grid((K + 3) / 4, pb, qb);
         sb_launch(modes_gemm2_kernel, grid, 256, 0, st, A2, sAr, sAp, B2, sBr, sBq, O2, sOp, sOq, P, Q, R, K, conjA, conjB);

@@ -37,6 +37,27 @@ extern "C" int sb200_device_arch(void) {
     return p.major * 10 + p.minor;
 }
 
+// SM count of the current device, cached per device ordinal
+int sb200_num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 148;
+    }
+    if (dev >= 0 && dev < 64) {
+        const int c = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;
+    }
+    if (dev >= 0 && dev < 64) __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
+    return n;
+}
+
 static double hermitian_weight(int kx, int W) {
     if (kx == 0) return 1.0;
     if ((W % 2 == 0) && kx == W / 2) return 1.0;

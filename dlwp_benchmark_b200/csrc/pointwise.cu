@@ -663,3 +663,42 @@ extern "C" int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_
     SB_LAUNCH_CHECK();
     return 0;
 }
+
+// ======================================================================================
+// channel sums  out[c] = sum_{b,p} g[b,c,p]  (bias gradient of a SpectralConv used without a skip conv).
+// Deterministic: one block per (b, c) image, fixed-order tree, then a fixed-order sum over b.
+// ======================================================================================
+__global__ void __launch_bounds__(256) channel_sum_partial_kernel(const float* __restrict__ g, float* __restrict__ part,
+                                                                  int64_t HW) {
+    const float* src = g + (int64_t)blockIdx.x * HW;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < HW; i += 256) s += __ldg(src + i);
+    __shared__ float red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) channel_sum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                                 int B, int C) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += part[(int64_t)b * C + c];
+    out[c] = s;
+}
+extern "C" int64_t sb200_channel_sum_workspace(int B, int C) { return (int64_t)B * C; }
+extern "C" int sb200_channel_sum(const float* g, float* out, int B, int C, int64_t HW, float* workspace, void* stream) {
+    SB_REQUIRE(g && out && workspace, "channel_sum: NULL argument");
+    SB_REQUIRE(B > 0 && C > 0 && HW > 0, "channel_sum: non-positive size");
+    SB_REQUIRE((int64_t)B * C < (1LL << 31), "channel_sum: B*C too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    sb_launch(channel_sum_partial_kernel, (unsigned)(B * C), 256, 0, st, g, workspace, HW);
+    SB_LAUNCH_CHECK();
+    sb_launch(channel_sum_reduce_kernel, (unsigned)((C + 255) / 256), 256, 0, st, (const float*)workspace, out, B, C);
+    SB_LAUNCH_CHECK();
+    return 0;
+}

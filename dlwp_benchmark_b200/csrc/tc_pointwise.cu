@@ -56,13 +56,16 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
     return 0;
 }
 
-static int g_tc_mode = 3;   // 0 = CUDA-core kernels only, 1 = TF32 single pass, 3 = 3xTF32 (fp32 parity)
+// Precision mode of the tensor-core kernels: a process-wide DEFAULT (atomic), read once at the top of every entry
+// point.  0 = CUDA-core kernels only, 1 = TF32 single pass, 3 = 3xTF32 (fp32 parity).
+static int g_tc_mode_default = 3;
 extern "C" int sb200_set_tc_mode(int mode) {
     SB_REQUIRE(mode == 0 || mode == 1 || mode == 3, "set_tc_mode: mode must be 0, 1 or 3");
-    g_tc_mode = mode;
+    __atomic_store_n(&g_tc_mode_default, mode, __ATOMIC_RELAXED);
     return 0;
 }
-extern "C" int sb200_get_tc_mode(void) { return g_tc_mode; }
+extern "C" int sb200_get_tc_mode(void) { return __atomic_load_n(&g_tc_mode_default, __ATOMIC_RELAXED); }
+#define g_tc_mode (sb200_get_tc_mode())
 
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent, warp-specialised
@@ -775,7 +778,6 @@ __global__ void __launch_bounds__(256) head_colsum_reduce_kernel(const float* __
 // ---------------------------------------------------------------------------------------------
 // dispatch (called from sb200_rowidft_pointwise)
 // ---------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
 
 int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, cudaStream_t st, int* handled) {
     *handled = 0;
@@ -818,9 +820,8 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     const size_t phi_bytes = has_spec ? ((((size_t)(p.K2pad / 8) * N * 32 + 1023) & ~(size_t)1023) * mult * 2) : 0;
     const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512 + 1024 + 2048;   // + barriers, bias_s, rot_s
     int stages = has_pw ? 6 : 1;
-    static const size_t ring_budget = []() {                       // bytes the ring may grow to (SB200_TP_SMEM_KB: experiments)
-        const char* e = getenv("SB200_TP_SMEM_KB");
-        const int kb = e ? atoi(e) : 0;
+    static const size_t ring_budget = []() {                       // bytes the ring may grow to (SB200_TP_SMEM_KB: bring-up builds)
+        const int kb = sb_env_int("SB200_TP_SMEM_KB", 0);
         return (size_t)((kb >= 64 && kb <= 227) ? kb : 224) * 1024;
     }();
     while (stages > 2 && fixed + stages * a_stage > ring_budget) --stages;
@@ -836,11 +837,7 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     if (has_pw)
         if (int rc = sb200_make_tmap_2d_f32(&tmap, q.A, (uint64_t)HW, (uint64_t)q.B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2))
             return rc;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        SB_CHECK_CUDA(cudaGetDevice(&dev));
-        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = sb200_num_sms();
     const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
     int tl = 0;
     while ((1 << (tl + 1)) * N <= TP_WTHREADS) ++tl;
@@ -904,11 +901,7 @@ static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn
     const size_t smem = fixed + stages * a_stage;
     CUtensorMap tmap;
     if (int rc = sb200_make_tmap_2d_f32(&tmap, h, (uint64_t)HW, (uint64_t)B * M, (uint64_t)HW * 4, 32, (uint32_t)p.KC, 2)) return rc;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        SB_CHECK_CUDA(cudaGetDevice(&dev));
-        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int g_num_sms = sb200_num_sms();
     const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
     *grid_out = grid;
     int tl = 0;
@@ -929,13 +922,7 @@ static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn
 }
 
 static int tp_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            return 148;
-    }
-    return g_num_sms;
+    return sb200_num_sms();
 }
 
 extern "C" int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const float* w2, const float* b2,

@@ -255,8 +255,6 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
     if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-int g_tr_sms = 0;
-
 }  // namespace
 
 // geometry both stages need: K chunks of 32 fp32, twiddle operand + at least a 2-stage ring inside 227 KB
@@ -294,12 +292,8 @@ static int tr_launch(const float* in, const float2* tab, float* out, int64_t row
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (int rc = sb200_make_tmap_2d_f32(&tmap, in, (uint64_t)K, (uint64_t)rows, (uint64_t)K * 4, 32, TR_ROWS, 1)) return rc;
-    if (g_tr_sms == 0) {
-        int dev = 0;
-        SB_CHECK_CUDA(cudaGetDevice(&dev));
-        SB_CHECK_CUDA(cudaDeviceGetAttribute(&g_tr_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const unsigned grid = p.ntiles < (uint32_t)g_tr_sms ? p.ntiles : (unsigned)g_tr_sms;
+    const unsigned nsm = (unsigned)sb200_num_sms();
+    const unsigned grid = p.ntiles < nsm ? p.ntiles : nsm;
     if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_rowdft_kernel<3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sb_launch(tc_rowdft_kernel<3, MODE>, grid, TR_THREADS, smem, st, tmap, p);
@@ -312,7 +306,7 @@ static int tr_launch(const float* in, const float2* tab, float* out, int64_t row
 }
 
 static bool tr_enabled() {
-    static const bool disabled = getenv("SB200_TC_ROWDFT_OFF") != nullptr;      // experiments: force the FFMA kernels
+    static const bool disabled = sb_env_flag("SB200_TC_ROWDFT_OFF");      // experiments: force the FFMA kernels
     return !disabled && sb200_get_tc_mode() != 0;
 }
 
@@ -339,7 +333,7 @@ int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, in
                       int* handled) {
     *handled = 0;
     if (!tr_enabled() || scratch == nullptr) return 0;
-    static const bool col_off = getenv("SB200_TC_COLDFT_OFF") != nullptr;       // experiments: tensor-core row stage only
+    static const bool col_off = sb_env_flag("SB200_TC_COLDFT_OFF");       // experiments: tensor-core row stage only
     if (col_off) return 0;
     const int passes = sb200_get_tc_mode();
     const int H = plan->H, W = plan->W, Mx = plan->Mx, My = plan->My;

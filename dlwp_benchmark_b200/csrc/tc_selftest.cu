@@ -1,3 +1,4 @@
+// Bring-up scaffold: built only with `make BRINGUP=1` (not part of the shipped library or of include/spectral_b200.h).
 // Self-test of the tcgen05 building blocks (descriptor conventions), used by tests/ and when
 // bringing up a new operand layout.  D[128, N] = A[128, K] * B[N, K]^T with selectable smem layouts.
 #include "common.cuh"

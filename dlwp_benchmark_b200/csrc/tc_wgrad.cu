@@ -310,17 +310,7 @@ channel_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out
     out[c] = s;
 }
 
-static int g_tw_sms = 0;
-static int tw_num_sms() {
-    if (g_tw_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_tw_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-            cudaGetLastError();
-            g_tw_sms = 148;
-        }
-    }
-    return g_tw_sms;
-}
+static int tw_num_sms() { return sb200_num_sms(); }
 
 // shape eligibility + geometry, shared by the workspace query and the launcher
 static bool tw_geometry(int Cout, int Cin, int64_t HW, int* Pc, int* Qc, int* transpose) {
@@ -364,9 +354,9 @@ static int tw_launch(const float* g, const float* x, float* gW, float* gbias, in
     const bool bias_mma = passes == 3 && gbias != nullptr && tr == 0 && Qc + 16 <= 256 && p.mblocks * (Qc + 16) <= 512;
     p.Qn = bias_mma ? Qc + 16 : Qc;
     const size_t chunk = (size_t)(Pc + p.Qn) * 128;
-    static const int env_ch = getenv("SB200_WG_CH") ? atoi(getenv("SB200_WG_CH")) : 0;
-    static const int env_st = getenv("SB200_WG_STAGES") ? atoi(getenv("SB200_WG_STAGES")) : 0;
-    static const int env_dbg = getenv("SB200_WG_DEBUG") ? atoi(getenv("SB200_WG_DEBUG")) : 0;
+    static const int env_ch = sb_env_int("SB200_WG_CH", 0);       // bring-up builds only (compiled out otherwise)
+    static const int env_st = sb_env_int("SB200_WG_STAGES", 0);
+    static const int env_dbg = sb_env_int("SB200_WG_DEBUG", 0);
     p.debug = env_dbg;
     p.CH = env_ch > 0 ? env_ch : 1;
     const size_t stage = chunk * p.CH * (passes == 3 ? 2 : 1);

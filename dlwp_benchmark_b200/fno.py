@@ -12,8 +12,9 @@ state_dict keys:
   fno_blocks.fno_skips.{l}.weight            [C,C,1,1]
   projection.fcs.{0,1}.{weight,bias}
 
-The FNO blocks run through ``FNOStackFn`` (hand-written sm_100a kernels).  Lifting / projection
-are SURVEY.md row (f1) ("next"): they are 1x1-conv MLPs evaluated with torch ops in fp32.
+``FNO.forward`` runs lifting MLP + FNO blocks + projection MLP as ONE autograd node (``FusedChainFn``) whose
+forward / backward are sequences of C-ABI kernel launches; a stand-alone ``MLP`` / ``FNOBlocks`` call goes
+through the same kernels.  No torch.matmul / cuBLAS / cuFFT sits on any of these paths.
 """
 from __future__ import annotations
 
@@ -29,15 +30,14 @@ from .spectral_conv import SpectralConv as _SpectralConv, FNOBlockFn, FNOStackFn
 from .chain import FusedChainFn
 
 
-def _conv1x1_fp32(x, conv: nn.Conv2d):
-    """1x1 Conv2d evaluated as an fp32 matmul (cuDNN would silently use TF32 for the conv and
-    its backward, which breaks the 1e-5 parity bar; fp32 matmul keeps full precision)."""
-    B, Ci, H, W = x.shape
-    w = conv.weight.reshape(conv.out_channels, Ci)
-    y = torch.matmul(w, x.reshape(B, Ci, H * W))
-    if conv.bias is not None:
-        y = y + conv.bias.reshape(1, -1, 1)
-    return y.reshape(B, conv.out_channels, H, W)
+def _check_grid(x):
+    if not x.is_cuda:
+        raise _lib.SpectralB200Error("FNO(B200) got a CPU tensor: there is no CPU / torch.fft path")
+    if x.dim() != 4 or x.shape[-1] % 4 != 0 or x.shape[-2] % 2 != 0:
+        raise _lib.SpectralB200Error(
+            f"FNO(B200): input {tuple(x.shape)} -- need [B,C,H,W] with W a multiple of 4 (16-byte vector stores) and "
+            "H even (the reference's double-fftshift quirk for odd H is not reproduced); every grid the reference "
+            "uses (64, 128, 256, 32x64) qualifies")
 
 
 class MLP(nn.Module):
@@ -52,8 +52,12 @@ class MLP(nn.Module):
         self.in_channels = in_channels
         self.out_channels = in_channels if out_channels is None else out_channels
         self.hidden_channels = in_channels if hidden_channels is None else hidden_channels
+        if non_linearity is not F.gelu:
+            raise NotImplementedError("MLP(B200): only non_linearity=F.gelu is implemented (fused epilogue)")
+        if dropout:
+            raise NotImplementedError("MLP(B200): dropout is not implemented (the reference never sets it)")
         self.non_linearity = non_linearity
-        self.dropout = nn.ModuleList([nn.Dropout(dropout) for _ in range(n_layers)]) if dropout > 0.0 else None
+        self.dropout = None
         self.fcs = nn.ModuleList()
         for i in range(n_layers):
             if i == 0 and i == n_layers - 1:
@@ -66,13 +70,14 @@ class MLP(nn.Module):
                 self.fcs.append(nn.Conv2d(self.hidden_channels, self.hidden_channels, 1))
 
     def forward(self, x):
-        for i, fc in enumerate(self.fcs):
-            x = _conv1x1_fp32(x, fc)
-            if i < self.n_layers - 1:
-                x = self.non_linearity(x)
-            if self.dropout is not None:
-                x = self.dropout[i](x)
-        return x
+        """The 1x1-conv stack as a chain of pointwise C-ABI launches (FusedChainFn without spectral branches)."""
+        _check_grid(x)
+        n = len(self.fcs)
+        params = []
+        for fc in self.fcs:
+            params += [None, fc.weight, fc.bias]
+        return FusedChainFn.apply(x, (2, 2), (False,) * n, tuple(i < n - 1 for i in range(n)),
+                                  torch.is_grad_enabled(), *params)
 
 
 class FNOBlocks(nn.Module):
@@ -124,7 +129,8 @@ class FNOBlocks(nn.Module):
         w = self.convs.dense_weight(index, H, W)
         b = self.convs.bias[index] if self.convs.bias is not None else None
         act = index < self.n_layers - 1
-        return FNOBlockFn.apply(x, w, self.fno_skips[index].weight, b, tuple(self.convs.n_modes), act)
+        return FNOBlockFn.apply(x, w, self.fno_skips[index].weight, b, tuple(self.convs.n_modes), act,
+                                torch.is_grad_enabled())
 
     def forward_all(self, x):
         """All blocks through one fused autograd node (what ``FNO.forward`` uses)."""
@@ -138,7 +144,7 @@ class FNOBlocks(nn.Module):
         dense = self.convs.dense_weights_all(H, W)
         for l in range(self.n_layers):
             params += [dense[l], self.fno_skips[l].weight, self.convs.bias[l]]
-        return FNOStackFn.apply(x, tuple(self.convs.n_modes), self.n_layers, *params)
+        return FNOStackFn.apply(x, tuple(self.convs.n_modes), self.n_layers, torch.is_grad_enabled(), *params)
 
 
 class FNO(nn.Module):
@@ -191,9 +197,8 @@ class FNO(nn.Module):
     def forward(self, x, output_shape=None, **kwargs):
         if output_shape is not None:
             raise NotImplementedError("FNO(B200): output_shape is only used by the 3-D wrappers (out of scope)")
-        if not x.is_cuda:
-            raise _lib.SpectralB200Error("FNO(B200) got a CPU tensor: there is no CPU / torch.fft path")
-        if self.fused and self.fno_blocks.convs.bias is not None and x.shape[-1] % 4 == 0:
+        _check_grid(x)
+        if self.fused and self.fno_blocks.convs.bias is not None:
             return self._forward_fused(x)
         x = self.lifting(x)
         x = self.fno_blocks.forward_all(x)
@@ -210,14 +215,21 @@ class FNO(nn.Module):
             params += [None, fc.weight, fc.bias]
         blocks = self.fno_blocks
         dense = blocks.convs.dense_weights_all(H, W)
+        bias = blocks.convs.bias
+        bsink = getattr(bias, "_sb200_grad_sink", None)        # ddp.GradSync(direct=True)
         for l in range(self.n_layers):
             spec.append(True); acts.append(l < self.n_layers - 1)
-            params += [dense[l], blocks.fno_skips[l].weight, blocks.convs.bias[l]]
+            b_l = bias[l]
+            if bsink is not None:                              # layer l's slice of the bias gradient destination
+                b_l._sb200_grad_sink = bsink.view(self.n_layers, -1)[l]
+                b_l._sb200_sink_owner = bias
+            params += [dense[l], blocks.fno_skips[l].weight, b_l]
         nl_proj = len(self.projection.fcs)
         for i, fc in enumerate(self.projection.fcs):
             spec.append(False); acts.append(i < nl_proj - 1)
             params += [None, fc.weight, fc.bias]
-        return FusedChainFn.apply(x, tuple(blocks.convs.n_modes), tuple(spec), tuple(acts), *params)
+        return FusedChainFn.apply(x, tuple(blocks.convs.n_modes), tuple(spec), tuple(acts), torch.is_grad_enabled(),
+                                  *params)
 
 
 class TFNO(FNO):

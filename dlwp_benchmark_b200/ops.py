@@ -1,10 +1,12 @@
 """Tensor-level wrappers over the C ABI (one python function per exported stage).
 
-Every function requires CUDA fp32 contiguous tensors and launches on torch's current stream.
+Every function requires CUDA fp32 contiguous tensors and launches on torch's current stream of the CURRENT
+device; the autograd Functions make the tensors' device current first (``_lib.on_tensor_device``).
 """
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Optional
 
 import torch
@@ -30,6 +32,25 @@ def _req(t: torch.Tensor, name: str):
         raise _lib.SpectralB200Error(f"{name}: expected float32, got {t.dtype}")
     if not t.is_contiguous():
         raise _lib.SpectralB200Error(f"{name}: expected a contiguous tensor")
+
+
+def grad_sink(p):
+    """Direct gradient destination of a parameter (``ddp.GradSync(direct=True)``): a contiguous fp32 view with the
+    parameter's numel into the flat all-reduce buffer, or None.  A backward that writes its result there returns
+    None for that input, so autograd neither allocates nor accumulates (the sink is OVERWRITTEN, not added to)."""
+    s = getattr(p, "_sb200_grad_sink", None) if p is not None else None
+    if s is not None:
+        owner = getattr(p, "_sb200_sink_owner", p)
+        owner._sb200_sink_used = True
+    return s
+
+
+def _out(out, shape, dev):
+    """``out`` viewed as ``shape`` (a grad sink) or a fresh tensor."""
+    if out is None:
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == math.prod(shape), (out.shape, shape)
+    return out.view(*shape)
 
 
 def rowdft_fwd(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
@@ -69,6 +90,8 @@ def analysis(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
     nimg = x.numel() // (plan.H * plan.W)
     lib = _lib.load()
     n = lib.sb200_analysis_scratch(plan.handle, nimg)
+    if n == 0 and (x.data_ptr() % 16 != 0 or nimg * plan.H >= 2 ** 31):
+        n = nimg * plan.H * plan.Mx * 2       # the fused kernel declines such inputs at launch: two-stage scratch
     scratch = torch.empty(n, device=x.device, dtype=torch.float32) if n > 0 else None
     Xh = torch.empty(*x.shape[:-2], plan.My, plan.Mx, 2, device=x.device, dtype=torch.float32)
     _lib.check(lib.sb200_analysis(plan.handle, pas, _p(x), _p(Xh), nimg, _p(scratch), _stream()), "analysis")
@@ -100,12 +123,12 @@ def mix_bwd_input(gYh: torch.Tensor, Wc: torch.Tensor) -> torch.Tensor:
     return modes_gemm(gYh, M, Cout * M, Wc, M, Cout * M, out, Cin * M, M, B, Cin, Cout, M, 2)
 
 
-def mix_bwd_weight(Xh: torch.Tensor, gYh: torch.Tensor) -> torch.Tensor:
+def mix_bwd_weight(Xh: torch.Tensor, gYh: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """gW[i,o,k] = sum_b conj(Xh[b,i,k]) gYh[b,o,k]"""
     B, Cin = Xh.shape[:2]
     Cout = gYh.shape[1]
     M = Xh.shape[2] * Xh.shape[3]
-    out = torch.empty(Cin, Cout, *Xh.shape[2:], device=Xh.device, dtype=torch.float32)
+    out = _out(out, (Cin, Cout, *Xh.shape[2:]), Xh.device)
     return modes_gemm(Xh, Cin * M, M, gYh, Cout * M, M, out, Cout * M, M, Cin, Cout, B, M, 1)
 
 
@@ -124,7 +147,7 @@ def rowidft_pointwise(plan: Plan, pas: int, Phi, A, Wp, w_sn, w_sm, bias, zprev,
     return y, z
 
 
-def pointwise_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+def pointwise_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True, out_w=None, out_b=None):
     """gW[o,i] = sum g[b,o,p] x[b,i,p]; gbias[o] = sum g[b,o,p].  g [B,Cout,H,W], x [B,Cin,H,W]."""
     _req(g, "g"); _req(x, "x")
     B, Cout = g.shape[:2]
@@ -133,11 +156,23 @@ def pointwise_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
     lib = _lib.load()
     n = lib.sb200_pointwise_wgrad_workspace(B, Cout, Cin, HW)
     ws = torch.empty(n, device=g.device, dtype=torch.float32)
-    gW = torch.empty(Cout, Cin, device=g.device, dtype=torch.float32)
-    gb = torch.empty(Cout, device=g.device, dtype=torch.float32) if want_bias else None
+    gW = _out(out_w, (Cout, Cin), g.device)
+    gb = _out(out_b, (Cout,), g.device) if want_bias else None
     _lib.check(lib.sb200_pointwise_wgrad(_p(g), _p(x), _p(gW), _p(gb), B, Cout, Cin, HW, _p(ws), _stream()),
                "pointwise_wgrad")
     return gW, gb
+
+
+def channel_sum(g: torch.Tensor) -> torch.Tensor:
+    """out[c] = sum_{b,h,w} g[b,c,h,w]"""
+    _req(g, "g")
+    B, C = g.shape[:2]
+    HW = g.shape[2] * g.shape[3]
+    lib = _lib.load()
+    ws = torch.empty(lib.sb200_channel_sum_workspace(B, C), device=g.device, dtype=torch.float32)
+    out = torch.empty(C, device=g.device, dtype=torch.float32)
+    _lib.check(lib.sb200_channel_sum(_p(g), _p(out), B, C, HW, _p(ws), _stream()), "channel_sum")
+    return out
 
 
 def gelu_fwd(z: torch.Tensor) -> torch.Tensor:
@@ -166,7 +201,8 @@ def pointwise_small_n(A: torch.Tensor, Wp: torch.Tensor, bias, apply_act: bool, 
     return y, z
 
 
-def wgrad_small(small: torch.Tensor, big: torch.Tensor, transpose: bool, want_small_sum: bool, want_big_sum: bool):
+def wgrad_small(small: torch.Tensor, big: torch.Tensor, transpose: bool, want_small_sum: bool, want_big_sum: bool,
+                out_dot=None, out_small=None, out_big=None):
     """dot[s,l] = sum small[b,s,p] big[b,l,p] (returned as [l,s] if transpose); channel sums on request."""
     _req(small, "small"); _req(big, "big")
     B, S = small.shape[:2]
@@ -174,9 +210,9 @@ def wgrad_small(small: torch.Tensor, big: torch.Tensor, transpose: bool, want_sm
     HW = small.shape[2] * small.shape[3]
     lib = _lib.load()
     ws = torch.empty(lib.sb200_wgrad_small_workspace(B, S, L, HW), device=small.device, dtype=torch.float32)
-    dot = torch.empty((L, S) if transpose else (S, L), device=small.device, dtype=torch.float32)
-    ss = torch.empty(S, device=small.device, dtype=torch.float32) if want_small_sum else None
-    bs = torch.empty(L, device=small.device, dtype=torch.float32) if want_big_sum else None
+    dot = _out(out_dot, (L, S) if transpose else (S, L), small.device)
+    ss = _out(out_small, (S,), small.device) if want_small_sum else None
+    bs = _out(out_big, (L,), small.device) if want_big_sum else None
     _lib.check(lib.sb200_wgrad_small(_p(small), _p(big), _p(dot), _p(ss), _p(bs), B, S, L, HW, int(transpose), _p(ws),
                                      _stream()), "wgrad_small")
     return dot, ss, bs
@@ -231,7 +267,7 @@ def mlp_head_fwd(h, W1, b1, w2, b2):
     return y
 
 
-def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True):
+def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True, out_gb1=None, out_gw2=None, out_gb2=None):
     """Returns (gz1 [B,256,H,W], gb1 [256], gw2 [256], gb2 [1] or None)."""
     for t, n in ((h, "h"), (W1, "W1"), (b1, "b1"), (w2, "w2"), (gy, "gy")):
         _req(t, n)
@@ -240,16 +276,16 @@ def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True):
     lib = _lib.load()
     dev = h.device
     gz1 = torch.empty(B, N, H, W, device=dev, dtype=torch.float32)
-    gb1 = torch.empty(N, device=dev, dtype=torch.float32)
-    gw2 = torch.empty(N, device=dev, dtype=torch.float32)
-    gb2 = torch.empty(1, device=dev, dtype=torch.float32) if want_gb2 else None
+    gb1 = _out(out_gb1, (N,), dev)
+    gw2 = _out(out_gw2, (N,), dev)
+    gb2 = _out(out_gb2, (1,), dev) if want_gb2 else None
     ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=dev, dtype=torch.float32)
     _lib.check(lib.sb200_mlp_head_bwd(_p(h), _p(W1), _p(b1), _p(w2), _p(gy), _p(gz1), _p(gb1), _p(gw2), _p(gb2), _p(ws),
                                       B, M, N, H * W, _stream()), "mlp_head_bwd")
     return gz1, gb1, gw2, gb2
 
 
-def lift_tail_bwd(g, W2, w1, b1, x):
+def lift_tail_bwd(g, W2, w1, b1, x, out_gw1=None, out_gb1=None):
     """Backward of the first lifting layer for a 1-channel input: returns (gw1 [256], gb1 [256]).
     g [B,C,H,W] gradient wrt the lifting output, W2 [C,256], w1/b1 [256], x [B,1,H,W]."""
     for t, n in ((g, "g"), (W2, "W2"), (w1, "w1"), (b1, "b1"), (x, "x")):
@@ -257,8 +293,8 @@ def lift_tail_bwd(g, W2, w1, b1, x):
     B, C, H, W = g.shape
     N = W2.shape[1]
     lib = _lib.load()
-    gw1 = torch.empty(N, device=g.device, dtype=torch.float32)
-    gb1 = torch.empty(N, device=g.device, dtype=torch.float32)
+    gw1 = _out(out_gw1, (N,), g.device)
+    gb1 = _out(out_gb1, (N,), g.device)
     ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=g.device, dtype=torch.float32)
     _lib.check(lib.sb200_lift_tail_bwd(_p(g), _p(W2), _p(w1), _p(b1), _p(x), _p(gw1), _p(gb1), _p(ws), B, C, N, H * W,
                                        _stream()), "lift_tail_bwd")
@@ -282,7 +318,7 @@ def lift_fwd(x, w1, b1, W2, b2):
     return y
 
 
-def lift_wgrad(g, x, w1, b1, want_bias: bool = True):
+def lift_wgrad(g, x, w1, b1, want_bias: bool = True, out_w=None, out_b=None):
     """(gW2 [C,256], gb2 [C] or None) with the hidden activations regenerated from x on chip."""
     for t, n in ((g, "g"), (x, "x"), (w1, "w1"), (b1, "b1")):
         _req(t, n)
@@ -290,8 +326,8 @@ def lift_wgrad(g, x, w1, b1, want_bias: bool = True):
     N = w1.numel()
     lib = _lib.load()
     ws = torch.empty(lib.sb200_pointwise_wgrad_workspace(B, C, N, H * W), device=g.device, dtype=torch.float32)
-    gW2 = torch.empty(C, N, device=g.device, dtype=torch.float32)
-    gb2 = torch.empty(C, device=g.device, dtype=torch.float32) if want_bias else None
+    gW2 = _out(out_w, (C, N), g.device)
+    gb2 = _out(out_b, (C,), g.device) if want_bias else None
     _lib.check(lib.sb200_lift_wgrad(_p(g), _p(x), _p(w1), _p(b1), _p(gW2), _p(gb2), _p(ws), B, C, N, H * W, _stream()),
                "lift_wgrad")
     return gW2, gb2

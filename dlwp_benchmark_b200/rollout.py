@@ -85,3 +85,105 @@ class Rollout:
             if t + 1 < steps:
                 self._x.copy_(self._y)
         return out
+
+
+def _flat_tc(t: torch.Tensor) -> torch.Tensor:
+    """einops "b t c h w -> b (t c) h w" on a contiguous tensor."""
+    return t.reshape(t.shape[0], t.shape[1] * t.shape[2], *t.shape[3:])
+
+
+def dlwp_sequence_forward(fno: nn.Module, constants: Optional[torch.Tensor], prescribed: Optional[torch.Tensor],
+                          prognostic: torch.Tensor, context_size: int) -> torch.Tensor:
+    """``FNO2DModule.forward`` of dlwpbench (src/dlwpbench/models/fno/fno.py:64-106), differentiable:
+
+        for t in [ctx, T):  prognostic_t = last ctx frames of [true frames before ctx ; outputs so far]
+                            x_t = cat(constants[:, 0], prescribed[:, t-ctx:t] (t c), prognostic_t (t c))
+                            out_t = prognostic_t[:, -1] + fno(x_t)
+
+    with the evident intent of the reference's two device slips (``list.to`` at :91-95, ``out.cpu()`` at :104): every
+    frame stays on the device, nothing is read back inside the loop.  Returns [B, T-ctx, C_prog, H, W]."""
+    ctx = int(context_size)
+    outs = []
+    T = prognostic.shape[1]
+    for t in range(ctx, T):
+        t_start = max(0, t - ctx)
+        if t == ctx:
+            prog_t = prognostic[:, t_start:t]
+        else:
+            prog_t = torch.cat([prognostic[:, t_start:ctx], torch.stack(outs, dim=1)[:, -ctx:]], dim=1)
+        parts = []
+        if constants is not None:
+            parts.append(constants[:, 0])
+        if prescribed is not None:
+            parts.append(_flat_tc(prescribed[:, t - ctx:t]))
+        parts.append(_flat_tc(prog_t))
+        outs.append(prog_t[:, -1] + fno(torch.cat(parts, dim=1)))
+    return torch.stack(outs, dim=1)
+
+
+class DLWPRollout:
+    """Inference engine for the dlwpbench loop (same semantics as ``dlwp_sequence_forward``): one model step is
+    captured as a CUDA graph over a static input buffer ``[B, Cc + ctx*(Cp+Cg), H, W]``; per frame the prescribed
+    window and the newest prognostic frame are copied into their channel slots on the device (the older
+    prognostic frames are shifted inside the buffer), the graph is replayed, and the residual add writes the
+    frame straight into the preallocated result.  Nothing is read back to the host inside the loop."""
+
+    def __init__(self, fno: nn.Module, context_size: int, graph: bool = True):
+        self.fno, self.ctx, self.use_graph = fno, int(context_size), graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._x: Optional[torch.Tensor] = None
+        self._y: Optional[torch.Tensor] = None
+
+    def _step(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._y = self.fno(self._x)
+
+    def _prepare(self, shape, device):
+        if self._x is not None and tuple(self._x.shape) == tuple(shape) and self._x.device == device:
+            return
+        self._x = torch.zeros(*shape, device=device, dtype=torch.float32)
+        self._graph = None
+        if not self.use_graph:
+            return
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._y = self.fno(self._x)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._y = self.fno(self._x)
+        self._graph = g
+
+    @torch.no_grad()
+    def __call__(self, constants, prescribed, prognostic, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not prognostic.is_cuda:
+            raise _lib.SpectralB200Error("DLWPRollout got a CPU tensor: there is no CPU path")
+        ctx = self.ctx
+        B, T, Cg, H, W = prognostic.shape
+        Cc = constants.shape[2] if constants is not None else 0
+        Cp = prescribed.shape[2] if prescribed is not None else 0
+        cin = Cc + ctx * (Cp + Cg)
+        self._prepare((B, cin, H, W), prognostic.device)
+        x = self._x
+        if out is None:
+            out = torch.empty(B, T - ctx, Cg, H, W, device=prognostic.device, dtype=torch.float32)
+        if Cc:
+            x[:, :Cc].copy_(constants[:, 0])
+        p0 = Cc + ctx * Cp                                  # first prognostic channel
+        xg = x[:, p0:].view(B, ctx, Cg, H, W)
+        xg.copy_(prognostic[:, :ctx])
+        for i, t in enumerate(range(ctx, T)):
+            if Cp:
+                x[:, Cc:p0].copy_(_flat_tc(prescribed[:, t - ctx:t]))
+            if i > 0:
+                if ctx > 1:
+                    xg[:, :-1].copy_(xg[:, 1:].clone())
+                xg[:, -1].copy_(out[:, i - 1])
+            self._step()
+            torch.add(xg[:, -1], self._y, out=out[:, i])
+        return out

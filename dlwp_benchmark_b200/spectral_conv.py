@@ -29,19 +29,15 @@ def _check_input(x: torch.Tensor):
             "SpectralConv (B200) got a CPU tensor: this implementation has no CPU / torch.fft path")
     if x.dim() != 4:
         raise _lib.SpectralB200Error(f"only 2-D spectral convolutions are implemented (got {x.dim() - 2}-D input)")
+    if x.shape[-1] % 4 != 0:
+        raise _lib.SpectralB200Error(
+            f"grid width W={x.shape[-1]} is not a multiple of 4: the row-synthesis kernels store 16-byte vectors "
+            "(every grid the reference uses -- 64, 128, 256, 32x64 -- qualifies)")
 
 
 # --------------------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------------------
-class _SpectralStage:
-    """Shared forward / backward building blocks (all on the current CUDA stream)."""
-
-    @staticmethod
-    def analysis(plan, pas, x):
-        return ops.analysis(plan, pas, x)
-
-
 class FNOBlockFn(torch.autograd.Function):
     """y = act( SpectralConv(x; W, bias) + Conv1x1(x; w_skip) )   -- one FNO block.
 
@@ -50,7 +46,8 @@ class FNOBlockFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, W, w_skip, bias, n_modes_halved, apply_act: bool):
+    @_lib.on_tensor_device
+    def forward(ctx, x, W, w_skip, bias, n_modes_halved, apply_act: bool, grad_mode: bool = True):
         _check_input(x)
         x = x.contiguous().float()
         W = W.contiguous().float()
@@ -58,12 +55,12 @@ class FNOBlockFn(torch.autograd.Function):
         Cout = W.shape[1]
         plan = fno_plan(x.device, H, Wd, n_modes_halved)
         assert tuple(W.shape[2:]) == (plan.My, plan.Mx, 2), (W.shape, plan.My, plan.Mx)
-        Xh = _SpectralStage.analysis(plan, 0, x)
+        Xh = ops.analysis(plan, 0, x)
         Yh = ops.mix_fwd(Xh, W)
         Phi = ops.coldft_inv(plan, 0, Yh)
         ws = w_skip.reshape(Cout, Cin).contiguous().float() if w_skip is not None else None
         bv = bias.reshape(Cout).contiguous().float() if bias is not None else None
-        need_z = apply_act and any(ctx.needs_input_grad)
+        need_z = apply_act and bool(grad_mode) and any(ctx.needs_input_grad)
         y, z = ops.rowidft_pointwise(plan, 0, Phi, x if ws is not None else None, ws, Cin, 1, bv, None,
                                      B, Cin, Cout, 0, apply_act, want_z=need_z)
         ctx.plan = plan
@@ -76,6 +73,7 @@ class FNOBlockFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, gy):
         x, W, ws, Xh, z = ctx.saved_tensors
         plan = ctx.plan
@@ -83,7 +81,7 @@ class FNOBlockFn(torch.autograd.Function):
         Cout = W.shape[1]
         gy = gy.contiguous().float()
         gz = ops.gelu_bwd(gy, z) if ctx.apply_act else gy
-        gYh = _SpectralStage.analysis(plan, 1, gz)
+        gYh = ops.analysis(plan, 1, gz)
         gW = ops.mix_bwd_weight(Xh, gYh) if ctx.needs_input_grad[1] else None
         gx = None
         if ctx.needs_input_grad[0]:
@@ -96,10 +94,10 @@ class FNOBlockFn(torch.autograd.Function):
             gws, gb = ops.pointwise_wgrad(gz, x, want_bias=ctx.has_bias)
             gws = gws.reshape(ctx.wskip_shape)
         elif ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = gz.sum(dim=(0, 2, 3))
+            gb = ops.channel_sum(gz)
         if gb is not None:
             gb = gb.reshape(ctx.bias_shape)
-        return gx, gW, gws, gb, None, None
+        return gx, gW, gws, gb, None, None, None
 
 
 class FNOStackFn(torch.autograd.Function):
@@ -111,11 +109,13 @@ class FNOStackFn(torch.autograd.Function):
     weighted analysis of gz, two mode contractions, a column synthesis, one fused
     [adjoint row synthesis + skip dgrad + GELU'(z_{l-1})] and one skip wgrad.
 
-    args: x, n_modes_halved, L, then per layer (W_l, wskip_l, bias_l)
+    args: x, n_modes_halved, L, grad_mode (the caller's ``torch.is_grad_enabled()``), then per layer
+    (W_l, wskip_l, bias_l)
     """
 
     @staticmethod
-    def forward(ctx, x, n_modes_halved, L, *params):
+    @_lib.on_tensor_device
+    def forward(ctx, x, n_modes_halved, L, grad_mode, *params):
         _check_input(x)
         x = x.contiguous().float()
         B, C, H, Wd = x.shape
@@ -123,12 +123,12 @@ class FNOStackFn(torch.autograd.Function):
         Ws = [params[3 * l].contiguous().float() for l in range(L)]
         wss = [params[3 * l + 1].reshape(C, C).contiguous().float() for l in range(L)]
         bvs = [params[3 * l + 2].reshape(C).contiguous().float() for l in range(L)]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         hs, Xhs, zs = [], [], []
         h = x
         for l in range(L):
             act = l < L - 1
-            Xh = _SpectralStage.analysis(plan, 0, h)
+            Xh = ops.analysis(plan, 0, h)
             Yh = ops.mix_fwd(Xh, Ws[l])
             Phi = ops.coldft_inv(plan, 0, Yh)
             y, z = ops.rowidft_pointwise(plan, 0, Phi, h, wss[l], C, 1, bvs[l], None, B, C, C, 0, act,
@@ -141,6 +141,7 @@ class FNOStackFn(torch.autograd.Function):
         return h
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, gy):
         L, C, plan = ctx.L, ctx.C, ctx.plan
         sv = list(ctx.saved_tensors)
@@ -153,7 +154,7 @@ class FNOStackFn(torch.autograd.Function):
         grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
         gx = None
         for l in range(L - 1, -1, -1):
-            gYh = _SpectralStage.analysis(plan, 1, gz)
+            gYh = ops.analysis(plan, 1, gz)
             grads[3 * l] = ops.mix_bwd_weight(Xhs[l], gYh)
             gws, gb = ops.pointwise_wgrad(gz, hs[l], want_bias=True)
             grads[3 * l + 1] = gws.reshape(ctx.shapes[l][0])
@@ -167,7 +168,7 @@ class FNOStackFn(torch.autograd.Function):
                     gz = gprev
                 else:
                     gx = gprev
-        return (gx, None, None, *grads)
+        return (gx, None, None, None, *grads)
 
 
 # --------------------------------------------------------------------------------------
@@ -273,7 +274,7 @@ class SpectralConv(nn.Module):
         H, W = x.shape[-2:]
         w = self.dense_weight(indices, H, W)
         b = self.bias[indices] if self.bias is not None else None
-        return FNOBlockFn.apply(x, w, None, b, tuple(self.n_modes), False)
+        return FNOBlockFn.apply(x, w, None, b, tuple(self.n_modes), False, torch.is_grad_enabled())
 
     def get_conv(self, indices):
         if self.n_layers == 1:

@@ -48,6 +48,7 @@ class TuckerReconstructManyFn(torch.autograd.Function):
     Real views of complex64: core [r0,r1,r2,r3,2], Uk [sk,rk,2], W [s0,s1,s2,s3,2]."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, n, *params):
         assert len(params) == 5 * n and 1 <= n <= MAX_GROUP
         if not params[0].is_cuda:
@@ -60,46 +61,55 @@ class TuckerReconstructManyFn(torch.autograd.Function):
             assert tuple(cores[l].shape[:4]) == tuple(r) and all(tuple(Us[k][l].shape[:2]) == (s[k], r[k]) for k in range(4))
         Ts = _mode_products(cores, Us, s, r)
         ctx.n, ctx.s, ctx.r = n, s, r
+        ctx.sinks = [ops.grad_sink(t) for t in params]      # ddp.GradSync(direct=True): gradients written in place
         ctx.save_for_backward(*Ts[0], *Ts[1], *Ts[2], *Ts[3], *Us[0], *Us[1], *Us[2], *Us[3])
         return tuple(Ts[4])
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, *gWs):
         n, s, r = ctx.n, ctx.s, ctx.r
         sv = ctx.saved_tensors
         T0, T1, T2, T3, U0, U1, U2, U3 = (list(sv[i * n:(i + 1) * n]) for i in range(8))
         dev = T0[0].device
+        sinks = ctx.sinks
+
+        def dest(k, shape):
+            """per-layer outputs of parameter slot k (0 = core, 1..4 = factors): the sink when there is one"""
+            return [ops._out(sinks[5 * l + k], (*shape, 2), dev) for l in range(n)]
+
         g4 = [(g if g is not None else torch.zeros(*s, 2, device=dev)).contiguous().float() for g in gWs]
         R, Q, IO = r[1] * r[2] * r[3], r[2] * r[3], s[0] * s[1]
         # ---- mode 3 ----
-        gU3 = _empty(dev, n, s[3], r[3])
+        gU3 = dest(4, (s[3], r[3]))
         ops.cgemm(g4, T3, gU3, M=s[3], N=r[3], K=IO * s[2], sAm=1, sAk=s[3], sBk=r[3], sBn=1, sCm=r[3], sCn=1,
                   conjB=True)
         g3 = _empty(dev, n, s[0], s[1], s[2], r[3])
         ops.cgemm(g4, U3, g3, M=IO * s[2], N=r[3], K=s[3], sAm=s[3], sAk=1, sBk=r[3], sBn=1, sCm=r[3], sCn=1,
                   conjB=True)
         # ---- mode 2 ----  reduction index (io, j) composite
-        gU2 = _empty(dev, n, s[2], r[2])
+        gU2 = dest(3, (s[2], r[2]))
         ops.cgemm(g3, T2, gU2, M=s[2], N=r[2], K=IO * r[3], K2=r[3], sAm=r[3], sAk=(s[2] * r[3], 1),
                   sBk=(r[2] * r[3], 1), sBn=r[3], sCm=r[2], sCn=1, conjB=True)
         g2 = _empty(dev, n, s[0], s[1], r[2], r[3])
         ops.cgemm(g3, U2, g2, M=IO * r[3], M2=r[3], N=r[2], K=s[2], sAm=(s[2] * r[3], 1), sAk=r[3], sBk=r[2], sBn=1,
                   sCm=(r[2] * r[3], 1), sCn=r[3], conjB=True)
         # ---- mode 1 ----  reduction index (i, Q) composite
-        gU1 = _empty(dev, n, s[1], r[1])
+        gU1 = dest(2, (s[1], r[1]))
         ops.cgemm(g2, T1, gU1, M=s[1], N=r[1], K=s[0] * Q, K2=Q, sAm=Q, sAk=(s[1] * Q, 1), sBk=(r[1] * Q, 1), sBn=Q,
                   sCm=r[1], sCn=1, conjB=True)
         g1 = _empty(dev, n, s[0], r[1], r[2], r[3])
         ops.cgemm(g2, U1, g1, M=s[0] * Q, M2=Q, N=r[1], K=s[1], sAm=(s[1] * Q, 1), sAk=Q, sBk=r[1], sBn=1,
                   sCm=(r[1] * Q, 1), sCn=Q, conjB=True)
         # ---- mode 0 ----
-        gU0 = _empty(dev, n, s[0], r[0])
+        gU0 = dest(1, (s[0], r[0]))
         ops.cgemm(g1, T0, gU0, M=s[0], N=r[0], K=R, sAm=R, sAk=1, sBk=1, sBn=R, sCm=r[0], sCn=1, conjB=True)
-        g0 = _empty(dev, n, r[0], r[1], r[2], r[3])
+        g0 = dest(0, (r[0], r[1], r[2], r[3]))
         ops.cgemm(g1, U0, g0, M=R, N=r[0], K=s[0], sAm=1, sAk=R, sBk=r[0], sBn=1, sCm=1, sCn=R, conjB=True)
         out = [None]
         for l in range(n):
-            out += [g0[l], gU0[l], gU1[l], gU2[l], gU3[l]]
+            out += [t if sinks[5 * l + k] is None else None
+                    for k, t in enumerate((g0[l], gU0[l], gU1[l], gU2[l], gU3[l]))]
         return tuple(out)
 
 

@@ -43,15 +43,12 @@ int sb200_device_arch(void);
 
 /* Tensor-core mode of the GEMM-shaped stages: 0 = CUDA-core (exact fp32 FFMA) kernels only,
  * 1 = tcgen05 kind::tf32 single pass (parity ~1e-3), 3 = tcgen05 3xTF32 split (parity <= 1e-5; default).
- * Shapes the tcgen05 kernels do not cover always run on the CUDA-core kernels. Process-global. */
+ * Shapes the tcgen05 kernels do not cover always run on the CUDA-core kernels.
+ * This is a process-wide DEFAULT (stored atomically, read once per entry point); it is the only mutable
+ * library state besides the plan cache and the launch counter. */
 int sb200_set_tc_mode(int mode);
 int sb200_get_tc_mode(void);
 
-/* Bring-up self-test of the tcgen05 path: D[128,N] = A[128,K] * B[N,K]^T (tf32, single pass) with A staged
- * K-major (a_layout 0) or MN-major (1; 2 = MN-major with LBO/SBO swapped) in 128B-swizzled shared memory.
- * info[0..5] receives the TMEM base address, the instruction descriptor and the first A/B descriptors. */
-int sb200_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_layout, int use_mask,
-                      uint32_t* info, void* stream);
 
 /* ---- plans ---------------------------------------------------------------------------
  * Retained block: rows ky = (ky0 + j) mod H, j in [0,My); cols kx in [0,Mx).
@@ -228,6 +225,11 @@ int sb200_afno_blocklinear_wgrad(const float* a, const float* gout, const float*
 /* Element-wise helpers used between layers: y = gelu(z);  gz = gy * gelu'(z) */
 int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream);
 int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream);
+
+/* out[c] = sum_{b,p} g[b,c,p] for g [B,C,HW]: the bias gradient of a SpectralConv that has no skip convolution
+ * (with a skip the sum comes out of sb200_pointwise_wgrad).  workspace: sb200_channel_sum_workspace(B,C) floats. */
+int64_t sb200_channel_sum_workspace(int B, int C);
+int sb200_channel_sum(const float* g, float* out, int B, int C, int64_t HW, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ commit (``neuralop/layers/spectral_convolution.py::SpectralConv.forward``,
 PARITY UNPINNED for this file: the reference holds no test, golden vector or fixture
 for the FNO path and neuralop cannot be executed here.  The only
 in-tree corroboration is the parameter-count labels of the reference's own sweeps
-(checked in ``tests/test_param_counts.py``).  The AFNO2D oracle (``afno_oracle.py``)
+(checked in ``tests/test_oracle_golden.py::test_reference_size_labels``).  The AFNO2D oracle (``afno_oracle.py``)
 *is* pinned against the reference class executed in this container.
 
 Every function works in the dtype of its inputs (use float64 for a tight oracle,
@@ -264,4 +264,35 @@ def rollout(sd, x0, n_modes, n_layers, steps: int, prefix: str = ""):
     for _ in range(steps):
         x = fno_forward(sd, x, n_modes, n_layers, prefix)
         outs.append(x)
+    return torch.stack(outs, dim=1)
+
+
+def dlwp_rollout(sd, constants, prescribed, prognostic, context_size: int, n_modes, n_layers, prefix: str = ""):
+    """``FNO2DModule.forward`` of dlwpbench (src/dlwpbench/models/fno/fno.py:64-106) with the evident intent of its
+    two device bugs (``[...].to(device=...)`` on a python list at :91-95 and ``outs.append(out.cpu())`` at :104, which
+    make the reference raise for ``T > context_size + 1`` / on CUDA): every frame stays on the input's device.
+
+    constants [B,1,Cc,H,W] or None, prescribed [B,T,Cp,H,W] or None, prognostic [B,T,Cg,H,W]
+    -> [B, T - context_size, Cg, H, W];   frame t:  out_t = prognostic_t[:, -1] + FNO(x_t),
+    x_t = cat(constants[:, 0], prescribed[:, t-ctx:t] as (t c), prognostic_t as (t c)) on the channel axis,
+    prognostic_t = the last ``ctx`` frames of [true frames before ctx ; model outputs so far].
+    """
+    ctx = int(context_size)
+    outs = []
+    B, T = prognostic.shape[:2]
+    flat = lambda t: t.reshape(t.shape[0], t.shape[1] * t.shape[2], *t.shape[3:])
+    for t in range(ctx, T):
+        t_start = max(0, t - ctx)
+        if t == ctx:
+            prog_t = prognostic[:, t_start:t]
+        else:
+            prog_t = torch.cat([prognostic[:, t_start:ctx], torch.stack(outs, dim=1)[:, -ctx:]], dim=1)
+        parts = []
+        if constants is not None:
+            parts.append(constants[:, 0])
+        if prescribed is not None:
+            parts.append(flat(prescribed[:, t - ctx:t]))
+        parts.append(flat(prog_t))
+        x_t = torch.cat(parts, dim=1)
+        outs.append(prog_t[:, -1] + fno_forward(sd, x_t, n_modes, n_layers, prefix))
     return torch.stack(outs, dim=1)
