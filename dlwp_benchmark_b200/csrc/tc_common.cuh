@@ -180,7 +180,20 @@ __device__ __forceinline__ uint32_t sw128b32_mnmajor_off(int mn, int k, uint32_t
            (uint32_t)((mn & 7) << 2);
 }
 
-__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// 3xTF32 operand split  v = hi + lo:  hi = v rounded to NEAREST tf32 (10 explicit mantissa bits), lo = v - hi (exact
+// in fp32; the tensor core reads it as tf32 by dropping its low 13 bits).
+// Rounding hi to nearest instead of truncating it matters: with a truncated hi, lo always has the sign of v, and
+// the hardware's truncation of lo then biases every product by about -2^-21 relative -- a systematic error that
+// does not average out over the K sum (measured in round 2: 2e-6 per GEMM stage against 3e-7 for the FFMA path,
+// 1.4e-5 on the cfg3 / cfg5 model outputs).  With hi rounded, lo has a random sign and its truncation error is
+// zero-mean, <= 2^-21 |v|.  Integer rounding (add half an ulp of tf32, clear 13 bits: round-half-away) runs at
+// full ALU rate; cvt.rna.tf32.f32 is a conversion-pipe instruction and measured 4 % slower on the cfg2 step.
+__device__ __forceinline__ float tf32_rna(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_trunc(float v) { return tf32_rna(v); }          // "hi" part (historic name)
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return v - hi; }
+__device__ __forceinline__ float4 tf32_lo4(float4 v, float4 h) {
+    return make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
+}
 
 }  // namespace tc
 

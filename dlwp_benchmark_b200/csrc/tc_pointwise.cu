@@ -213,7 +213,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const float hi = tc::tf32_trunc(v);
             const uint32_t off = tc::sw32_kmajor_off(px, k, 4096u);
             *reinterpret_cast<float*>(E_hi + off) = hi;
-            if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = v - hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(E_lo + off) = tc::tf32_lo(v, hi);
         }
         for (int idx = tid; idx < p.V * p.Mx; idx += TP_THREADS) rot_s[idx] = __ldg(p.rot + idx);
         // zero both Phi buffers once: the K padding columns are never written again
@@ -228,7 +228,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const float hi = tc::tf32_trunc(w);
             const uint32_t off = (uint32_t)(k >> 5) * b_chunk_bytes + tc::sw128_kmajor_off(n, k & 31);
             *reinterpret_cast<float*>(B_hi + off) = hi;
-            if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = w - hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = tc::tf32_lo(w, hi);
         }
     }
     for (int idx = tid; idx < 256; idx += TP_THREADS) bias_s[idx] = (bias_epi && idx < p.N) ? __ldg(p.bias + idx) : 0.f;
@@ -248,7 +248,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const float hi = tc::tf32_trunc(v);
             const uint32_t off = tc::sw32_kmajor_off(n, p.K2, phi_kstep);
             *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + off) = hi;
-            if (PASSES == 3) *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + phi_bytes + off) = v - hi;
+            if (PASSES == 3) *reinterpret_cast<float*>(Phi_s + (uint32_t)a * phi_buf_bytes + phi_bytes + off) = tc::tf32_lo(v, hi);
         }
     }
     tc::fence_proxy_async_smem();
@@ -424,7 +424,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                             }
                             const float2 h = make_float2(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y));
                             *reinterpret_cast<float2*>(pbuf + st_off[u]) = h;
-                            if (PASSES == 3) *reinterpret_cast<float2*>(pbuf + phi_bytes + st_off[u]) = make_float2(g.x - h.x, g.y - h.y);
+                            if (PASSES == 3) *reinterpret_cast<float2*>(pbuf + phi_bytes + st_off[u]) = make_float2(tc::tf32_lo(g.x, h.x), tc::tf32_lo(g.y, h.y));
                         }
                     }
                 } else if (st_active) {
@@ -454,7 +454,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                                                      (uint32_t)(((((rem >> 1) & 1) ^ ((n_st >> 2) & 1)) << 4) | ((rem & 1) << 3));
                                 const float2 h = make_float2(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y));
                                 *reinterpret_cast<float2*>(ph + off) = h;
-                                if (PASSES == 3) *reinterpret_cast<float2*>(ph + phi_bytes + off) = make_float2(g.x - h.x, g.y - h.y);
+                                if (PASSES == 3) *reinterpret_cast<float2*>(ph + phi_bytes + off) = make_float2(tc::tf32_lo(g.x, h.x), tc::tf32_lo(g.y, h.y));
                             }
                         }
                     }
@@ -489,7 +489,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     for (int j = 0; j < 8; ++j) {
                         const float g = gelu_f(fmaf(w, xv[j], bb));
                         hv[j] = tc::tf32_trunc(g);
-                        lv[j] = g - hv[j];
+                        lv[j] = tc::tf32_lo(g, hv[j]);
                     }
                     if (k_local < KC) {
                         float4* dh = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + goff);
@@ -515,7 +515,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         const float4 v = ah[idx];
                         const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
                         ah[idx] = h;
-                        al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        al[idx] = tc::tf32_lo4(v, h);
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();

@@ -105,7 +105,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
         const float hi = tc::tf32_trunc(v);
         const uint32_t off = (uint32_t)(x >> 5) * b_chunk + tc::sw128_kmajor_off(n, x & 31);
         *reinterpret_cast<float*>(B_hi + off) = hi;
-        if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = v - hi;
+        if (PASSES == 3) *reinterpret_cast<float*>(B_lo + off) = tc::tf32_lo(v, hi);
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
@@ -193,7 +193,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
                         const float4 v = ah[idx];
                         const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
                         ah[idx] = h;
-                        al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        al[idx] = tc::tf32_lo4(v, h);
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();

@@ -184,7 +184,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                         const uint32_t off = (uint32_t)j * chunk_bytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((piece ^ (row & 7)) << 4));
                         *reinterpret_cast<float4*>(sb + off) = h;
                         if (PASSES == 3)
-                            *reinterpret_cast<float4*>(sb + raw_bytes + off) = make_float4(g.x - h.x, g.y - h.y, g.z - h.z, g.w - h.w);
+                            *reinterpret_cast<float4*>(sb + raw_bytes + off) = tc::tf32_lo4(g, h);
                     }
                 }
                 tc::mbar_wait(full_bar + s, ph);                       // Q side landed
@@ -196,7 +196,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                             const float4 v = ah[idx];
                             const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
                             ah[idx] = h;
-                            al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                            al[idx] = tc::tf32_lo4(v, h);
                         }
                     }
                 }
@@ -215,7 +215,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                     const float4 v = ah[idx];
                     const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
                     ah[idx] = h;
-                    al[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    al[idx] = tc::tf32_lo4(v, h);
                 }
                 tc::fence_proxy_async_smem();
                 __syncwarp();

@@ -58,6 +58,21 @@ def main():
                 line["b200_kernels_vs_cpu_fp64"] = rel(y, ref64)
             except Exception as ex:  # noqa: BLE001
                 line["b200_kernels_error"] = repr(ex)[:200]
+        # the oracle's SpectralConv forward + backward (autograd through rfftn / irfftn) on CUDA vs on the CPU
+        try:
+            from oracle import spectral_oracle as so
+            x = torch.randn(2, 4, H, W)
+            w = torch.randn(4, 4, My, Mx, dtype=torch.complex64) * 0.3
+            res = {}
+            for dev in (["cpu", "cuda"] if torch.cuda.is_available() else ["cpu"]):
+                xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+                y = so.spectral_conv_dense(xd, wd, None, [My, Mx])
+                y.square().sum().backward()
+                res[dev] = (y.detach(), xd.grad, torch.view_as_real(wd.grad))
+            if "cuda" in res:
+                line["oracle_layer_cuda_vs_cpu(y,gx,gW)"] = [rel(a, b) for a, b in zip(res["cuda"], res["cpu"])]
+        except Exception as ex:  # noqa: BLE001
+            line["oracle_layer_error"] = repr(ex)[:200]
         print(json.dumps(line), flush=True)
 
 

@@ -67,7 +67,8 @@ def test_cfg2_full_tfno_model_fwd_loss_all_grads_and_graph_replay():
     assert abs(loss.item() - lo) / abs(lo) < TOL
     _check_grads(m, go, 2e-5)
     eager = {k: p.grad.clone() for k, p in m.named_parameters()}
-    # --- captured graph: fwd + MSE + bwd, replayed twice on fresh inputs
+    del out, loss          # drop the eager autograd graph: its AccumulateGrad nodes belong to the default stream
+    # --- captured graph: fwd + MSE + bwd, replayed twice
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
