@@ -621,7 +621,7 @@ def run_b200(args, wl, rank, world, local_rank):
     model = build_model(wl).to(dev)
     params = [p for p in model.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
-    sync = GradSync(params, world) if world > 1 else None
+    sync = GradSync(params, world, avg=not args.ddp_sum) if world > 1 else None
     B = wl["batch"]
     g = torch.Generator().manual_seed(1234 + rank)
     hx = torch.randn(B, wl["cin"], wl["H"], wl["W"], generator=g).pin_memory()
@@ -832,6 +832,7 @@ def main():
     ap.add_argument("--tc-mode", type=int, default=int(os.environ["SB200_TC_MODE"]) if os.environ.get("SB200_TC_MODE") else None,
                     help="0 = CUDA-core fp32, 1 = single-pass TF32 (parity ~1e-3), 3 = 3xTF32 (parity <= 1e-5; library default)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--ddp-sum", action="store_true", help="gradient all-reduce as SUM + scale instead of ReduceOp.AVG")
     ap.add_argument("--skip-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -1,0 +1,506 @@
+// General fp32 GEMM on the tcgen05 tensor cores (3xTF32 split for fp32 parity, or one TF32 pass):
+//
+//      D[m, n] = sum_k A(m, k) * B(n, k)      (+ bias[n], GELU / GELU'(aux) / residual in the epilogue)
+//
+// Either operand may be K-major (memory [rows][K], the contraction index contiguous: activations [tokens][C],
+// nn.Linear weights [out][in]) or MN-major (memory [K][rows]: the same arrays used transposed -- data gradients
+// need W^T, weight gradients contract over the token axis of two [tokens][C] arrays).  Both arrive by TMA exactly as
+// they lie in HBM: K-major tiles as {32 k, rows} boxes with the 128B swizzle (UMMA SWIZZLE_128B, K-major), MN-major
+// tiles as {32 rows, 32 k} boxes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (UMMA SWIZZLE_128B_BASE32B, the only
+// MN-major layout tcgen05 accepts for 32-bit operands).  No operand is ever transposed or copied in HBM.
+//
+// This is the FourCastNet token path of the reference (src/dlwpbench/models/fourcastnet/fourcastnet.py:42-57 ``Mlp``
+// = Linear -> GELU -> Linear, :283-293 PatchEmbed, :257 head) and the backward of those layers.
+//
+//   persistent CTAs over work units (m-tile 128, n-tile BN <= 128, k-split);
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-17: tf32 hi/lo split of landed chunks, then epilogue
+//   TMEM: two accumulator buffers; in the 3-pass mode each buffer holds TWO accumulators -- hi*hi products in
+//   one, the 2^-11 times smaller lo*hi + hi*lo corrections in the other -- so the chain of (truncating) tensor-core
+//   accumulations that the large terms go through is K/8 long instead of 3K/8; the epilogue adds the two.
+//   split-K (weight gradients: K = tokens): partial tiles go to a workspace, a second kernel reduces them in a
+//   fixed order (deterministic).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+extern "C" int sb200_get_tc_mode(void);
+
+namespace {
+
+constexpr int TG_WORKER_WARPS = 16;
+constexpr int TG_THREADS = 32 * (2 + TG_WORKER_WARPS);
+constexpr int TG_WTHREADS = 32 * TG_WORKER_WARPS;
+constexpr uint32_t TG_A_BYTES = 128 * 128;     // one K chunk of the A tile: 128 rows x 32 fp32 (either major)
+constexpr uint32_t TG_NLO = 2;                 // buffers for the tf32 "lo" parts (live from the split to the MMAs)
+
+struct TgParams {
+    int M, N, K;
+    int BN;                       // n-tile width (multiple of 16; of 32 when B is MN-major)
+    int a_mn, b_mn;               // 1 = MN-major operand
+    int mtiles, ntiles, nsplit;
+    int kc_total;                 // K chunks of 32 (last one zero-filled by TMA)
+    int kc_per_split;
+    uint32_t nunits;
+    int stages;
+    int R;                        // rotating "main" accumulators per TMEM buffer (chain of truncating accumulations = K/(8R))
+    // direct epilogue (nsplit == 1)
+    float* D; int64_t ldd;
+    const float* bias;            // [N] or NULL
+    int act;                      // 0 none | 1 GELU | 2 multiply by GELU'(aux[m][n])
+    const float* aux; int64_t ld_aux;
+    const float* resid; int64_t ld_res; int res_rows;   // residual row = m % res_rows when res_rows > 0 (pos_embed broadcast)
+    float* zout; int64_t ld_z;    // pre-activation store (act == 1) or NULL
+    // split-K epilogue (nsplit > 1): ws[split][M][N]
+    float* ws;
+    uint32_t idesc, tmem_cols;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const TgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S = p.stages, BN = p.BN;
+    const uint32_t b_bytes = (uint32_t)BN * 128;
+    const uint32_t stage_bytes = TG_A_BYTES + b_bytes;                 // [A chunk | B chunk]
+    uint8_t* St = base;
+    uint8_t* Lo = St + (uint32_t)S * stage_bytes;                      // [TG_NLO][stage_bytes]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(Lo + (PASSES == 3 ? TG_NLO * stage_bytes : 0));
+    uint64_t* split_bar = full_bar + S;
+    uint64_t* empty_bar = split_bar + S;
+    uint64_t* tfull_bar = empty_bar + S;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmapA);
+        tc::tma_prefetch_desc(&tmapB);
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(full_bar + s, 1);
+            tc::mbar_init(split_bar + s, TG_WORKER_WARPS);
+            tc::mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(tfull_bar + a, 1);
+            tc::mbar_init(tempty_bar + a, TG_WORKER_WARPS);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, p.tmem_cols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t first = blockIdx.x, stride = gridDim.x, nunits = p.nunits;
+    const uint32_t my_units = first < nunits ? (nunits - first + stride - 1) / stride : 0;
+    const uint32_t R = (uint32_t)p.R;
+    const uint32_t acc_cols = (uint32_t)BN * (R + (PASSES == 3 ? 1u : 0u));   // TMEM columns of one buffer: [main x R | corr]
+
+    // unit -> (m-tile, n-tile, k-split); n-tiles fastest so that concurrently running CTAs share the A rows in L2
+    auto decode = [&](uint32_t u, int& m0, int& n0, int& kc0, int& kcn, uint32_t& split) {
+        split = u % (uint32_t)p.nsplit;
+        const uint32_t t = u / (uint32_t)p.nsplit;
+        n0 = (int)(t % (uint32_t)p.ntiles) * BN;
+        m0 = (int)(t / (uint32_t)p.ntiles) * 128;
+        kc0 = (int)split * p.kc_per_split;
+        kcn = min(p.kc_per_split, p.kc_total - kc0);
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t it = 0; it < my_units; ++it) {
+                int m0, n0, kc0, kcn; uint32_t split;
+                decode(first + it * stride, m0, n0, kc0, kcn, split);
+                for (int kc = 0; kc < kcn; ++kc) {
+                    const int k0 = (kc0 + kc) * 32;
+                    tc::mbar_wait(empty_bar + s, ph ^ 1);
+                    uint8_t* dA = St + s * stage_bytes;
+                    uint8_t* dB = dA + TG_A_BYTES;
+                    tc::mbar_expect_tx(full_bar + s, stage_bytes);
+                    if (p.a_mn) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tc::tma_load_2d(dA + i * 4096, &tmapA, m0 + 32 * i, k0, full_bar + s);
+                    } else {
+                        tc::tma_load_2d(dA, &tmapA, k0, m0, full_bar + s);
+                    }
+                    if (p.b_mn) {
+                        for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(dB + j * 4096, &tmapB, n0 + 32 * j, k0, full_bar + s);
+                    } else {
+                        tc::tma_load_2d(dB, &tmapB, k0, n0, full_bar + s);
+                    }
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // K-major tile: 8-row atoms of 1024 B (SBO), k-step = +32 B.  MN-major tile: 32-row (mn) blocks 4096 B apart
+            // (LBO), 4-k-row atoms of 512 B (SBO), k-step (8 k rows) = +1024 B.
+            const uint32_t a_hi32 = p.a_mn ? tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B) : tc::desc_hi(1024, tc::LAYOUT_SW128);
+            const uint32_t b_hi32 = p.b_mn ? tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B) : tc::desc_hi(1024, tc::LAYOUT_SW128);
+            const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+            const uint32_t a_step = (p.a_mn ? 1024u : 32u) >> 4, b_step = (p.b_mn ? 1024u : 32u) >> 4;
+            uint32_t s = 0, ph = 0, lo = 0;
+            for (uint32_t it = 0; it < my_units; ++it) {
+                int m0, n0, kc0, kcn; uint32_t split;
+                decode(first + it * stride, m0, n0, kc0, kcn, split);
+                const uint32_t a = it & 1, tround = it >> 1;
+                tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
+                tc::tc_fence_after_sync();
+                const uint32_t d_buf = tmem_base + a * acc_cols;
+                const uint32_t d_corr = d_buf + R * (uint32_t)BN;
+                uint32_t started_c = 0, ra = 0;
+                for (int kc = 0; kc < kcn; ++kc) {
+                    const uint32_t d_main = d_buf + ra * (uint32_t)BN;
+                    uint32_t started = (uint32_t)kc >= R ? 1u : 0u;
+                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
+                    tc::tc_fence_after_sync();
+                    const uint32_t sa = tc::smem_u32(St + s * stage_bytes);
+                    const uint32_t la = tc::smem_u32(Lo + lo * stage_bytes);
+                    uint32_t ah = tc::desc_lo(sa, a_lbo), bh = tc::desc_lo(sa + TG_A_BYTES, b_lbo);
+                    uint32_t al = tc::desc_lo(la, a_lbo), bl = tc::desc_lo(la + TG_A_BYTES, b_lbo);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc::umma_tf32_lh(d_main, ah, a_hi32, bh, b_hi32, p.idesc, started);
+                        if (PASSES == 3) {
+                            tc::umma_tf32_lh(d_corr, al, a_hi32, bh, b_hi32, p.idesc, started_c);
+                            tc::umma_tf32_lh(d_corr, ah, a_hi32, bl, b_hi32, p.idesc, 1u);
+                        }
+                        started = 1; started_c = 1;
+                        ah += a_step; al += a_step; bh += b_step; bl += b_step;
+                    }
+                    tc::umma_commit(empty_bar + s);                    // frees the stage AND the lo buffer of this chunk
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                    if (++lo == TG_NLO) lo = 0;
+                    if (++ra == R) ra = 0;
+                }
+                tc::umma_commit(tfull_bar + a);
+            }
+        }
+    } else {
+        // ================= workers: split (unit it + 1), epilogue (unit it) =================
+        const int wk = warp - 2, wtid = tid - 64;
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cpart = wk >> 2;                          // column part it drains
+        const int ncol_part = (((BN + 3) / 4) + 15) & ~15;  // multiple of 16
+        const int c_begin = cpart * ncol_part;
+        const int c_end = min(BN, c_begin + ncol_part);
+        uint32_t sp_s = 0, sp_ph = 0, sp_lo = 0;
+        uint32_t lag_s = 0, lag_ph = 0, g = 0;
+        const int n4 = (int)(stage_bytes / 16);
+        auto split_unit = [&](uint32_t u) {
+            if (PASSES == 3) {
+                int m0, n0, kc0, kcn; uint32_t split;
+                decode(u, m0, n0, kc0, kcn, split);
+                for (int kc = 0; kc < kcn; ++kc) {
+                    if (g >= TG_NLO) {
+                        // lo[sp_lo] was last read by the MMAs of chunk g - TG_NLO: their commit is that chunk's empty phase
+                        tc::mbar_wait(empty_bar + lag_s, lag_ph);
+                        if (++lag_s == (uint32_t)S) { lag_s = 0; lag_ph ^= 1; }
+                    }
+                    ++g;
+                    tc::mbar_wait(full_bar + sp_s, sp_ph);
+                    float4* ah = reinterpret_cast<float4*>(St + sp_s * stage_bytes);
+                    float4* al = reinterpret_cast<float4*>(Lo + sp_lo * stage_bytes);
+                    for (int idx = wtid; idx < n4; idx += TG_WTHREADS) {
+                        const float4 v = ah[idx];
+                        const float4 h = make_float4(tc::tf32_rna(v.x), tc::tf32_rna(v.y), tc::tf32_rna(v.z), tc::tf32_rna(v.w));
+                        ah[idx] = h;
+                        al[idx] = tc::tf32_lo4(v, h);
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
+                    if (++sp_lo == TG_NLO) sp_lo = 0;
+                }
+            }
+        };
+        if (my_units > 0) split_unit(first);
+        for (uint32_t it = 0; it < my_units; ++it) {
+            if (it + 1 < my_units) split_unit(first + (it + 1) * stride);
+            int m0, n0, kc0, kcn; uint32_t split;
+            decode(first + it * stride, m0, n0, kc0, kcn, split);
+            const uint32_t a = it & 1, tround = it >> 1;
+            tc::mbar_wait(tfull_bar + a, tround & 1);
+            tc::tc_fence_after_sync();
+            const int m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * acc_cols;
+            const uint32_t nacc = min(R, (uint32_t)kcn);     // main accumulators this unit actually wrote
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t r[16];
+                float v[16];
+                if (PASSES == 3) {
+                    tc::tmem_ld_32x32b_x16(taddr + R * (uint32_t)BN + (uint32_t)c0, r);     // small corrections first
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                for (uint32_t q = 0; q < nacc; ++q) {
+                    tc::tmem_ld_32x32b_x16(taddr + q * (uint32_t)BN + (uint32_t)c0, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                const int n = n0 + c0;
+                if (!row_ok || n >= p.N) continue;
+                const bool full16 = n + 16 <= p.N;
+                if (p.nsplit > 1) {
+                    float* dst = p.ws + ((int64_t)split * p.M + m) * p.N + n;
+                    if (full16 && (p.N & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) dst[j] = v[j];
+                    }
+                    continue;
+                }
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                }
+                if (p.zout) {
+                    float* zd = p.zout + (int64_t)m * p.ld_z + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) zd[j] = v[j];
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = gelu_f(v[j]);
+                } else if (p.act == 2) {
+                    const float* ax = p.aux + (int64_t)m * p.ld_aux + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] *= gelu_grad_f(__ldg(ax + j));
+                }
+                if (p.resid) {
+                    const float* rs = p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(rs + j);
+                }
+                float* dst = p.D + (int64_t)m * p.ldd + n;
+                if (full16 && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) dst[j] = v[j];
+                }
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// out[m][n] = sum_s ws[s][m][n]  (fixed order: deterministic)
+__global__ void __launch_bounds__(256) tg_splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t ldd,
+                                                               int M, int N, int nsplit) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += ws[(int64_t)k * M * N + i];
+    out[(i / N) * ldd + (i % N)] = s;
+}
+
+// exact-fp32 CUDA-core GEMM (tc mode 0 and shapes / alignments the tensor-core kernel does not take): 64 x 64 tile,
+// 4 x 4 outputs per thread, generic strides for both majors; same epilogue as the tensor-core kernel.
+struct FgParams {
+    const float* A; int64_t a_sm, a_sk;        // element (m,k) at A[m*a_sm + k*a_sk]
+    const float* B; int64_t b_sn, b_sk;
+    int M, N, K;
+    float* D; int64_t ldd;
+    const float* bias; int act;
+    const float* aux; int64_t ld_aux;
+    const float* resid; int64_t ld_res; int res_rows;
+    float* zout; int64_t ld_z;
+};
+__global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
+    __shared__ float As[16][65], Bs[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+            // consecutive threads walk the contiguous axis of each operand
+            int r, k;
+            if (p.a_sk == 1) { k = idx & 15; r = idx >> 4; } else { r = idx & 63; k = idx >> 6; }
+            const int m = m0 + r, kk = k0 + k;
+            As[k][r] = (m < p.M && kk < p.K) ? __ldg(p.A + (int64_t)m * p.a_sm + (int64_t)kk * p.a_sk) : 0.f;
+            if (p.b_sk == 1) { k = idx & 15; r = idx >> 4; } else { r = idx & 63; k = idx >> 6; }
+            const int n = n0 + r, kb = k0 + k;
+            Bs[k][r] = (n < p.N && kb < p.K) ? __ldg(p.B + (int64_t)n * p.b_sn + (int64_t)kb * p.b_sk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j];
+            if (p.bias) v += __ldg(p.bias + n);
+            if (p.zout) p.zout[(int64_t)m * p.ld_z + n] = v;
+            if (p.act == 1) v = gelu_f(v);
+            else if (p.act == 2) v *= gelu_grad_f(__ldg(p.aux + (int64_t)m * p.ld_aux + n));
+            if (p.resid) v += __ldg(p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n);
+            p.D[(int64_t)m * p.ldd + n] = v;
+        }
+    }
+}
+
+// what the tensor-core kernel needs from an operand: 16-byte aligned base and row stride, at least one full box row
+bool tg_operand_ok(const float* ptr, int64_t ld, int mn_major, int rows, int K) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 3) != 0) return false;
+    (void)mn_major; (void)rows; (void)K;
+    return true;
+}
+
+struct TgGeom { int BN, R, ntiles, mtiles, nsplit, kc_total, kc_per_split, stages; size_t smem; };
+
+bool tg_geometry(int M, int N, int K, int b_mn, int passes, int want_split, TgGeom* g) {
+    if (M <= 0 || N <= 0 || K <= 0) return false;
+    g->mtiles = (M + 127) / 128;
+    g->kc_total = (K + 31) / 32;
+    // The tensor core's accumulation truncates, so the error of an accumulator grows with the number of MMAs chained
+    // into it (measured: 2.4e-6 at K = 1024 in one chain).  Policy: at most ~12 K-chunks (48 MMAs) per main accumulator;
+    // long contractions use 64-wide n-tiles, which leaves TMEM room for 3 rotating main accumulators per buffer.
+    int BN = N >= 128 ? 128 : (N + 15) / 16 * 16;
+    int nsplit = 1;
+    int kc_unit = g->kc_total;
+    if (want_split) {
+        const int tiles = ((N + 127) / 128) * g->mtiles;
+        const int sms = sb200_num_sms();
+        nsplit = (sms + tiles - 1) / tiles;                      // fill the machine ...
+        if (nsplit > g->kc_total / 8) nsplit = g->kc_total / 8;  // ... keeping at least 8 chunks per split
+        if (nsplit < 1) nsplit = 1;
+        kc_unit = (g->kc_total + nsplit - 1) / nsplit;
+    }
+    if (kc_unit > 12 && BN > 64) BN = 64;
+    if (b_mn) BN = (BN + 31) / 32 * 32;
+    if (BN > 128) BN = 128;
+    g->BN = BN;
+    g->ntiles = (N + BN - 1) / BN;
+    int R = 512 / (2 * BN) - (passes == 3 ? 1 : 0);
+    if (R > 4) R = 4;
+    if (R < 1) R = 1;
+    g->R = R;
+    if (want_split && kc_unit > 12 * R) {                        // still too long: more splits (more partial traffic, less error)
+        nsplit = (g->kc_total + 12 * R - 1) / (12 * R);
+    }
+    g->kc_per_split = (g->kc_total + nsplit - 1) / nsplit;
+    g->nsplit = (g->kc_total + g->kc_per_split - 1) / g->kc_per_split;
+    const size_t stage = TG_A_BYTES + (size_t)BN * 128;
+    const size_t fixed = 1024 + (passes == 3 ? TG_NLO * stage : 0) + 512;
+    int stages = 6;
+    while (stages > 2 && fixed + stages * stage > 220 * 1024) --stages;
+    if (fixed + stages * stage > 227 * 1024) return false;
+    g->stages = stages;
+    g->smem = fixed + stages * stage;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k) {
+    if (!split_k) return 0;
+    TgGeom g;
+    const int passes = sb200_get_tc_mode() == 1 ? 1 : 3;
+    if (!tg_geometry(M, N, K, b_mn, passes, 1, &g)) return 0;
+    return g.nsplit > 1 ? (int64_t)g.nsplit * M * N : 0;
+}
+
+extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
+                          int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
+                          const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int split_k,
+                          float* workspace, void* stream) {
+    SB_REQUIRE(A && B && D, "gemm: NULL operand");
+    SB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive size");
+    SB_REQUIRE(act >= 0 && act <= 2, "gemm: act must be 0, 1 or 2");
+    SB_REQUIRE(act != 2 || aux, "gemm: act 2 needs aux");
+    SB_REQUIRE(!split_k || (!bias && act == 0 && !resid && !zout), "gemm: split-K has no fused epilogue");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = sb200_get_tc_mode();
+    TgGeom g;
+    const int passes = mode == 1 ? 1 : 3;
+    bool tc_ok = mode != 0 && tg_operand_ok(A, lda, a_mn, M, K) && tg_operand_ok(B, ldb, b_mn, N, K) &&
+                 tg_geometry(M, N, K, b_mn, passes, split_k, &g);
+    if (tc_ok && g.nsplit > 1 && workspace == nullptr) tc_ok = false;
+    if (!tc_ok) {
+        FgParams f;
+        f.A = A; f.a_sm = a_mn ? 1 : lda; f.a_sk = a_mn ? lda : 1;
+        f.B = B; f.b_sn = b_mn ? 1 : ldb; f.b_sk = b_mn ? ldb : 1;
+        f.M = M; f.N = N; f.K = K; f.D = D; f.ldd = ldd; f.bias = bias; f.act = act; f.aux = aux; f.ld_aux = ld_aux;
+        f.resid = resid; f.ld_res = ld_res; f.res_rows = res_rows; f.zout = zout; f.ld_z = ld_z;
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        SB_REQUIRE(grid.y <= 65535, "gemm: M too large for the CUDA-core kernel");
+        sb_launch(ffma_gemm_kernel, grid, 256, 0, st, f);
+        SB_LAUNCH_CHECK();
+        return 0;
+    }
+    TgParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.BN = g.BN; p.a_mn = a_mn; p.b_mn = b_mn;
+    p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.nsplit = g.nsplit; p.kc_total = g.kc_total; p.kc_per_split = g.kc_per_split;
+    p.nunits = (uint32_t)g.mtiles * (uint32_t)g.ntiles * (uint32_t)g.nsplit;
+    p.stages = g.stages; p.R = g.R;
+    p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.aux = aux; p.ld_aux = ld_aux; p.resid = resid; p.ld_res = ld_res;
+    p.res_rows = res_rows;
+    p.zout = zout; p.ld_z = ld_z; p.ws = workspace;
+    p.idesc = tc::make_idesc_tf32(128, g.BN, a_mn, b_mn);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * g.BN * (g.R + (passes == 3 ? 1 : 0)))) cols <<= 1;
+    p.tmem_cols = cols;
+    CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmB, 0, sizeof(tmB));
+    // K-major: dims {K, rows}, box {32, rows of the tile}.  MN-major: dims {rows, K}, box {32, 32}.
+    if (a_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, 32, 32, 2)) return rc; }
+    else      { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, 32, 128, 1)) return rc; }
+    if (b_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, 32, 32, 2)) return rc; }
+    else      { if (int rc = sb200_make_tmap_2d_f32(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 4, 32, (uint32_t)g.BN, 1)) return rc; }
+    const unsigned nsm = (unsigned)sb200_num_sms();
+    const unsigned grid = p.nunits < nsm ? p.nunits : nsm;
+    if (passes == 3) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        sb_launch(tc_gemm_kernel<3>, grid, TG_THREADS, g.smem, st, tmA, tmB, p);
+    } else {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        sb_launch(tc_gemm_kernel<1>, grid, TG_THREADS, g.smem, st, tmA, tmB, p);
+    }
+    SB_LAUNCH_CHECK();
+    if (g.nsplit > 1) {
+        sb_launch(tg_splitk_reduce_kernel, (unsigned)ceil_div64((int64_t)M * N, 256), 256, 0, st, (const float*)workspace, D, ldd,
+                  M, N, g.nsplit);
+        SB_LAUNCH_CHECK();
+    }
+    return 0;
+}

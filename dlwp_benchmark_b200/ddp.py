@@ -30,7 +30,7 @@ _ALIGN = 64   # floats: 256-byte aligned views (vector stores / TMA-friendly des
 
 class GradSync:
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, bucket_bytes: int = 64 << 20,
-                 group=None, direct: Optional[bool] = None):
+                 group=None, direct: Optional[bool] = None, avg: Optional[bool] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.world = int(world_size)
         self.group = group
@@ -62,7 +62,8 @@ class GradSync:
         if b_start < off:
             self.buckets.append(self.flat[b_start:off])
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
-        self._avg = dev.type == "cuda"          # NCCL has ReduceOp.AVG; gloo does not
+        # NCCL has ReduceOp.AVG (gloo does not); avg=False = SUM followed by one scaling kernel
+        self._avg = (dev.type == "cuda") if avg is None else (bool(avg) and dev.type == "cuda")
 
     def detach(self):
         """Remove the sinks (parameters keep their last gradients as ordinary tensors)."""

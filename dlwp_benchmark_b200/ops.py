@@ -331,3 +331,82 @@ def lift_wgrad(g, x, w1, b1, want_bias: bool = True, out_w=None, out_b=None):
     _lib.check(lib.sb200_lift_wgrad(_p(g), _p(x), _p(w1), _p(b1), _p(gW2), _p(gb2), _p(ws), B, C, N, H * W, _stream()),
                "lift_wgrad")
     return gW2, gb2
+
+
+# ---------------------------------------------------------------------------------------------
+# channels-last token path (FourCastNet block remainder)
+# ---------------------------------------------------------------------------------------------
+def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = 0, aux=None,
+         resid=None, res_rows: int = 0, want_z: bool = False, out=None, split_k: bool = False):
+    """D[m,n] = sum_k A(m,k) B(n,k) on 2-D contiguous fp32 tensors.  ``a_mn=False``: A is [M,K] (K-major);
+    ``a_mn=True``: A is [K,M] (used transposed, MN-major); likewise B ([N,K] or [K,N]).  Epilogue: + bias[n];
+    z = pre-activation (returned when ``want_z``); act 1 = GELU, 2 = multiply by GELU'(aux[m,n]); + resid (row
+    ``m % res_rows`` when ``res_rows > 0``).  ``split_k``: K split over CTAs (weight gradients), no epilogue.
+    Returns D, or (D, z) when ``want_z``."""
+    _req(A, "A"); _req(B, "B")
+    assert A.dim() == 2 and B.dim() == 2
+    (K, M) = A.shape if a_mn else A.shape[::-1]
+    (Kb, N) = B.shape if b_mn else B.shape[::-1]
+    assert K == Kb, (A.shape, B.shape, a_mn, b_mn)
+    for t, n in ((bias, "bias"), (aux, "aux"), (resid, "resid")):
+        if t is not None:
+            _req(t, n)
+    dev = A.device
+    D = _out(out, (M, N), dev)
+    z = torch.empty(M, N, device=dev, dtype=torch.float32) if want_z else None
+    lib = _lib.load()
+    nws = lib.sb200_gemm_workspace(M, N, K, int(b_mn), int(split_k))
+    ws = torch.empty(nws, device=dev, dtype=torch.float32) if nws > 0 else None
+    _lib.check(lib.sb200_gemm(_p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(D), N, M, N, K, _p(bias), act,
+                              _p(aux), N, _p(resid), N, res_rows, _p(z), N, int(split_k), _p(ws), _stream()), "gemm")
+    return (D, z) if want_z else D
+
+
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float):
+    """x [T, C] -> (y [T, C], mean [T], rstd [T])"""
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    T, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(T, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().sb200_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), T, C,
+                                               ctypes.c_float(eps), _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, out_g=None, out_b=None):
+    """-> (dx [T, C] (+ dres), dgamma [C], dbeta [C])"""
+    for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (mean, "mean"), (rstd, "rstd")):
+        _req(t, n)
+    if dres is not None:
+        _req(dres, "dres")
+    T, C = x.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.sb200_layernorm_bwd_workspace(T, C), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    dg = _out(out_g, (C,), x.device)
+    db = _out(out_b, (C,), x.device)
+    _lib.check(lib.sb200_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dg), _p(db), _p(ws),
+                                       T, C, _stream()), "layernorm_bwd")
+    return dx, dg, db
+
+
+def colsum(a: torch.Tensor, out=None) -> torch.Tensor:
+    """a [T, N] -> [N]"""
+    _req(a, "a")
+    T, N = a.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.sb200_colsum_workspace(T, N), device=a.device, dtype=torch.float32)
+    o = _out(out, (N,), a.device)
+    _lib.check(lib.sb200_colsum(_p(a), N, _p(o), T, N, _p(ws), _stream()), "colsum")
+    return o
+
+
+def batch_sum(a: torch.Tensor, out=None) -> torch.Tensor:
+    """a [B, ...] -> [...]"""
+    _req(a, "a")
+    B = a.shape[0]
+    n = a.numel() // B
+    o = _out(out, tuple(a.shape[1:]), a.device)
+    _lib.check(_lib.load().sb200_batch_sum(_p(a), _p(o), B, n, _stream()), "batch_sum")
+    return o

@@ -226,6 +226,41 @@ int sb200_afno_blocklinear_wgrad(const float* a, const float* gout, const float*
 int sb200_gelu_fwd(const float* z, float* y, int64_t n, void* stream);
 int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* stream);
 
+/* ---- channels-last token path (FourCastNet block remainder: src/dlwpbench/models/fourcastnet/fourcastnet.py:42-57
+ * Mlp, :156-193 Block, :283-293 PatchEmbed / head; src/nsbench/models/fourcastnet/fourcastnet.py:129-165) ----------
+ *
+ * General fp32 GEMM on the tcgen05 tensor cores:  D[m][n] = sum_k A(m,k) B(n,k)  (row-major D, leading dim ldd).
+ *   a_mn = 0: A is K-major, element (m,k) at A[m*lda + k]  (activations [tokens][C], nn.Linear weights [out][in]);
+ *   a_mn = 1: A is MN-major, element (m,k) at A[k*lda + m] (the same arrays used transposed); likewise b_mn / ldb.
+ *   Epilogue (split_k == 0): + bias[n]; zout[m][n] = pre-activation (optional); act 1 = GELU, act 2 = multiply by
+ *   GELU'(aux[m][n]); + resid[(res_rows > 0 ? m % res_rows : m)][n]; replaces nn.Linear / F.gelu / the residual adds.
+ *   split_k != 0: the K range is split over CTAs (weight gradients: K = tokens), partials in `workspace`
+ *   (sb200_gemm_workspace floats) are reduced in a fixed order; no fused epilogue.
+ *   Bases and leading dimensions must be 16-byte multiples for the tensor-core path; anything else (and tc mode 0)
+ *   runs the exact-fp32 CUDA-core kernel. */
+int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k);
+int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
+               int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
+               const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int split_k,
+               float* workspace, void* stream);
+
+/* LayerNorm over the last (channel) axis of x [T, C] (biased variance, eps inside the sqrt: torch.nn.LayerNorm as
+ * built at fourcastnet.py:236 norm_layer = partial(nn.LayerNorm, eps=1e-6)); mean / rstd [T] are saved for the backward.
+ * Backward: dx (+ dres, a gradient that bypasses the norm, added in the same pass), dgamma, dbeta.
+ * workspace: sb200_layernorm_bwd_workspace(T, C) floats. */
+int sb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                        int64_t T, int C, float eps, void* stream);
+int64_t sb200_layernorm_bwd_workspace(int64_t T, int C);
+int sb200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        const float* dres, float* dx, float* dgamma, float* dbeta, float* workspace, int64_t T, int C,
+                        void* stream);
+
+/* out[n] = sum_t a[t*lda + n] (bias gradient of a token Linear); workspace: sb200_colsum_workspace(T, N) floats */
+int64_t sb200_colsum_workspace(int64_t T, int N);
+int sb200_colsum(const float* a, int64_t lda, float* out, int64_t T, int N, float* workspace, void* stream);
+/* out[i] = sum_b a[b*n + i] (pos_embed gradient) */
+int sb200_batch_sum(const float* a, float* out, int B, int64_t n, void* stream);
+
 /* out[c] = sum_{b,p} g[b,c,p] for g [B,C,HW]: the bias gradient of a SpectralConv that has no skip convolution
  * (with a skip the sum comes out of sb200_pointwise_wgrad).  workspace: sb200_channel_sum_workspace(B,C) floats. */
 int64_t sb200_channel_sum_workspace(int B, int C);

@@ -65,7 +65,7 @@ def main():
             w = torch.randn(4, 4, My, Mx, dtype=torch.complex64) * 0.3
             res = {}
             for dev in (["cpu", "cuda"] if torch.cuda.is_available() else ["cpu"]):
-                xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+                xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().clone().to(dev).requires_grad_(True)
                 y = so.spectral_conv_dense(xd, wd, None, [My, Mx])
                 y.square().sum().backward()
                 res[dev] = (y.detach(), xd.grad, torch.view_as_real(wd.grad))
