@@ -9,6 +9,7 @@ from .plan import Plan, get_plan  # noqa: F401
 from .spectral_conv import SpectralConv  # noqa: F401
 from .fno import FNO, TFNO, FNOBlocks, MLP  # noqa: F401
 from .afno import AFNO2D  # noqa: F401
+from .fourcastnet import AFNONet, AFNONetNS, Block, Mlp, PatchEmbed  # noqa: F401
 from .shim import install_neuralop_shim, patch_fourcastnet  # noqa: F401
 from .rollout import Rollout, sequence_forward, dlwp_sequence_forward, DLWPRollout  # noqa: F401
 

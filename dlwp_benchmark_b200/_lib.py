@@ -52,6 +52,7 @@ SIGNATURES = {
     "sb200_cl_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "sb200_cl_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "sb200_cl_rowidft_res": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _vp]),
+    "sb200_cl_rowidft_res2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "sb200_afno_blocklinear_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _vp]),
     "sb200_afno_blocklinear_dgrad": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "sb200_afno_blocklinear_wgrad_workspace": (_i64, [_i64, _i, _i, _i]),

@@ -41,60 +41,74 @@ def _bl_wgrad(a, gout, fwd_out, kind, ntok, nb, Ni, No):
     return gw, gb
 
 
+def afno_forward(x, w1c, b1c, w2c, b2c, nb: int, lam: float, frac: float, resid, resid2=None):
+    """The AFNO2D filter on x [B,h,w,C] (fp32, contiguous): returns (y, saved) with
+    y = synthesis(block_mlp(analysis(x))) + resid + resid2 (either may be None); ``saved`` feeds ``afno_backward``."""
+    B, h, w, C = x.shape
+    bs = C // nb
+    bsf = w1c.shape[-1]
+    plan = afno_plan(x.device, h, w, frac)
+    lib = _lib.load()
+    My, Mx = plan.My, plan.Mx
+    ntok = B * My * Mx
+    T = torch.empty(B, h, Mx, C, 2, device=x.device, dtype=torch.float32)
+    _lib.check(lib.sb200_cl_rowdft_fwd(plan.handle, 0, _p(x), _p(T), B * h, C, _stream()), "cl_rowdft_fwd")
+    Xh = torch.empty(B, My, Mx, C, 2, device=x.device, dtype=torch.float32)
+    _lib.check(lib.sb200_cl_coldft_fwd(plan.handle, 0, _p(T), _p(Xh), B, C, _stream()), "cl_coldft_fwd")
+    O1 = _bl_fwd(Xh, w1c, b1c, ntok, nb, bs, bsf, 1, 0.0)
+    Yh = _bl_fwd(O1, w2c, b2c, ntok, nb, bsf, bs, 2, lam)
+    Phi = torch.empty(B, h, Mx, C, 2, device=x.device, dtype=torch.float32)
+    _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 0, _p(Yh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
+    y = torch.empty_like(x)
+    _lib.check(lib.sb200_cl_rowidft_res2(plan.handle, 0, _p(Phi), _p(resid), _p(resid2), _p(y), B * h, C, _stream()),
+               "cl_rowidft_res")
+    return y, (plan, (B, h, w, C, nb, bs, bsf, ntok), Xh, O1, Yh)
+
+
+def afno_backward(saved, w1c, w2c, gy, resid_grad, need_gx: bool = True):
+    """Backward of ``afno_forward``: gy [B,h,w,C] -> (gx or None, gw1, gb1, gw2, gb2); ``resid_grad`` (gy when the filter
+    input was also its residual, else None) is added to gx inside the adjoint row synthesis."""
+    plan, (B, h, w, C, nb, bs, bsf, ntok), Xh, O1, Yh = saved
+    lib = _lib.load()
+    My, Mx = plan.My, plan.Mx
+    dev = gy.device
+    T = torch.empty(B, h, Mx, C, 2, device=dev, dtype=torch.float32)
+    _lib.check(lib.sb200_cl_rowdft_fwd(plan.handle, 1, _p(gy), _p(T), B * h, C, _stream()), "cl_rowdft_fwd")
+    gYh = torch.empty(B, My, Mx, C, 2, device=dev, dtype=torch.float32)
+    _lib.check(lib.sb200_cl_coldft_fwd(plan.handle, 1, _p(T), _p(gYh), B, C, _stream()), "cl_coldft_fwd")
+    gw2, gb2 = _bl_wgrad(O1, gYh, Yh, 2, ntok, nb, bsf, bs)
+    gO1 = _bl_dgrad(gYh, Yh, 2, w2c, ntok, nb, bsf, bs)
+    gw1, gb1 = _bl_wgrad(Xh, gO1, O1, 1, ntok, nb, bs, bsf)
+    gx = None
+    if need_gx:
+        gXh = _bl_dgrad(gO1, O1, 1, w1c, ntok, nb, bs, bsf)
+        Phi = torch.empty(B, h, Mx, C, 2, device=dev, dtype=torch.float32)
+        _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 1, _p(gXh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
+        gx = torch.empty_like(gy)
+        _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 1, _p(Phi), _p(resid_grad), _p(gx), B * h, C, _stream()),
+                   "cl_rowidft_res")
+    return gx, gw1, gb1, gw2, gb2
+
+
 class AFNO2DFn(torch.autograd.Function):
     @staticmethod
     @_lib.on_tensor_device
     def forward(ctx, x, w1, b1, w2, b2, num_blocks, lam, frac, add_residual=True):
         _req(x.contiguous(), "x")
         x = x.contiguous()
-        B, h, w, C = x.shape
-        nb = int(num_blocks)
-        bs = C // nb
-        bsf = w1.shape[-1]
-        plan = afno_plan(x.device, h, w, frac)
-        lib = _lib.load()
         w1c, b1c, w2c, b2c = (t.contiguous().float() for t in (w1, b1, w2, b2))
-        My, Mx = plan.My, plan.Mx
-        ntok = B * My * Mx
-        T = torch.empty(B, h, Mx, C, 2, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sb200_cl_rowdft_fwd(plan.handle, 0, _p(x), _p(T), B * h, C, _stream()), "cl_rowdft_fwd")
-        Xh = torch.empty(B, My, Mx, C, 2, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sb200_cl_coldft_fwd(plan.handle, 0, _p(T), _p(Xh), B, C, _stream()), "cl_coldft_fwd")
-        O1 = _bl_fwd(Xh, w1c, b1c, ntok, nb, bs, bsf, 1, 0.0)
-        Yh = _bl_fwd(O1, w2c, b2c, ntok, nb, bsf, bs, 2, lam)
-        Phi = torch.empty(B, h, Mx, C, 2, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 0, _p(Yh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
-        y = torch.empty_like(x)
-        _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 0, _p(Phi), _p(x) if add_residual else None, _p(y), B * h, C,
-                                            _stream()), "cl_rowidft_res")
+        y, saved = afno_forward(x, w1c, b1c, w2c, b2c, int(num_blocks), lam, frac, x if add_residual else None)
         ctx.add_residual = bool(add_residual)
-        ctx.plan, ctx.dims = plan, (B, h, w, C, nb, bs, bsf, ntok)
-        ctx.save_for_backward(Xh, O1, Yh, w1c, w2c)
+        ctx.saved_misc = saved[:2]
+        ctx.save_for_backward(saved[2], saved[3], saved[4], w1c, w2c)
         return y
 
     @staticmethod
     @_lib.on_tensor_device
     def backward(ctx, gy):
         Xh, O1, Yh, w1c, w2c = ctx.saved_tensors
-        plan = ctx.plan
-        B, h, w, C, nb, bs, bsf, ntok = ctx.dims
-        lib = _lib.load()
         gy = gy.contiguous().float()
-        My, Mx = plan.My, plan.Mx
-        dev = gy.device
-        T = torch.empty(B, h, Mx, C, 2, device=dev, dtype=torch.float32)
-        _lib.check(lib.sb200_cl_rowdft_fwd(plan.handle, 1, _p(gy), _p(T), B * h, C, _stream()), "cl_rowdft_fwd")
-        gYh = torch.empty(B, My, Mx, C, 2, device=dev, dtype=torch.float32)
-        _lib.check(lib.sb200_cl_coldft_fwd(plan.handle, 1, _p(T), _p(gYh), B, C, _stream()), "cl_coldft_fwd")
-        gw2, gb2 = _bl_wgrad(O1, gYh, Yh, 2, ntok, nb, bsf, bs)
-        gO1 = _bl_dgrad(gYh, Yh, 2, w2c, ntok, nb, bsf, bs)
-        gw1, gb1 = _bl_wgrad(Xh, gO1, O1, 1, ntok, nb, bs, bsf)
-        gx = None
-        if ctx.needs_input_grad[0]:
-            gXh = _bl_dgrad(gO1, O1, 1, w1c, ntok, nb, bs, bsf)
-            Phi = torch.empty(B, h, Mx, C, 2, device=dev, dtype=torch.float32)
-            _lib.check(lib.sb200_cl_coldft_inv(plan.handle, 1, _p(gXh), _p(Phi), B, C, _stream()), "cl_coldft_inv")
-            gx = torch.empty_like(gy)
-            _lib.check(lib.sb200_cl_rowidft_res(plan.handle, 1, _p(Phi), _p(gy) if ctx.add_residual else None, _p(gx),
-                                                B * h, C, _stream()), "cl_rowidft_res")
+        saved = (*ctx.saved_misc, Xh, O1, Yh)
+        gx, gw1, gb1, gw2, gb2 = afno_backward(saved, w1c, w2c, gy, gy if ctx.add_residual else None,
+                                               need_gx=ctx.needs_input_grad[0])
         return gx, gw1, gb1, gw2, gb2, None, None, None, None

@@ -106,7 +106,8 @@ extern "C" int sb200_cl_rowdft_fwd(sb200_plan_t p, int pass, const float* x, flo
 template <int KG, int CPT>
 __global__ void __launch_bounds__(128)
 cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__ tab /*[Mx][W]*/,
-                      const float* __restrict__ resid, float* __restrict__ y, int W, int Mx, int C, int accumulate) {
+                      const float* __restrict__ resid, const float* __restrict__ resid2, float* __restrict__ y, int W, int Mx,
+                      int C, int accumulate) {
     extern __shared__ float2 tsm[];     // [KG][W]
     const int64_t row = blockIdx.x;
     const int c0 = (blockIdx.y * 128 + threadIdx.x) * CPT;
@@ -145,6 +146,10 @@ cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__
             if (CPT == 2) { const float2 r = __ldg(reinterpret_cast<const float2*>(resid + off)); o[0] = r.x; o[CPT - 1] = r.y; }
             else o[0] = __ldg(resid + off);
         }
+        if (resid2 != nullptr && blockIdx.z == 0) {      // second skip connection of the FourCastNet block (double_skip)
+            if (CPT == 2) { const float2 r = __ldg(reinterpret_cast<const float2*>(resid2 + off)); o[0] += r.x; o[CPT - 1] += r.y; }
+            else o[0] += __ldg(resid2 + off);
+        }
 #pragma unroll
         for (int k = 0; k < KG; ++k) {
             const float2 t = tsm[k * W + w];
@@ -160,20 +165,26 @@ cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__
 }
 
 template <int KG, int CPT>
-static int launch_cl_rowidft(const float2* Phi, const float2* tab, const float* resid, float* y, int64_t rows, int W,
-                             int Mx, int C, cudaStream_t st) {
+static int launch_cl_rowidft(const float2* Phi, const float2* tab, const float* resid, const float* resid2, float* y,
+                             int64_t rows, int W, int Mx, int C, cudaStream_t st) {
     const size_t smem = (size_t)KG * W * sizeof(float2);
     SB_REQUIRE(smem <= 160 * 1024, "cl_rowidft_res: W=%d too large", W);
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(cl_rowidft_res_kernel<KG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)rows, (unsigned)((C / CPT + 127) / 128), 1);
-    sb_launch(cl_rowidft_res_kernel<KG, CPT>, grid, 128, smem, st, Phi, tab, resid, y, W, Mx, C, 0);
+    sb_launch(cl_rowidft_res_kernel<KG, CPT>, grid, 128, smem, st, Phi, tab, resid, resid2, y, W, Mx, C, 0);
     SB_LAUNCH_CHECK();
     return 0;
 }
 
+extern "C" int sb200_cl_rowidft_res2(sb200_plan_t p, int pass, const float* Phi, const float* resid, const float* resid2,
+                                     float* y, int64_t rows, int C, void* stream);
 extern "C" int sb200_cl_rowidft_res(sb200_plan_t p, int pass, const float* Phi, const float* resid, float* y,
                                     int64_t rows, int C, void* stream) {
+    return sb200_cl_rowidft_res2(p, pass, Phi, resid, nullptr, y, rows, C, stream);
+}
+extern "C" int sb200_cl_rowidft_res2(sb200_plan_t p, int pass, const float* Phi, const float* resid, const float* resid2,
+                                     float* y, int64_t rows, int C, void* stream) {
     SB_REQUIRE(p && Phi && y, "cl_rowidft_res: NULL argument");
     SB_REQUIRE(pass == 0 || pass == 1, "cl_rowidft_res: pass must be 0 or 1");
     SB_REQUIRE(rows < (1LL << 31), "cl_rowidft_res: too many rows");
@@ -184,13 +195,13 @@ extern "C" int sb200_cl_rowidft_res(sb200_plan_t p, int pass, const float* Phi, 
     const int W = p->W, Mx = p->Mx;
     SB_REQUIRE(Mx <= 33, "cl_rowidft_res: Mx=%d > 33 retained columns is not implemented", Mx);
     if (C % 2 == 0 && Mx <= 17) {
-        if (Mx <= 5) return launch_cl_rowidft<5, 2>(Ph, tab, resid, y, rows, W, Mx, C, st);
-        if (Mx <= 9) return launch_cl_rowidft<9, 2>(Ph, tab, resid, y, rows, W, Mx, C, st);
-        return launch_cl_rowidft<17, 2>(Ph, tab, resid, y, rows, W, Mx, C, st);
+        if (Mx <= 5) return launch_cl_rowidft<5, 2>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
+        if (Mx <= 9) return launch_cl_rowidft<9, 2>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
+        return launch_cl_rowidft<17, 2>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
     }
-    if (Mx <= 9) return launch_cl_rowidft<9, 1>(Ph, tab, resid, y, rows, W, Mx, C, st);
-    if (Mx <= 17) return launch_cl_rowidft<17, 1>(Ph, tab, resid, y, rows, W, Mx, C, st);
-    return launch_cl_rowidft<33, 1>(Ph, tab, resid, y, rows, W, Mx, C, st);
+    if (Mx <= 9) return launch_cl_rowidft<9, 1>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
+    if (Mx <= 17) return launch_cl_rowidft<17, 1>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
+    return launch_cl_rowidft<33, 1>(Ph, tab, resid, resid2, y, rows, W, Mx, C, st);
 }
 
 // ======================================================================================

@@ -42,6 +42,14 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
                            uint32_t box0, uint32_t box1, int swizzle) {
     std::call_once(g_encode_once, load_encode);
     SB_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    {
+        // cuTensorMapEncodeTiled is a DRIVER call and needs a current context.  A thread that has made no runtime call
+        // yet (the autograd engine's worker when torch's caching allocator served every allocation) has none:
+        // cudaSetDevice on the current device binds the primary context (CUDA 12) and is legal during graph capture.
+        int dev = 0;
+        SB_CHECK_CUDA(cudaGetDevice(&dev));
+        SB_CHECK_CUDA(cudaSetDevice(dev));
+    }
     cuuint64_t gdim[2] = {dim0, dim1};
     cuuint64_t gstr[1] = {stride1_bytes};
     cuuint32_t box[2] = {box0, box1};

@@ -36,8 +36,12 @@ def install_neuralop_shim(force: bool = False):
     return pkg
 
 
-def patch_fourcastnet(module):
-    """Swap the reference module's AFNO2D for the B200 one (same ctor / parameters / forward)."""
+def patch_fourcastnet(module, blocks: bool = True):
+    """Swap the reference module's AFNO2D (and, with ``blocks``, its Block / Mlp / PatchEmbed) for the B200 ones: same
+    constructors, parameters and forward, so the reference's own ``AFNONet`` builds on them unchanged."""
     from .afno import AFNO2D
+    from . import fourcastnet as f
     module.AFNO2D = AFNO2D
+    if blocks:
+        module.Block, module.Mlp, module.PatchEmbed = f.Block, f.Mlp, f.PatchEmbed
     return module

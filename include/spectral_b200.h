@@ -204,6 +204,8 @@ int sb200_cl_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, 
 int sb200_cl_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, int B, int C, void* stream);
 /* Phi [rows,Mx,C] (+ resid [rows,W,C] or NULL) -> y [rows,W,C]; replaces the w-axis half of irfft2
  * and the residual add `x + bias` (:126) */
+int sb200_cl_rowidft_res2(sb200_plan_t plan, int pass, const float* Phi, const float* resid, const float* resid2,
+                          float* y, int64_t rows, int C, void* stream);   /* + a second residual (Block double_skip, :186-188) */
 int sb200_cl_rowidft_res(sb200_plan_t plan, int pass, const float* Phi, const float* resid, float* y,
                          int64_t rows, int C, void* stream);
 /* Block-diagonal complex linear layer: out[t,n,o] = act( sum_i in[t,n,i] * W[n,i,o] + b[n,o] ),

@@ -91,3 +91,46 @@ def afno2d_explicit(x, w1, b1, w2, b2, num_blocks: int, sparsity_threshold: floa
     Phi = torch.einsum("ky,bkqc->byqc", EH.conj(), Yh)
     y = s * torch.einsum("byqc,qx,q->byxc", Phi, EW.conj(), wk.to(cd)).real
     return y + x
+
+
+# --------------------------------------------------------------------------------------
+# FourCastNet block remainder: restatement of the reference's ``Block`` / ``Mlp`` / ``PatchEmbed`` /
+# ``AFNONet.forward_features`` + head in plain torch on a reference-layout state_dict.  PINNED like the filter:
+# tests/golden/fcn_*.npz come from the reference's own classes (oracle/make_golden.py::make_fourcastnet).
+# --------------------------------------------------------------------------------------
+def block_forward(sd, prefix, x, num_blocks, sparsity_threshold=0.01, hard_thresholding_fraction=1.0, double_skip=True,
+                  eps=1e-6):
+    """reference ``Block.forward`` (src/dlwpbench/models/fourcastnet/fourcastnet.py:181-193); x [B,h,w,C]."""
+    g = lambda k: sd[prefix + k].to(x.dtype)
+    C = x.shape[-1]
+    residual = x
+    h = F.layer_norm(x, (C,), g("norm1.weight"), g("norm1.bias"), eps)
+    h = afno2d_fft(h, g("filter.w1"), g("filter.b1"), g("filter.w2"), g("filter.b2"), num_blocks, sparsity_threshold,
+                   hard_thresholding_fraction)
+    if double_skip:
+        h = h + residual
+        residual = h
+    h = F.layer_norm(h, (C,), g("norm2.weight"), g("norm2.bias"), eps)
+    h = F.linear(F.gelu(F.linear(h, g("mlp.fc1.weight"), g("mlp.fc1.bias"))), g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    return h + residual
+
+
+def afnonet_step(sd, x_t, patch_size, depth, num_blocks, use_pos_embed=True, sparsity_threshold=0.01,
+                 hard_thresholding_fraction=1.0, prefix=""):
+    """PatchEmbed (+ pos_embed) -> blocks -> head -> pixel shuffle (reference :283-293, :343-353); x_t [B,Cin,H,W]
+    -> [B,Cout,H,W] (the network proper, without the ``prognostic_t[:, -1] +`` residual of the loop)."""
+    g = lambda k: sd[prefix + k].to(x_t.dtype)
+    p1, p2 = patch_size
+    B, _, H, W = x_t.shape
+    h, w = H // p1, W // p2
+    t = F.conv2d(x_t, g("patch_embed.proj.weight"), g("patch_embed.proj.bias"), stride=(p1, p2)).flatten(2).transpose(1, 2)
+    if use_pos_embed:
+        t = t + g("pos_embed")
+    E = t.shape[-1]
+    t = t.reshape(B, h, w, E)
+    for i in range(depth):
+        t = block_forward(sd, f"{prefix}blocks.{i}.", t, num_blocks, sparsity_threshold, hard_thresholding_fraction)
+    y = F.linear(t, g("head.weight"))
+    c_out = y.shape[-1] // (p1 * p2)
+    y = y.reshape(B, h, w, p1, p2, c_out).permute(0, 5, 1, 3, 2, 4)
+    return y.reshape(B, c_out, h * p1, w * p2)

@@ -142,7 +142,90 @@ def make_fno():
         print("wrote", name)
 
 
+def _dump_module(path, m, inputs, out, gout, extra):
+    """inputs: dict name -> tensor (requires_grad where a gradient is wanted); runs backward and writes everything"""
+    out.backward(gout)
+    d = {"y": out.detach().numpy(), "gy": gout.numpy(), **extra}
+    for k, v in inputs.items():
+        d["in:" + k] = v.detach().numpy()
+        if v.grad is not None:
+            d["gin:" + k] = v.grad.numpy()
+    for k, v in m.state_dict().items():
+        d["p:" + k] = v.detach().numpy()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            d["g:" + k] = p.grad.numpy()
+    np.savez_compressed(path, **d)
+
+
+def make_fourcastnet():
+    """FourCastNet block remainder from the reference's own classes: one ``Block`` (both flavours share
+    it), a depth-2 dlwpbench ``AFNONet`` (single step: the reference loop raises for T > context_size + 1, see
+    spectral_oracle.dlwp_rollout) and a depth-2 nsbench ``AFNONet`` with patch (2,2), context 2, teacher forcing."""
+    from functools import partial
+    ref = load_reference_fourcastnet("dlwpbench")
+    torch.manual_seed(1234)
+    blk = ref.Block(dim=32, mlp_ratio=4., norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_blocks=4)
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.startswith("filter."):
+                p.mul_(12.0)                       # exercise ReLU / softshrink on both sides of their kinks
+            elif "norm" in n:
+                p.add_(0.3 * torch.randn_like(p))  # non-trivial LayerNorm affine parameters
+            else:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(2, 8, 16, 32, requires_grad=True)
+    y = blk(x)
+    _dump_module(os.path.join(OUT, "fcn_block.npz"), blk, {"x": x}, y, torch.randn_like(y),
+                 {"meta": np.array([2, 8, 16, 32, 4], dtype=np.int64)})
+    print("wrote fcn_block")
+
+    torch.manual_seed(4321)
+    net = ref.AFNONet(img_height=16, img_width=32, patch_size=(1, 1), constant_channels=4, prescribed_channels=1,
+                      prognostic_channels=8, embed_dim=32, depth=2, mlp_ratio=4., num_blocks=4, context_size=1,
+                      use_pos_embed=True)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if ".filter." in n:
+                p.mul_(12.0)
+            elif n.endswith("bias") or "norm" in n:
+                p.add_(0.2 * torch.randn_like(p))
+            elif "mlp" in n or "head" in n:
+                p.mul_(6.0)
+    B, T = 2, 2
+    c = torch.randn(B, 1, 4, 16, 32)
+    pr = torch.randn(B, T, 1, 16, 32)
+    pg = torch.randn(B, T, 8, 16, 32)
+    y = net(constants=c, prescribed=pr, prognostic=pg)
+    _dump_module(os.path.join(OUT, "fcn_dlwp_net.npz"), net, {"constants": c, "prescribed": pr, "prognostic": pg}, y,
+                 torch.randn_like(y), {"meta": np.array([16, 32, 1, 1, 4, 1, 8, 32, 2, 4, 1], dtype=np.int64)})
+    print("wrote fcn_dlwp_net")
+
+    refn = load_reference_fourcastnet("nsbench")
+    torch.manual_seed(999)
+    net = refn.AFNONet(img_height=16, img_width=16, patch_size=(2, 2), in_chans=2, out_chans=2, embed_dim=32, depth=2,
+                       mlp_ratio=4., num_blocks=4, context_size=2)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if ".filter." in n:
+                p.mul_(12.0)
+            elif n.endswith("bias") or "norm" in n:
+                p.add_(0.2 * torch.randn_like(p))
+            elif "mlp" in n or "head" in n:
+                p.mul_(6.0)
+    x = torch.randn(2, 5, 2, 16, 16)
+    y = net(x, teacher_forcing_steps=3)
+    _dump_module(os.path.join(OUT, "fcn_ns_net.npz"), net, {"x": x}, y, torch.randn_like(y),
+                 {"meta": np.array([16, 16, 2, 2, 2, 2, 32, 2, 4, 2, 3], dtype=np.int64)})
+    print("wrote fcn_ns_net")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    make_afno()
-    make_fno()
+    which = sys.argv[1:] or ["afno", "fno", "fcn"]
+    if "afno" in which:
+        make_afno()
+    if "fno" in which:
+        make_fno()
+    if "fcn" in which:
+        make_fourcastnet()

@@ -124,3 +124,42 @@ def test_reference_size_labels():
     for hc, m in want.items():
         got = so.fno_param_count((12, 12), 10, hc, 256, 256, 1, 4) / 1e6
         assert abs(got - m) < 6e-4, (hc, got)
+
+
+# --------------------------------------------------------------------------------------
+# FourCastNet block remainder (row f3): oracle restatement vs vectors from the reference's own classes
+# --------------------------------------------------------------------------------------
+def _fcn(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    sd = {k[2:]: torch.tensor(d[k]) for k in d.files if k.startswith("p:")}
+    return d, sd
+
+
+def test_fcn_block_oracle_matches_reference_class(golden_dir):
+    from oracle import afno_oracle as ao
+    d, sd = _fcn(golden_dir, "fcn_block")
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x = torch.tensor(d["in:x"]).double().requires_grad_(True)
+    y = ao.block_forward(leaves, "", x, int(d["meta"][4]))
+    y.backward(torch.tensor(d["gy"]).double())
+    assert rel_l2(y, torch.tensor(d["y"])) < 2e-6          # the vectors are fp32 outputs of the reference
+    assert rel_l2(x.grad, torch.tensor(d["gin:x"])) < 5e-6
+    for k, v in leaves.items():
+        assert rel_l2(v.grad, torch.tensor(d["g:" + k])) < 2e-5, k
+
+
+def test_fcn_dlwp_net_oracle_matches_reference_class(golden_dir):
+    from oracle import afno_oracle as ao
+    d, sd = _fcn(golden_dir, "fcn_dlwp_net")
+    H, W, p1, p2, cc, cp, cg, E, depth, nb, ctx = [int(v) for v in d["meta"]]
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    c, pr, pg = (torch.tensor(d["in:" + k]).double() for k in ("constants", "prescribed", "prognostic"))
+    step = lambda x_t: ao.afnonet_step(leaves, x_t, (p1, p2), depth, nb)
+    x_t = torch.cat([c[:, 0], pr[:, 0:1].flatten(1, 2), pg[:, 0:1].flatten(1, 2)], dim=1)
+    y = (pg[:, 0] + step(x_t)).unsqueeze(1)
+    y.backward(torch.tensor(d["gy"]).double())
+    assert rel_l2(y, torch.tensor(d["y"])) < 2e-6
+    for k, v in leaves.items():
+        if "g:" + k in d.files:
+            assert rel_l2(v.grad, torch.tensor(d["g:" + k])) < 3e-5, k
+    assert "g:norm.weight" not in d.files                    # the final norm is unused by the reference forward
