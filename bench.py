@@ -41,9 +41,12 @@ WORKLOADS = {
     "cfg3": dict(desc="FNO2D 256x256 in1 width64 modes32 L4 batch64/GPU (BASELINE configs[2])",
                  n_modes=(32, 32), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=256, W=256, batch=64, rank=0.0),
     # the two below are not train-step lines of the FNO metric: they have their own metric names
-    "cfg4": dict(desc="FourCastNet AFNO2D filter stack: 8 layers x AFNO2D(embed 256, 8 blocks) on 32x64 tokens, batch 16/GPU "
-                      "(BASELINE configs[3]; LayerNorm / token MLP of the FourCastNet block are SURVEY rows f3, not built)",
-                 kind="afno", embed=256, nb=8, depth=8, H=32, W=64, batch=16),
+    "cfg4": dict(desc="FourCastNet AFNONet (dlwpbench flavour): 32x64 grid, patch 1x1, 4 const + 1 prescribed + 8 prognostic = 13 in / "
+                      "8 out channels, embed 256, depth 8, num_blocks 8, mlp_ratio 4, pos_embed, batch 16/GPU, single step "
+                      "(BASELINE configs[3])",
+                 kind="afnonet", embed=256, nb=8, depth=8, H=32, W=64, batch=16, cin=13, cout=8),
+    "cfg4f": dict(desc="AFNO2D filter stack only: 8 x AFNO2D(embed 256, 8 blocks) on 32x64 tokens, batch 16/GPU",
+                  kind="afno", embed=256, nb=8, depth=8, H=32, W=64, batch=16),
     "cfg5": dict(desc="FNO2D closed-loop rollout 128x128 in1 width64 modes32 L4, 512 initial conditions/GPU x 100 steps "
                       "(BASELINE configs[4])",
                  kind="rollout", n_modes=(32, 32), hidden=64, cin=1, cout=1, L=4, lift=256, proj=256, H=128, W=128,
@@ -447,7 +450,53 @@ def _timed(step, steps, warmup, world, local_rank, dist):
 # ----------------------------------------------------------------------------------------
 # cfg4: AFNO2D filter stack (train step), cfg5: closed-loop rollout (inference)
 # ----------------------------------------------------------------------------------------
+def _tf_peak():
+    """dense TF32 tensor peak used for the GEMM-bound stages: half of the measured dense bf16 rate"""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]) / 2, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate)"
+    except Exception:  # noqa: BLE001
+        return 1100.0 / 2, "fallback: nominal 1.1 PFLOP/s dense tf32 (B200_PROFILING.md) / 2"
+
+
+def cpu_afnonet_rate(wl, steps=2):
+    """cfg4 on the host cores: one train step (fwd + MSE + bwd) of the oracle restatement of the reference AFNONet
+    (oracle/afno_oracle.py, pinned to the reference classes by tests/golden/fcn_*.npz), bounded batch."""
+    import torch
+    from oracle import afno_oracle as ao
+    import dlwp_benchmark_b200 as pkg
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    net = _build_afnonet(pkg, wl)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    Bs = max(1, min(wl["batch"], 4))
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(Bs, wl["cin"], wl["H"], wl["W"], generator=g)
+    y = torch.randn(Bs, wl["cout"], wl["H"], wl["W"], generator=g)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        out = ao.afnonet_step(sd, x, (1, 1), wl["depth"], wl["nb"])
+        torch.nn.functional.mse_loss(out, y).backward()
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": Bs / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"batch {Bs} of {wl['batch']}, fwd+MSE+bwd, {steps} steps after 1 warm-up ({(steps + 1) * dt:.1f} s of CPU "
+                      "work), oracle restatement pinned to the reference classes"}
+
+
+def _build_afnonet(pkg, wl):
+    return pkg.AFNONet(img_height=wl["H"], img_width=wl["W"], patch_size=(1, 1), constant_channels=4, prescribed_channels=1,
+                       prognostic_channels=wl["cout"], embed_dim=wl["embed"], depth=wl["depth"], mlp_ratio=4.,
+                       num_blocks=wl["nb"], context_size=1, use_pos_embed=True)
+
+
 def run_afno(args, wl, rank, world, local_rank):
+    """cfg4: train step of the dlwpbench FourCastNet (AFNONet) -- or, for ``cfg4f``, of the bare AFNO2D filter stack."""
     import torch
     import torch.distributed as dist
     import dlwp_benchmark_b200 as pkg
@@ -458,25 +507,40 @@ def run_afno(args, wl, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234)
-    model = torch.nn.Sequential(*[pkg.AFNO2D(wl["embed"], num_blocks=wl["nb"]) for _ in range(wl["depth"])]).to(dev)
+    full = wl["kind"] == "afnonet"
+    B, H, W, C = wl["batch"], wl["H"], wl["W"], wl["embed"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    if full:
+        model = _build_afnonet(pkg, wl).to(dev)
+        host = [torch.randn(B, 1, 4, H, W, generator=g).pin_memory(), torch.randn(B, 2, 1, H, W, generator=g).pin_memory(),
+                torch.randn(B, 2, wl["cout"], H, W, generator=g).pin_memory()]
+        dv = [t.to(dev) for t in host]
+
+        def fwd_loss():
+            out = model(constants=dv[0], prescribed=dv[1], prognostic=dv[2])      # [B, 1, 8, H, W]
+            return torch.nn.functional.mse_loss(out, dv[2][:, 1:])
+    else:
+        model = torch.nn.Sequential(*[pkg.AFNO2D(C, num_blocks=wl["nb"]) for _ in range(wl["depth"])]).to(dev)
+        host = [torch.randn(B, H, W, C, generator=g).pin_memory(), torch.randn(B, H, W, C, generator=g).pin_memory()]
+        dv = [t.to(dev) for t in host]
+
+        def fwd_loss():
+            return torch.nn.functional.mse_loss(model(dv[0]), dv[1])
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     sync = GradSync(params, world) if world > 1 else None
-    B, H, W, C = wl["batch"], wl["H"], wl["W"], wl["embed"]
-    g = torch.Generator().manual_seed(1234 + rank)
-    hx = torch.randn(B, H, W, C, generator=g).pin_memory()
-    hy = torch.randn(B, H, W, C, generator=g).pin_memory()
-    x, y = hx.to(dev), hy.to(dev)
     loss_buf = torch.zeros((), device=dev)
     hloss = torch.zeros((), pin_memory=True)
     lib = _lib.load()
+    if args.tc_mode is not None:
+        lib.sb200_set_tc_mode(args.tc_mode)
 
     def step_eager():
         if sync:
             sync.zero()
         else:
             opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(model(x), y)
+        loss = fwd_loss()
         loss.backward()
         loss_buf.copy_(loss.detach())
         if sync:
@@ -489,24 +553,30 @@ def run_afno(args, wl, rank, world, local_rank):
     launches = int(lib.sb200_kernel_launches() - n0)
     step = step_eager
     graph = None
-    if not args.no_graph and sync is None:
+    if not args.no_graph:
         s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
                 step_eager()
         torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
-        opt.zero_grad(set_to_none=True)
+        if sync is None:
+            opt.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss = torch.nn.functional.mse_loss(model(x), y)
+            if sync:
+                sync.zero()
+            loss = fwd_loss()
             loss.backward()
             loss_buf.copy_(loss.detach())
+            if sync:
+                sync.allreduce()
             opt.step()
         step = graph.replay
     t_dev, clocks = _timed(step, args.steps, args.warmup, world, local_rank, dist)
 
     def step_e2e():
-        x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
+        for d, hsrc in zip(dv, host):
+            d.copy_(hsrc, non_blocking=True)
         step()
         hloss.copy_(loss_buf, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -518,24 +588,50 @@ def run_afno(args, wl, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = _peak()
         P = B * H * W * C
-        alg = 20 * P * wl["depth"]        # per layer: fwd 8P (read x, write y) + bwd 12P (read gy, x for the masks/weights, write gx)
-        line = {"metric": "AFNO2D filter stack train samples/s (fwd+bwd)", "value": B * world * args.steps / t_dev,
+        per = t_dev / args.steps
+        if full:
+            # GEMM-bound: the token MLP (2 Linear layers of C x 4C, fwd + dgrad + wgrad = 3 x 2 GEMMs) dominates the flops;
+            # algorithmic flops = fp32 GEMM flops (2MNK), NOT multiplied by the 3 tf32 passes of the parity mode
+            T = B * H * W
+            mlp = 6 * 2 * T * C * 4 * C
+            bs = C // wl["nb"]
+            kept = (H // 2 + 1)
+            ntok_f = B * min(2 * kept, H) * min(kept, W // 2 + 1)
+            afno = 3 * (2 * 8 * ntok_f * wl["nb"] * bs * bs) + 3 * 2 * (4 * P * min(kept, W // 2 + 1) + 8 * B * C * min(kept, W // 2 + 1) * H * min(2 * kept, H))
+            flops = wl["depth"] * (mlp + afno) + 3 * 2 * T * C * (wl["cin"] + wl["cout"])
+            tpeak, tsrc = _tf_peak()
+            roof = {"bound": "tensor", "kernel": "whole AFNONet train step (tcgen05 GEMMs of the token MLP dominate)",
+                    "achieved": flops / per / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": flops / per / 1e12 / tpeak,
+                    "traffic": None, "peak_source": tsrc, "alg_flops": flops,
+                    "note": "algorithmic fp32 flops (2MNK per GEMM, fwd+dgrad+wgrad) over the whole-step time (includes Adam, "
+                            "LayerNorm, the AFNO2D filters); the fp32-parity mode issues 3 tf32 MMAs per product, so 1/3 of the "
+                            "tf32 peak is the ceiling of this mode"}
+            metric, cpu = "FourCastNet (AFNONet) train samples/s (fwd+bwd)", None
+            if world == 1 and not args.skip_cpu:
+                cpu = cpu_afnonet_rate(wl)
+        else:
+            alg = 20 * P * wl["depth"]        # per layer: fwd 8P (read x, write y) + bwd 12P (read gy, x for the masks/weights, write gx)
+            roof = {"bound": "hbm", "kernel": "AFNO2D layer (all kernels of one layer, fwd+bwd)",
+                    "achieved": alg / per / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / per / 1e9 / peak, "traffic": None,
+                    "peak_source": peak_src, "alg_bytes": alg,
+                    "note": "whole-step time over 20*P bytes per layer (includes Adam and the loss)"}
+            metric = "AFNO2D filter stack train samples/s (fwd+bwd)"
+            cpu = cpu_afno_rate(wl) if (world == 1 and not args.skip_cpu) else None
+        line = {"metric": metric, "value": B * world * args.steps / t_dev,
                 "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [H, W], "parallelism": f"dp{world}",
                            "step": "fwd+MSE+bwd+Adam(fused)", "cuda_graph": step is not step_eager,
-                           "l2": "working set (8 layers x saved spectra + activations, ~0.6 GB) exceeds the 126 MB L2"},
+                           "tc_mode": int(lib.sb200_get_tc_mode()),
+                           "l2": "working set (saved activations of 8 blocks incl. the 4x hidden tensors, > 2 GB) exceeds the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
-                        "h2d_bytes_per_step": 2 * P * 4 * world, "d2h_bytes_per_step": 4 * world,
+                        "h2d_bytes_per_step": sum(t.numel() for t in host) * 4 * world, "d2h_bytes_per_step": 4 * world,
                         "ms_per_step": t_e2e / args.steps * 1e3},
                 "gpu_launches": launches * args.steps,
-                "roofline": {"bound": "hbm", "kernel": "AFNO2D layer (all kernels of one layer, fwd+bwd)",
-                             "achieved": alg / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": alg / (t_dev / args.steps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "alg_bytes": alg, "note": "whole-step time over 20*P bytes per layer (includes Adam and the loss)"},
-                "cpu_baseline": cpu_afno_rate(wl) if (world == 1 and not args.skip_cpu) else None}
+                "roofline": roof,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     _finish(world, (graph,))
 
@@ -849,7 +945,7 @@ def main():
             return
         run_reference(args, wl, rank, world)
         return
-    if wl.get("kind") == "afno":
+    if wl.get("kind") in ("afno", "afnonet"):
         run_afno(args, wl, rank, world, local_rank)
     elif wl.get("kind") == "rollout":
         run_rollout(args, wl, rank, world, local_rank)

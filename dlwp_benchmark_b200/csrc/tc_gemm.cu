@@ -13,7 +13,8 @@
 // = Linear -> GELU -> Linear, :283-293 PatchEmbed, :257 head) and the backward of those layers.
 //
 //   persistent CTAs over work units (m-tile 128, n-tile BN <= 128, k-split);
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-17: tf32 hi/lo split of landed chunks, then epilogue
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9: tf32 hi/lo split (+ optional GELU transform) of the landed
+//   chunks | warps 10-17: epilogue (overlaps the next unit's MMAs through the double-buffered accumulators)
 //   TMEM: two accumulator buffers; in the 3-pass mode each buffer holds TWO accumulators -- hi*hi products in
 //   one, the 2^-11 times smaller lo*hi + hi*lo corrections in the other -- so the chain of (truncating) tensor-core
 //   accumulations that the large terms go through is K/8 long instead of 3K/8; the epilogue adds the two.
@@ -26,9 +27,10 @@ extern "C" int sb200_get_tc_mode(void);
 
 namespace {
 
-constexpr int TG_WORKER_WARPS = 16;
-constexpr int TG_THREADS = 32 * (2 + TG_WORKER_WARPS);
-constexpr int TG_WTHREADS = 32 * TG_WORKER_WARPS;
+constexpr int TG_SPLIT_WARPS = 8;              // operand split (+ transform) only
+constexpr int TG_EPI_WARPS = 8;                // epilogue only: two per TMEM lane quarter
+constexpr int TG_THREADS = 32 * (2 + TG_SPLIT_WARPS + TG_EPI_WARPS);
+constexpr int TG_SPLIT_THREADS = 32 * TG_SPLIT_WARPS;
 constexpr uint32_t TG_A_BYTES = 128 * 128;     // one K chunk of the A tile: 128 rows x 32 fp32 (either major)
 constexpr uint32_t TG_NLO = 2;                 // buffers for the tf32 "lo" parts (live from the split to the MMAs)
 
@@ -48,7 +50,9 @@ struct TgParams {
     int act;                      // 0 none | 1 GELU | 2 multiply by GELU'(aux[m][n])
     const float* aux; int64_t ld_aux;
     const float* resid; int64_t ld_res; int res_rows;   // residual row = m % res_rows when res_rows > 0 (pos_embed broadcast)
-    float* zout; int64_t ld_z;    // pre-activation store (act == 1) or NULL
+    float* zout; int64_t ld_z;    // pre-activation store or NULL
+    int a_xform, b_xform;         // 1: the operand is GELU(what lies in HBM), applied in the split pass (h = GELU(z) never stored)
+    int vec_ok;                   // every epilogue pointer / leading dimension allows 16-byte accesses
     // split-K epilogue (nsplit > 1): ws[split][M][N]
     float* ws;
     uint32_t idesc, tmem_cols;
@@ -77,12 +81,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         tc::tma_prefetch_desc(&tmapB);
         for (int s = 0; s < S; ++s) {
             tc::mbar_init(full_bar + s, 1);
-            tc::mbar_init(split_bar + s, TG_WORKER_WARPS);
+            tc::mbar_init(split_bar + s, TG_SPLIT_WARPS);
             tc::mbar_init(empty_bar + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(tfull_bar + a, 1);
-            tc::mbar_init(tempty_bar + a, TG_WORKER_WARPS);
+            tc::mbar_init(tempty_bar + a, TG_EPI_WARPS);
         }
         tc::fence_barrier_init();
     }
@@ -161,7 +165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 for (int kc = 0; kc < kcn; ++kc) {
                     const uint32_t d_main = d_buf + ra * (uint32_t)BN;
                     uint32_t started = (uint32_t)kc >= R ? 1u : 0u;
-                    tc::mbar_wait((PASSES == 3 ? split_bar : full_bar) + s, ph);
+                    tc::mbar_wait(((PASSES == 3 || p.a_xform || p.b_xform) ? split_bar : full_bar) + s, ph);
                     tc::tc_fence_after_sync();
                     const uint32_t sa = tc::smem_u32(St + s * stage_bytes);
                     const uint32_t la = tc::smem_u32(Lo + lo * stage_bytes);
@@ -185,23 +189,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 tc::umma_commit(tfull_bar + a);
             }
         }
-    } else {
-        // ================= workers: split (unit it + 1), epilogue (unit it) =================
-        const int wk = warp - 2, wtid = tid - 64;
-        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-        const int cpart = wk >> 2;                          // column part it drains
-        const int ncol_part = (((BN + 3) / 4) + 15) & ~15;  // multiple of 16
-        const int c_begin = cpart * ncol_part;
-        const int c_end = min(BN, c_begin + ncol_part);
-        uint32_t sp_s = 0, sp_ph = 0, sp_lo = 0;
-        uint32_t lag_s = 0, lag_ph = 0, g = 0;
-        const int n4 = (int)(stage_bytes / 16);
-        auto split_unit = [&](uint32_t u) {
-            if (PASSES == 3) {
+    } else if (warp < 2 + TG_SPLIT_WARPS) {
+        // ================= splitter warps: tf32 hi/lo split (+ optional GELU of an operand) of every landed chunk =====
+        // They never touch the epilogue, so the MMA pipeline is fed continuously while the epilogue warps drain the
+        // previous unit's accumulators.
+        if (PASSES == 3 || p.a_xform || p.b_xform) {
+            const int wtid = tid - 64;
+            uint32_t sp_s = 0, sp_ph = 0, sp_lo = 0;
+            uint32_t lag_s = 0, lag_ph = 0, g = 0;
+            const int nA4 = (int)(TG_A_BYTES / 16), n4 = (int)(stage_bytes / 16);
+            for (uint32_t it = 0; it < my_units; ++it) {
                 int m0, n0, kc0, kcn; uint32_t split;
-                decode(u, m0, n0, kc0, kcn, split);
+                decode(first + it * stride, m0, n0, kc0, kcn, split);
                 for (int kc = 0; kc < kcn; ++kc) {
-                    if (g >= TG_NLO) {
+                    if (PASSES == 3 && g >= TG_NLO) {
                         // lo[sp_lo] was last read by the MMAs of chunk g - TG_NLO: their commit is that chunk's empty phase
                         tc::mbar_wait(empty_bar + lag_s, lag_ph);
                         if (++lag_s == (uint32_t)S) { lag_s = 0; lag_ph ^= 1; }
@@ -210,11 +211,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     tc::mbar_wait(full_bar + sp_s, sp_ph);
                     float4* ah = reinterpret_cast<float4*>(St + sp_s * stage_bytes);
                     float4* al = reinterpret_cast<float4*>(Lo + sp_lo * stage_bytes);
-                    for (int idx = wtid; idx < n4; idx += TG_WTHREADS) {
-                        const float4 v = ah[idx];
-                        const float4 h = make_float4(tc::tf32_rna(v.x), tc::tf32_rna(v.y), tc::tf32_rna(v.z), tc::tf32_rna(v.w));
-                        ah[idx] = h;
-                        al[idx] = tc::tf32_lo4(v, h);
+                    for (int idx = wtid; idx < n4; idx += TG_SPLIT_THREADS) {
+                        float4 v = ah[idx];
+                        if (idx < nA4 ? p.a_xform : p.b_xform)         // operand = GELU(stored pre-activation): never in HBM
+                            v = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+                        if (PASSES == 3) {
+                            const float4 h = make_float4(tc::tf32_rna(v.x), tc::tf32_rna(v.y), tc::tf32_rna(v.z), tc::tf32_rna(v.w));
+                            ah[idx] = h;
+                            al[idx] = tc::tf32_lo4(v, h);
+                        } else {
+                            ah[idx] = v;
+                        }
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
@@ -223,10 +230,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     if (++sp_lo == TG_NLO) sp_lo = 0;
                 }
             }
-        };
-        if (my_units > 0) split_unit(first);
+        }
+    } else {
+        // ================= epilogue warps: TMEM -> registers -> fused epilogue -> global =================
+        const int wk = warp - 2 - TG_SPLIT_WARPS;          // 0..7
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cpart = wk >> 2;                          // column half it drains
+        const int ncol_part = (((BN + 1) / 2) + 15) & ~15;  // multiple of 16
+        const int c_begin = cpart * ncol_part;
+        const int c_end = min(BN, c_begin + ncol_part);
         for (uint32_t it = 0; it < my_units; ++it) {
-            if (it + 1 < my_units) split_unit(first + (it + 1) * stride);
             int m0, n0, kc0, kcn; uint32_t split;
             decode(first + it * stride, m0, n0, kc0, kcn, split);
             const uint32_t a = it & 1, tround = it >> 1;
@@ -268,35 +281,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     }
                     continue;
                 }
+                const bool vec = full16 && p.vec_ok;          // every pointer / leading dimension is 16-byte aligned
                 if (p.bias) {
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                    }
                 }
                 if (p.zout) {
                     float* zd = p.zout + (int64_t)m * p.ld_z + n;
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) zd[j] = v[j];
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(zd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) zd[j] = v[j];
+                    }
                 }
                 if (p.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = gelu_f(v[j]);
                 } else if (p.act == 2) {
                     const float* ax = p.aux + (int64_t)m * p.ld_aux + n;
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] *= gelu_grad_f(__ldg(ax + j));
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 z4 = __ldg(reinterpret_cast<const float4*>(ax + j));
+                            v[j] *= gelu_grad_f(z4.x); v[j + 1] *= gelu_grad_f(z4.y);
+                            v[j + 2] *= gelu_grad_f(z4.z); v[j + 3] *= gelu_grad_f(z4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] *= gelu_grad_f(__ldg(ax + j));
+                    }
                 }
                 if (p.resid) {
                     const float* rs = p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n;
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(rs + j);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 q4 = __ldg(reinterpret_cast<const float4*>(rs + j));
+                            v[j] += q4.x; v[j + 1] += q4.y; v[j + 2] += q4.z; v[j + 3] += q4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(rs + j);
+                    }
                 }
-                float* dst = p.D + (int64_t)m * p.ldd + n;
-                if (full16 && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
+                if (p.D) {
+                    float* dst = p.D + (int64_t)m * p.ldd + n;
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) dst[j] = v[j];
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) dst[j] = v[j];
+                    }
                 }
             }
             tc::tc_fence_before_sync();
@@ -330,6 +376,7 @@ struct FgParams {
     const float* aux; int64_t ld_aux;
     const float* resid; int64_t ld_res; int res_rows;
     float* zout; int64_t ld_z;
+    int a_xform, b_xform;
 };
 __global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
     __shared__ float As[16][65], Bs[16][65];
@@ -342,10 +389,14 @@ __global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
             int r, k;
             if (p.a_sk == 1) { k = idx & 15; r = idx >> 4; } else { r = idx & 63; k = idx >> 6; }
             const int m = m0 + r, kk = k0 + k;
-            As[k][r] = (m < p.M && kk < p.K) ? __ldg(p.A + (int64_t)m * p.a_sm + (int64_t)kk * p.a_sk) : 0.f;
+            float av = (m < p.M && kk < p.K) ? __ldg(p.A + (int64_t)m * p.a_sm + (int64_t)kk * p.a_sk) : 0.f;
+            if (p.a_xform) av = gelu_f(av);
+            As[k][r] = (m < p.M && kk < p.K) ? av : 0.f;
             if (p.b_sk == 1) { k = idx & 15; r = idx >> 4; } else { r = idx & 63; k = idx >> 6; }
             const int n = n0 + r, kb = k0 + k;
-            Bs[k][r] = (n < p.N && kb < p.K) ? __ldg(p.B + (int64_t)n * p.b_sn + (int64_t)kb * p.b_sk) : 0.f;
+            float bv = (n < p.N && kb < p.K) ? __ldg(p.B + (int64_t)n * p.b_sn + (int64_t)kb * p.b_sk) : 0.f;
+            if (p.b_xform) bv = gelu_f(bv);
+            Bs[k][r] = (n < p.N && kb < p.K) ? bv : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -372,7 +423,7 @@ __global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
             if (p.act == 1) v = gelu_f(v);
             else if (p.act == 2) v *= gelu_grad_f(__ldg(p.aux + (int64_t)m * p.ld_aux + n));
             if (p.resid) v += __ldg(p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n);
-            p.D[(int64_t)m * p.ldd + n] = v;
+            if (p.D) p.D[(int64_t)m * p.ldd + n] = v;
         }
     }
 }
@@ -440,9 +491,10 @@ extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split
 
 extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
                           int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
-                          const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int split_k,
-                          float* workspace, void* stream) {
-    SB_REQUIRE(A && B && D, "gemm: NULL operand");
+                          const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform,
+                          int b_xform, int split_k, float* workspace, void* stream) {
+    SB_REQUIRE(A && B && (D || zout), "gemm: NULL operand");
+    SB_REQUIRE(D || !split_k, "gemm: split-K needs D");
     SB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive size");
     SB_REQUIRE(act >= 0 && act <= 2, "gemm: act must be 0, 1 or 2");
     SB_REQUIRE(act != 2 || aux, "gemm: act 2 needs aux");
@@ -460,6 +512,7 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
         f.B = B; f.b_sn = b_mn ? 1 : ldb; f.b_sk = b_mn ? ldb : 1;
         f.M = M; f.N = N; f.K = K; f.D = D; f.ldd = ldd; f.bias = bias; f.act = act; f.aux = aux; f.ld_aux = ld_aux;
         f.resid = resid; f.ld_res = ld_res; f.res_rows = res_rows; f.zout = zout; f.ld_z = ld_z;
+        f.a_xform = a_xform; f.b_xform = b_xform;
         dim3 grid((N + 63) / 64, (M + 63) / 64);
         SB_REQUIRE(grid.y <= 65535, "gemm: M too large for the CUDA-core kernel");
         sb_launch(ffma_gemm_kernel, grid, 256, 0, st, f);
@@ -473,7 +526,11 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     p.nunits = (uint32_t)g.mtiles * (uint32_t)g.ntiles * (uint32_t)g.nsplit;
     p.stages = g.stages; p.R = g.R;
     p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.aux = aux; p.ld_aux = ld_aux; p.resid = resid; p.ld_res = ld_res;
-    p.res_rows = res_rows;
+    p.res_rows = res_rows; p.a_xform = a_xform; p.b_xform = b_xform;
+    {
+        auto al = [](const void* q, int64_t ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld & 3) == 0); };
+        p.vec_ok = al(D, ldd) && al(bias, 0) && al(aux, ld_aux) && al(resid, ld_res) && al(zout, ld_z);
+    }
     p.zout = zout; p.ld_z = ld_z; p.ws = workspace;
     p.idesc = tc::make_idesc_tf32(128, g.BN, a_mn, b_mn);
     uint32_t cols = 32;

@@ -119,31 +119,30 @@ class BlockFn(torch.autograd.Function):
                                     x if double_skip else None)
         x1 = x1_4.view(T, C)
         xn2, m2, r2 = ops.layernorm_fwd(x1, g2c, be2c, LN_EPS)
-        if need:
-            h1, z1 = ops.gemm(xn2, fw1c, bias=fb1c, act=1, want_z=True)
-        else:
-            h1, z1 = ops.gemm(xn2, fw1c, bias=fb1c, act=1), None
-        y = ops.gemm(h1, fw2c, bias=fb2c, resid=x1 if double_skip else x2)
+        # fc1 writes only the pre-activation z1; h1 = GELU(z1) is formed on chip by the consumers' split pass (fc2 below,
+        # the fc2 weight gradient in the backward), so the activated [T, 4C] tensor never exists in HBM
+        z1 = ops.gemm(xn2, fw1c, bias=fb1c, z_only=True)
+        y = ops.gemm(z1, fw2c, bias=fb2c, resid=x1 if double_skip else x2, a_gelu=True)
         if need:
             ctx.double_skip = bool(double_skip)
             ctx.dims = (B, h, w, C)
             ctx.amisc = asaved[:2]
             ctx.sinks = [ops.grad_sink(t) for t in (g1, be1, g2, be2, fw1, fb1, fw2, fb2)]
-            ctx.save_for_backward(x2, m1, r1, x1, m2, r2, xn2, z1, h1, asaved[2], asaved[3], asaved[4],
+            ctx.save_for_backward(x2, m1, r1, x1, m2, r2, xn2, z1, asaved[2], asaved[3], asaved[4],
                                   g1c, g2c, aw1c, aw2c, fw1c, fw2c)
         return y.view(B, h, w, C)
 
     @staticmethod
     @_lib.on_tensor_device
     def backward(ctx, gy):
-        (x2, m1, r1, x1, m2, r2, xn2, z1, h1, Xh, O1, Yh, g1c, g2c, aw1c, aw2c, fw1c, fw2c) = ctx.saved_tensors
+        (x2, m1, r1, x1, m2, r2, xn2, z1, Xh, O1, Yh, g1c, g2c, aw1c, aw2c, fw1c, fw2c) = ctx.saved_tensors
         B, h, w, C = ctx.dims
         T = B * h * w
         s_g1, s_be1, s_g2, s_be2, s_fw1, s_fb1, s_fw2, s_fb2 = ctx.sinks
         gy2 = _f32c(gy).view(T, C)
         keep = lambda t, s: None if s is not None else t
         # ---- token MLP ----
-        gfw2 = ops.gemm(gy2, h1, a_mn=True, b_mn=True, split_k=True, out=s_fw2)            # [C, 4C]
+        gfw2 = ops.gemm(gy2, z1, a_mn=True, b_mn=True, b_gelu=True, split_k=True, out=s_fw2)   # [C, 4C] = gy^T GELU(z1)
         gfb2 = ops.colsum(gy2, out=s_fb2)
         gz1 = ops.gemm(gy2, fw2c, b_mn=True, act=2, aux=z1)                                # [T, 4C] = (gy W2) * GELU'(z1)
         gfw1 = ops.gemm(gz1, xn2, a_mn=True, b_mn=True, split_k=True, out=s_fw1)           # [4C, C]

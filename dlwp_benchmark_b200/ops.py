@@ -337,12 +337,14 @@ def lift_wgrad(g, x, w1, b1, want_bias: bool = True, out_w=None, out_b=None):
 # channels-last token path (FourCastNet block remainder)
 # ---------------------------------------------------------------------------------------------
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias=None, act: int = 0, aux=None,
-         resid=None, res_rows: int = 0, want_z: bool = False, out=None, split_k: bool = False):
+         resid=None, res_rows: int = 0, want_z: bool = False, out=None, split_k: bool = False, a_gelu: bool = False,
+         b_gelu: bool = False, z_only: bool = False):
     """D[m,n] = sum_k A(m,k) B(n,k) on 2-D contiguous fp32 tensors.  ``a_mn=False``: A is [M,K] (K-major);
     ``a_mn=True``: A is [K,M] (used transposed, MN-major); likewise B ([N,K] or [K,N]).  Epilogue: + bias[n];
     z = pre-activation (returned when ``want_z``); act 1 = GELU, 2 = multiply by GELU'(aux[m,n]); + resid (row
     ``m % res_rows`` when ``res_rows > 0``).  ``split_k``: K split over CTAs (weight gradients), no epilogue.
-    Returns D, or (D, z) when ``want_z``."""
+    ``a_gelu`` / ``b_gelu``: the operand is GELU(A) / GELU(B), applied on chip.  ``z_only``: only the pre-activation
+    z = A B^T + bias is produced (returned alone).  Returns D, or (D, z) when ``want_z``."""
     _req(A, "A"); _req(B, "B")
     assert A.dim() == 2 and B.dim() == 2
     (K, M) = A.shape if a_mn else A.shape[::-1]
@@ -352,13 +354,16 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if t is not None:
             _req(t, n)
     dev = A.device
-    D = _out(out, (M, N), dev)
-    z = torch.empty(M, N, device=dev, dtype=torch.float32) if want_z else None
+    D = None if z_only else _out(out, (M, N), dev)
+    z = torch.empty(M, N, device=dev, dtype=torch.float32) if (want_z or z_only) else None
     lib = _lib.load()
     nws = lib.sb200_gemm_workspace(M, N, K, int(b_mn), int(split_k))
     ws = torch.empty(nws, device=dev, dtype=torch.float32) if nws > 0 else None
     _lib.check(lib.sb200_gemm(_p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(D), N, M, N, K, _p(bias), act,
-                              _p(aux), N, _p(resid), N, res_rows, _p(z), N, int(split_k), _p(ws), _stream()), "gemm")
+                              _p(aux), N, _p(resid), N, res_rows, _p(z), N, int(a_gelu), int(b_gelu), int(split_k), _p(ws),
+                              _stream()), "gemm")
+    if z_only:
+        return z
     return (D, z) if want_z else D
 
 

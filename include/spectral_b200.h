@@ -236,6 +236,9 @@ int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* 
  *   a_mn = 1: A is MN-major, element (m,k) at A[k*lda + m] (the same arrays used transposed); likewise b_mn / ldb.
  *   Epilogue (split_k == 0): + bias[n]; zout[m][n] = pre-activation (optional); act 1 = GELU, act 2 = multiply by
  *   GELU'(aux[m][n]); + resid[(res_rows > 0 ? m % res_rows : m)][n]; replaces nn.Linear / F.gelu / the residual adds.
+ *   a_xform / b_xform = 1: the operand is GELU(what lies in memory), applied on chip while the tile is split into its
+ *   tf32 parts -- the activated hidden tensor of an MLP (h = GELU(z)) is never written to HBM; D may be NULL when only
+ *   the pre-activation `zout` is wanted.
  *   split_k != 0: the K range is split over CTAs (weight gradients: K = tokens), partials in `workspace`
  *   (sb200_gemm_workspace floats) are reduced in a fixed order; no fused epilogue.
  *   Bases and leading dimensions must be 16-byte multiples for the tensor-core path; anything else (and tc mode 0)
@@ -243,8 +246,8 @@ int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* 
 int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k);
 int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
                int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
-               const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int split_k,
-               float* workspace, void* stream);
+               const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform, int b_xform,
+               int split_k, float* workspace, void* stream);
 
 /* LayerNorm over the last (channel) axis of x [T, C] (biased variance, eps inside the sqrt: torch.nn.LayerNorm as
  * built at fourcastnet.py:236 norm_layer = partial(nn.LayerNorm, eps=1e-6)); mean / rstd [T] are saved for the backward.

@@ -91,3 +91,25 @@ def test_colsum_and_batch_sum():
     assert rel_l2(ops.colsum(a.to(DEV)), a.double().sum(0)) < 2e-6
     b = _rand(16, 2048, 40, seed=17)
     assert rel_l2(ops.batch_sum(b.to(DEV)), b.double().sum(0)) < 1e-6
+
+
+def test_gemm_gelu_operand_transform_and_z_only():
+    """h = GELU(z) formed on chip: as the A operand (fc2 forward) and as the B operand (fc2 weight gradient)."""
+    T, C, Hd = 640, 64, 256
+    z, W2, gy = _rand(T, Hd, seed=21), _rand(C, Hd, seed=22, scale=0.1), _rand(T, C, seed=23)
+    h = F.gelu(z.double())
+    y = ops.gemm(z.to(DEV), W2.to(DEV), a_gelu=True)
+    assert rel_l2(y, h @ W2.double().t()) < 2e-6
+    gW2 = ops.gemm(gy.to(DEV), z.to(DEV), a_mn=True, b_mn=True, b_gelu=True, split_k=True)
+    assert rel_l2(gW2, gy.double().t() @ h) < 3e-6
+    x, W1, b1 = _rand(T, C, seed=24), _rand(Hd, C, seed=25, scale=0.2), _rand(Hd, seed=26)
+    zz = ops.gemm(x.to(DEV), W1.to(DEV), bias=b1.to(DEV), z_only=True)
+    assert rel_l2(zz, x.double() @ W1.double().t() + b1.double()) < 2e-6
+    lib = _lib.load()
+    old = lib.sb200_get_tc_mode()
+    try:
+        for mode, tol in ((1, 2e-3), (0, 2e-6)):
+            lib.sb200_set_tc_mode(mode)
+            assert rel_l2(ops.gemm(z.to(DEV), W2.to(DEV), a_gelu=True), h @ W2.double().t()) < tol
+    finally:
+        lib.sb200_set_tc_mode(old)
