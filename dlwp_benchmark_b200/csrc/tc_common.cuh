@@ -34,7 +34,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef SB200_TEST_WAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -47,6 +51,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
+}
+
+// Whole-warp wait: ONE lane polls the barrier, the others park at the warp barrier (fewer try_wait requests on the
+// shared-memory pipe; measured neutral on the kernels of this library, kept because it is never worse).
+// __syncwarp() orders memory among the participating lanes, so data published before the barrier completed is
+// visible to all of them afterwards.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 
 // ---------------- TMA ----------------
