@@ -19,8 +19,8 @@
 
 constexpr int AF_ROWS = 256;                 // image rows per group
 #ifndef AF_RTHREADS_V
-#define AF_RTHREADS_V 256
-#endif
+#define AF_RTHREADS_V 128      // 2 image rows per row-stage thread: every broadcast twiddle LDS.128 feeds 20 FFMA2 instead of 10
+#endif                         // (measured in round 2 at cfg2 shapes: 34.5 us against 37.7 us with 256 threads x 1 row)
 constexpr int AF_RTHREADS = AF_RTHREADS_V;   // row-stage threads
 constexpr int AF_RPT = AF_ROWS / AF_RTHREADS; // image rows per row-stage thread
 constexpr int AF_CTHREADS = 160;             // column-stage threads

@@ -193,17 +193,18 @@ __device__ __forceinline__ uint32_t sw128b32_mnmajor_off(int mn, int k, uint32_t
            (uint32_t)((mn & 7) << 2);
 }
 
-// 3xTF32 operand split  v = hi + lo:  hi = v rounded to NEAREST tf32 (10 explicit mantissa bits), lo = v - hi (exact
-// in fp32; the tensor core reads it as tf32 by dropping its low 13 bits).
-// Rounding hi to nearest instead of truncating it matters: with a truncated hi, lo always has the sign of v, and
-// the hardware's truncation of lo then biases every product by about -2^-21 relative -- a systematic error that
-// does not average out over the K sum (measured in round 2: 2e-6 per GEMM stage against 3e-7 for the FFMA path,
-// 1.4e-5 on the cfg3 / cfg5 model outputs).  With hi rounded, lo has a random sign and its truncation error is
-// zero-mean, <= 2^-21 |v|.  Integer rounding (add half an ulp of tf32, clear 13 bits: round-half-away) runs at
-// full ALU rate; cvt.rna.tf32.f32 is a conversion-pipe instruction and measured 4 % slower on the cfg2 step.
+// 3xTF32 operand split  v = hi + lo:  hi = v rounded to NEAREST tf32 (10 explicit mantissa bits), lo = (v - hi) rounded
+// to nearest tf32 (v - hi is exact in fp32).  The tensor core reads a 32-bit operand as tf32 by DROPPING its low 13 bits,
+// so whatever is not rounded here is truncated there.  Measured in round 2 on whole models (rel-L2 of the cfg3 / cfg5
+// outputs against the fp64 oracle; the FFMA path gives 2e-6, plain fp32 torch 1.3e-6):
+//     hi truncated, lo truncated by the hardware   1.4e-5 / 1.8e-5   (every product biased by about -2^-21: lo >= 0 always)
+//     hi rounded,   lo truncated by the hardware   > 1e-5 at cfg3     (truncation always shrinks |lo|: still a bias)
+//     hi rounded,   lo rounded                      7.8e-6            (symmetric errors, <= 2^-23 relative per product)
+// Integer rounding (add half an ulp of tf32, clear 13 bits: round-half-away) runs at full ALU rate; cvt.rna.tf32.f32
+// is a conversion-pipe instruction and measured 4 % slower on the cfg2 step.
 __device__ __forceinline__ float tf32_rna(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_trunc(float v) { return tf32_rna(v); }          // "hi" part (historic name)
-__device__ __forceinline__ float tf32_lo(float v, float hi) { return v - hi; }
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rna(v - hi); }
 __device__ __forceinline__ float4 tf32_lo4(float4 v, float4 h) {
     return make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
 }

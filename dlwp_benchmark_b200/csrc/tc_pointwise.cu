@@ -104,6 +104,9 @@ struct TcPwParams {
     int64_t ntiles;
     int mode, apply_act;
     uint32_t idesc, idesc_spec, tmem_cols;
+    int corr;                // 3-pass mode, 4N <= 512: the lo*hi + hi*lo corrections accumulate in their own TMEM columns (behind the
+                             // N main columns of each buffer), so the large hi*hi terms go through a chain of K/8 truncating
+                             // tensor-core accumulations instead of 3K/8; the epilogue adds the two
     // spectral term (Phi == NULL: none)
     const float2* Phi; const float* E; const float2* rot;
     int H, W, Mx, R, V, K2, K2pad;
@@ -307,8 +310,10 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 const uint32_t tround = it >> 1;
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
                 tc::tc_fence_after_sync();
-                const uint32_t tmem_d = tmem_base + (uint32_t)a * (uint32_t)p.N;
-                uint32_t started = 0;
+                const uint32_t bufw = (uint32_t)p.N * (p.corr ? 2u : 1u);
+                const uint32_t tmem_d = tmem_base + (uint32_t)a * bufw;
+                const uint32_t tmem_c = p.corr ? tmem_d + (uint32_t)p.N : tmem_d;   // correction accumulator
+                uint32_t started = 0, started_c = p.corr ? 0u : 1u;
                 if (spectral) {
                     tc::mbar_wait(phi_bar + a, tround & 1);
                     tc::tc_fence_after_sync();
@@ -319,8 +324,9 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         tc::umma_tf32_lh(tmem_d, eh, s_hi32, fh, s_hi32, p.idesc_spec, started);
                         started = 1;
                         if (PASSES == 3) {
-                            tc::umma_tf32_lh(tmem_d, el, s_hi32, fh, s_hi32, p.idesc_spec, 1u);
-                            tc::umma_tf32_lh(tmem_d, eh, s_hi32, fl, s_hi32, p.idesc_spec, 1u);
+                            tc::umma_tf32_lh(tmem_c, el, s_hi32, fh, s_hi32, p.idesc_spec, started_c);
+                            tc::umma_tf32_lh(tmem_c, eh, s_hi32, fl, s_hi32, p.idesc_spec, 1u);
+                            started_c = 1;
                         }
                         eh += 4096 >> 4; el += 4096 >> 4; fh += phi_step; fl += phi_step;
                     }
@@ -337,8 +343,9 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         tc::umma_tf32_lh(tmem_d, ah, a_hi32, bh_base + boff, b_hi32, p.idesc, started);
                         started = 1;
                         if (PASSES == 3) {
-                            tc::umma_tf32_lh(tmem_d, al, a_hi32, bh_base + boff, b_hi32, p.idesc, 1u);
-                            tc::umma_tf32_lh(tmem_d, ah, a_hi32, bl_base + boff, b_hi32, p.idesc, 1u);
+                            tc::umma_tf32_lh(tmem_c, al, a_hi32, bh_base + boff, b_hi32, p.idesc, started_c);
+                            tc::umma_tf32_lh(tmem_c, ah, a_hi32, bl_base + boff, b_hi32, p.idesc, 1u);
+                            started_c = 1;
                         }
                         ah += 1024 >> 4; al += 1024 >> 4; boff += 32 >> 4;   // KC <= 32: stays inside one 32-wide K chunk
                     }
@@ -567,7 +574,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const uint32_t tround = it >> 1;
             tc::mbar_wait(tfull_bar + a, tround & 1);
             tc::tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N * (p.corr ? 2u : 1u);
             if constexpr (EPI == 5) {
                 // ---- fused head forward: this warp's columns -> one partial dot product per pixel ----
                 float part = 0.f;
@@ -673,6 +680,13 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 }
                 tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
+                if (PASSES == 3 && p.corr) {
+                    uint32_t rc[16];
+                    tc::tmem_ld_32x32b_x16(taddr + (uint32_t)(p.N + c0), rc);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+                }
                 if (bias_epi) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -810,8 +824,9 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     p.mode = q.mode; p.apply_act = q.apply_act;
     p.idesc = tc::make_idesc_tf32(128, N, /*A MN-major*/ 1, /*B K-major*/ 0);
     p.idesc_spec = tc::make_idesc_tf32(128, N, 0, 0);
+    p.corr = (passes == 3 && 4 * N <= 512) ? 1 : 0;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * N)) cols <<= 1;
+    while (cols < (uint32_t)(2 * N * (p.corr ? 2 : 1))) cols <<= 1;
     p.tmem_cols = cols;
     p.ntiles = (HW + TP_PX - 1) / TP_PX * q.B;
     p.H = q.H; p.W = q.W; p.Mx = q.Mx;
@@ -991,8 +1006,9 @@ extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, 
     p.KC = 32; p.nkc = N / 32;
     p.idesc = tc::make_idesc_tf32(128, C, 1, 0);
     p.idesc_spec = tc::make_idesc_tf32(128, C, 0, 0);
+    p.corr = (passes == 3 && 4 * C <= 512) ? 1 : 0;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * C)) cols <<= 1;
+    while (cols < (uint32_t)(2 * C * (p.corr ? 2 : 1))) cols <<= 1;
     p.tmem_cols = cols;
     p.ntiles = (HW + TP_PX - 1) / TP_PX * B;
     p.w2 = w1; p.b2 = b1; p.gy = x;
