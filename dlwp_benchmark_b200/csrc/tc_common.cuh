@@ -204,6 +204,7 @@ __device__ __forceinline__ uint32_t sw128b32_mnmajor_off(int mn, int k, uint32_t
 // is a conversion-pipe instruction and measured 4 % slower on the cfg2 step.
 __device__ __forceinline__ float tf32_rna(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_trunc(float v) { return tf32_rna(v); }          // "hi" part (historic name)
+__device__ __forceinline__ float tf32_cut(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }   // what the tensor core reads
 __device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rna(v - hi); }
 __device__ __forceinline__ float4 tf32_lo4(float4 v, float4 h) {
     return make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));

@@ -43,6 +43,9 @@ struct TgParams {
     int kc_per_split;
     uint32_t nunits;
     int stages;
+    int nlo;                      // depth of the ring of tf32 "lo" buffers: 2 (decoupled from the stages), or `stages` with b_pre
+    int b_pre;                    // the B operand arrives pre-split: hi plane through tmapB, lo plane through tmapBlo (weights that
+                                  // every m-tile re-reads are split ONCE by a tiny kernel instead of once per tile by the CTAs)
     int R;                        // rotating "main" accumulators per TMEM buffer (chain of truncating accumulations = K/(8R))
     // direct epilogue (nsplit == 1)
     float* D; int64_t ldd;
@@ -56,19 +59,27 @@ struct TgParams {
     // split-K epilogue (nsplit > 1): ws[split][M][N]
     float* ws;
     uint32_t idesc, tmem_cols;
+    long long* trace;             // bring-up builds only: clock64 stamps of CTA 0 [role][chunk or unit][event]
 };
+#ifdef SB200_BRINGUP
+#define TG_TRACE(role, i, ev) do { if (p.trace && blockIdx.x == 0 && (i) < 32) p.trace[((role) * 32 + (i)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TG_TRACE(role, i, ev) do { } while (0)
+#endif
 
 template <int PASSES>
 __global__ void __launch_bounds__(TG_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const TgParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+               const __grid_constant__ CUtensorMap tmapBlo, const TgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages, BN = p.BN;
     const uint32_t b_bytes = (uint32_t)BN * 128;
     const uint32_t stage_bytes = TG_A_BYTES + b_bytes;                 // [A chunk | B chunk]
     uint8_t* St = base;
-    uint8_t* Lo = St + (uint32_t)S * stage_bytes;                      // [TG_NLO][stage_bytes]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(Lo + (PASSES == 3 ? TG_NLO * stage_bytes : 0));
+    uint8_t* Lo = St + (uint32_t)S * stage_bytes;                      // [nlo][stage_bytes]
+    const uint32_t NLO = (uint32_t)p.nlo;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(Lo + (PASSES == 3 ? NLO * stage_bytes : 0));
     uint64_t* split_bar = full_bar + S;
     uint64_t* empty_bar = split_bar + S;
     uint64_t* tfull_bar = empty_bar + S;
@@ -118,16 +129,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, gc = 0;
             for (uint32_t it = 0; it < my_units; ++it) {
                 int m0, n0, kc0, kcn; uint32_t split;
                 decode(first + it * stride, m0, n0, kc0, kcn, split);
                 for (int kc = 0; kc < kcn; ++kc) {
                     const int k0 = (kc0 + kc) * 32;
+                    TG_TRACE(0, gc, 0);
                     tc::mbar_wait(empty_bar + s, ph ^ 1);
+                    TG_TRACE(0, gc, 1);
                     uint8_t* dA = St + s * stage_bytes;
                     uint8_t* dB = dA + TG_A_BYTES;
-                    tc::mbar_expect_tx(full_bar + s, stage_bytes);
+                    tc::mbar_expect_tx(full_bar + s, stage_bytes + (p.b_pre ? b_bytes : 0u));
                     if (p.a_mn) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) tc::tma_load_2d(dA + i * 4096, &tmapA, m0 + 32 * i, k0, full_bar + s);
@@ -139,6 +152,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     } else {
                         tc::tma_load_2d(dB, &tmapB, k0, n0, full_bar + s);
                     }
+                    if (p.b_pre) {                          // lo plane of B straight into the lo slot of this stage (nlo == S)
+                        uint8_t* dL = Lo + s * stage_bytes + TG_A_BYTES;
+                        if (p.b_mn) {
+                            for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(dL + j * 4096, &tmapBlo, n0 + 32 * j, k0, full_bar + s);
+                        } else {
+                            tc::tma_load_2d(dL, &tmapBlo, k0, n0, full_bar + s);
+                        }
+                    }
+                    TG_TRACE(0, gc, 2); ++gc;
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
             }
@@ -152,12 +174,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const uint32_t b_hi32 = p.b_mn ? tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B) : tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
             const uint32_t a_step = (p.a_mn ? 1024u : 32u) >> 4, b_step = (p.b_mn ? 1024u : 32u) >> 4;
-            uint32_t s = 0, ph = 0, lo = 0;
+            uint32_t s = 0, ph = 0, lo = 0, gc = 0;
             for (uint32_t it = 0; it < my_units; ++it) {
                 int m0, n0, kc0, kcn; uint32_t split;
                 decode(first + it * stride, m0, n0, kc0, kcn, split);
                 const uint32_t a = it & 1, tround = it >> 1;
+                TG_TRACE(3, it, 0);
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
+                TG_TRACE(3, it, 1);
                 tc::tc_fence_after_sync();
                 const uint32_t d_buf = tmem_base + a * acc_cols;
                 const uint32_t d_corr = d_buf + R * (uint32_t)BN;
@@ -165,7 +189,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 for (int kc = 0; kc < kcn; ++kc) {
                     const uint32_t d_main = d_buf + ra * (uint32_t)BN;
                     uint32_t started = (uint32_t)kc >= R ? 1u : 0u;
+                    TG_TRACE(1, gc, 0);
                     tc::mbar_wait(((PASSES == 3 || p.a_xform || p.b_xform) ? split_bar : full_bar) + s, ph);
+                    TG_TRACE(1, gc, 1);
                     tc::tc_fence_after_sync();
                     const uint32_t sa = tc::smem_u32(St + s * stage_bytes);
                     const uint32_t la = tc::smem_u32(Lo + lo * stage_bytes);
@@ -182,8 +208,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         ah += a_step; al += a_step; bh += b_step; bl += b_step;
                     }
                     tc::umma_commit(empty_bar + s);                    // frees the stage AND the lo buffer of this chunk
+                    TG_TRACE(1, gc, 2); ++gc;
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
-                    if (++lo == TG_NLO) lo = 0;
+                    if (++lo == NLO) lo = 0;
                     if (++ra == R) ra = 0;
                 }
                 tc::umma_commit(tfull_bar + a);
@@ -202,32 +229,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 int m0, n0, kc0, kcn; uint32_t split;
                 decode(first + it * stride, m0, n0, kc0, kcn, split);
                 for (int kc = 0; kc < kcn; ++kc) {
-                    if (PASSES == 3 && g >= TG_NLO) {
+                    if (wtid == 0) TG_TRACE(2, g, 0);
+                    if (PASSES == 3 && !p.b_pre && g >= NLO) {
                         // lo[sp_lo] was last read by the MMAs of chunk g - TG_NLO: their commit is that chunk's empty phase
                         tc::mbar_wait(empty_bar + lag_s, lag_ph);
                         if (++lag_s == (uint32_t)S) { lag_s = 0; lag_ph ^= 1; }
                     }
-                    ++g;
+                    if (wtid == 0) TG_TRACE(2, g, 1);
                     tc::mbar_wait(full_bar + sp_s, sp_ph);
+                    if (wtid == 0) TG_TRACE(2, g, 2);
                     float4* ah = reinterpret_cast<float4*>(St + sp_s * stage_bytes);
                     float4* al = reinterpret_cast<float4*>(Lo + sp_lo * stage_bytes);
-                    for (int idx = wtid; idx < n4; idx += TG_SPLIT_THREADS) {
+                    const int nsp = p.b_pre ? nA4 : n4;
+                    for (int idx = wtid; idx < nsp; idx += TG_SPLIT_THREADS) {
                         float4 v = ah[idx];
-                        if (idx < nA4 ? p.a_xform : p.b_xform)         // operand = GELU(stored pre-activation): never in HBM
+                        const bool xf = idx < nA4 ? p.a_xform : p.b_xform;
+                        if (xf) {                                      // operand = GELU(stored pre-activation): never in HBM
                             v = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+                            if (PASSES != 3 || p.b_pre) ah[idx] = v;
+                        }
                         if (PASSES == 3) {
-                            const float4 h = make_float4(tc::tf32_rna(v.x), tc::tf32_rna(v.y), tc::tf32_rna(v.z), tc::tf32_rna(v.w));
-                            ah[idx] = h;
-                            al[idx] = tc::tf32_lo4(v, h);
-                        } else {
-                            ah[idx] = v;
+                            // hi is NOT written back: the tensor core reads the fp32 word as tf32 by dropping its low 13 bits,
+                            // i.e. hi = trunc(v); lo = RN_tf32(v - trunc(v)) makes hi + lo exact to 2^-22 |v| (the residual is
+                            // rounded, so nothing is left for the hardware to truncate).  Saves a third of the split's
+                            // shared-memory writes -- these kernels are bound by shared-memory bandwidth.
+                            // (measured: faster where only A is split in the CTA, slower in the split-K weight-gradient GEMMs
+                            // that split both operands -- those keep the rounded hi written back)
+                            if (p.b_pre) {
+                                const float4 h = make_float4(tc::tf32_cut(v.x), tc::tf32_cut(v.y), tc::tf32_cut(v.z), tc::tf32_cut(v.w));
+                                al[idx] = tc::tf32_lo4(v, h);
+                            } else {
+                                const float4 h = make_float4(tc::tf32_rna(v.x), tc::tf32_rna(v.y), tc::tf32_rna(v.z), tc::tf32_rna(v.w));
+                                ah[idx] = h;
+                                al[idx] = tc::tf32_lo4(v, h);
+                            }
                         }
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (wtid == 0) TG_TRACE(2, g, 3);
+                    ++g;
                     if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
-                    if (++sp_lo == TG_NLO) sp_lo = 0;
+                    if (++sp_lo == NLO) sp_lo = 0;
                 }
             }
         }
@@ -244,6 +288,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             decode(first + it * stride, m0, n0, kc0, kcn, split);
             const uint32_t a = it & 1, tround = it >> 1;
             tc::mbar_wait(tfull_bar + a, tround & 1);
+            if (wk == 0 && lane == 0) TG_TRACE(3, it, 2);
             tc::tc_fence_after_sync();
             const int m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
@@ -348,6 +393,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             tc::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+            if (wk == 0 && lane == 0) TG_TRACE(3, it, 3);
         }
     }
     tc::tc_fence_before_sync();
@@ -435,9 +481,9 @@ bool tg_operand_ok(const float* ptr, int64_t ld, int mn_major, int rows, int K) 
     return true;
 }
 
-struct TgGeom { int BN, R, ntiles, mtiles, nsplit, kc_total, kc_per_split, stages; size_t smem; };
+struct TgGeom { int BN, R, ntiles, mtiles, nsplit, kc_total, kc_per_split, stages, nlo, b_pre; size_t smem; };
 
-bool tg_geometry(int M, int N, int K, int b_mn, int passes, int want_split, TgGeom* g) {
+bool tg_geometry(int M, int N, int K, int b_mn, int passes, int want_split, int b_xform, TgGeom* g) {
     if (M <= 0 || N <= 0 || K <= 0) return false;
     g->mtiles = (M + 127) / 128;
     g->kc_total = (K + 31) / 32;
@@ -470,22 +516,46 @@ bool tg_geometry(int M, int N, int K, int b_mn, int passes, int want_split, TgGe
     g->kc_per_split = (g->kc_total + nsplit - 1) / nsplit;
     g->nsplit = (g->kc_total + g->kc_per_split - 1) / g->kc_per_split;
     const size_t stage = TG_A_BYTES + (size_t)BN * 128;
+    // pre-split B when it is re-read by many m-tiles (weights of the forward / data-gradient GEMMs)
+    g->b_pre = (passes == 3 && !want_split && !b_xform && g->mtiles >= 8) ? 1 : 0;
+    if (g->b_pre) {
+        int stages = 4;                                          // every stage owns a lo slot
+        while (stages > 2 && 1024 + 512 + (size_t)stages * 2 * stage > 220 * 1024) --stages;
+        if (1024 + 512 + (size_t)stages * 2 * stage > 227 * 1024) { g->b_pre = 0; }
+        else { g->stages = stages; g->nlo = stages; g->smem = 1024 + 512 + (size_t)stages * 2 * stage; return true; }
+    }
     const size_t fixed = 1024 + (passes == 3 ? TG_NLO * stage : 0) + 512;
     int stages = 6;
     while (stages > 2 && fixed + stages * stage > 220 * 1024) --stages;
     if (fixed + stages * stage > 227 * 1024) return false;
     g->stages = stages;
+    g->nlo = TG_NLO;
     g->smem = fixed + stages * stage;
     return true;
 }
 
 }  // namespace
 
+// B -> [hi plane | lo plane] (same layout twice)
+__global__ void __launch_bounds__(256) tg_presplit_kernel(const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float v = __ldg(b + i);
+    const float h = tc::tf32_rna(v);
+    out[i] = h;
+    out[n + i] = tc::tf32_lo(v, h);
+}
+
 extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k) {
-    if (!split_k) return 0;
+    if (!split_k) {
+        if (sb200_get_tc_mode() != 3) return 0;
+        TgGeom g;
+        if (!tg_geometry(M, N, K, b_mn, 3, 0, 0, &g) || !g.b_pre) return 0;
+        return 2 * (int64_t)N * K;                           // pre-split copy of B (hi plane, lo plane)
+    }
     TgGeom g;
     const int passes = sb200_get_tc_mode() == 1 ? 1 : 3;
-    if (!tg_geometry(M, N, K, b_mn, passes, 1, &g)) return 0;
+    if (!tg_geometry(M, N, K, b_mn, passes, 1, 0, &g)) return 0;
     return g.nsplit > 1 ? (int64_t)g.nsplit * M * N : 0;
 }
 
@@ -504,8 +574,17 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     TgGeom g;
     const int passes = mode == 1 ? 1 : 3;
     bool tc_ok = mode != 0 && tg_operand_ok(A, lda, a_mn, M, K) && tg_operand_ok(B, ldb, b_mn, N, K) &&
-                 tg_geometry(M, N, K, b_mn, passes, split_k, &g);
+                 tg_geometry(M, N, K, b_mn, passes, split_k, b_xform, &g);
     if (tc_ok && g.nsplit > 1 && workspace == nullptr) tc_ok = false;
+    if (tc_ok && g.b_pre && (workspace == nullptr || (ldb != (b_mn ? N : K)))) {
+        // no room for the pre-split copy (or a strided B): per-tile split instead
+        g.b_pre = 0;
+        const size_t stage = TG_A_BYTES + (size_t)g.BN * 128;
+        const size_t fixed = 1024 + TG_NLO * stage + 512;
+        int stages = 6;
+        while (stages > 2 && fixed + stages * stage > 220 * 1024) --stages;
+        g.stages = stages; g.nlo = TG_NLO; g.smem = fixed + stages * stage;
+    }
     if (!tc_ok) {
         FgParams f;
         f.A = A; f.a_sm = a_mn ? 1 : lda; f.a_sk = a_mn ? lda : 1;
@@ -524,7 +603,7 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     p.M = M; p.N = N; p.K = K; p.BN = g.BN; p.a_mn = a_mn; p.b_mn = b_mn;
     p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.nsplit = g.nsplit; p.kc_total = g.kc_total; p.kc_per_split = g.kc_per_split;
     p.nunits = (uint32_t)g.mtiles * (uint32_t)g.ntiles * (uint32_t)g.nsplit;
-    p.stages = g.stages; p.R = g.R;
+    p.stages = g.stages; p.R = g.R; p.nlo = g.nlo; p.b_pre = g.b_pre;
     p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.aux = aux; p.ld_aux = ld_aux; p.resid = resid; p.ld_res = ld_res;
     p.res_rows = res_rows; p.a_xform = a_xform; p.b_xform = b_xform;
     {
@@ -536,24 +615,66 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * g.BN * (g.R + (passes == 3 ? 1 : 0)))) cols <<= 1;
     p.tmem_cols = cols;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBlo;
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmB, 0, sizeof(tmB));
+    memset(&tmBlo, 0, sizeof(tmBlo));
+    const float* Bhi = B;
+    if (g.b_pre) {
+        const int64_t nb = (int64_t)N * K;
+        sb_launch(tg_presplit_kernel, (unsigned)ceil_div64(nb, 256), 256, 0, st, B, workspace, nb);
+        SB_LAUNCH_CHECK();
+        Bhi = workspace;
+    }
     // K-major: dims {K, rows}, box {32, rows of the tile}.  MN-major: dims {rows, K}, box {32, 32}.
     if (a_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, 32, 32, 2)) return rc; }
     else      { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, 32, 128, 1)) return rc; }
-    if (b_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, 32, 32, 2)) return rc; }
-    else      { if (int rc = sb200_make_tmap_2d_f32(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 4, 32, (uint32_t)g.BN, 1)) return rc; }
+    for (int pl = 0; pl < (g.b_pre ? 2 : 1); ++pl) {
+        CUtensorMap* tm = pl ? &tmBlo : &tmB;
+        const float* bp = Bhi + (pl ? (int64_t)N * K : 0);
+        if (b_mn) { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, 32, 32, 2)) return rc; }
+        else      { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 4, 32, (uint32_t)g.BN, 1)) return rc; }
+    }
+    if (!g.b_pre) tmBlo = tmB;
     const unsigned nsm = (unsigned)sb200_num_sms();
     const unsigned grid = p.nunits < nsm ? p.nunits : nsm;
+#ifdef SB200_BRINGUP
+    static long long* trace_dev = nullptr;
+    const int want_trace = sb_env_int("SB200_TG_TRACE", 0);
+    if (want_trace) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 4 * 32 * 4 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 4 * 32 * 4 * sizeof(long long), st);
+        p.trace = trace_dev;
+    }
+#endif
     if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        sb_launch(tc_gemm_kernel<3>, grid, TG_THREADS, g.smem, st, tmA, tmB, p);
+        sb_launch(tc_gemm_kernel<3>, grid, TG_THREADS, g.smem, st, tmA, tmB, tmBlo, p);
     } else {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        sb_launch(tc_gemm_kernel<1>, grid, TG_THREADS, g.smem, st, tmA, tmB, p);
+        sb_launch(tc_gemm_kernel<1>, grid, TG_THREADS, g.smem, st, tmA, tmB, tmBlo, p);
     }
     SB_LAUNCH_CHECK();
+#ifdef SB200_BRINGUP
+    if (want_trace) {
+        static int calls = 0;
+        if (++calls == want_trace) {
+            long long h[4 * 32 * 4];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+            long long t0 = h[(0 * 32 + 0) * 4 + 0];
+            const char* names[4] = {"producer(wait0,wait1,issued)", "mma(wait0,wait1,committed)", "split(start,lag ok,full ok,done)", "unit(mma tempty0,tempty1; epi wake,done)"};
+            for (int r = 0; r < 4; ++r) {
+                printf("%s\n", names[r]);
+                for (int i = 0; i < (r == 3 ? 4 : 26); ++i) {
+                    printf("  %2d:", i);
+                    for (int e = 0; e < 4; ++e) printf(" %7lld", h[(r * 32 + i) * 4 + e] ? h[(r * 32 + i) * 4 + e] - t0 : -1);
+                    printf("\n");
+                }
+            }
+        }
+    }
+#endif
     if (g.nsplit > 1) {
         sb_launch(tg_splitk_reduce_kernel, (unsigned)ceil_div64((int64_t)M * N, 256), 256, 0, st, (const float*)workspace, D, ldd,
                   M, N, g.nsplit);
