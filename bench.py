@@ -533,7 +533,7 @@ def run_afno(args, wl, rank, world, local_rank):
     hloss = torch.zeros((), pin_memory=True)
     lib = _lib.load()
     if args.tc_mode is not None:
-        lib.sb200_set_tc_mode(args.tc_mode)
+        _lib.set_tc_mode(args.tc_mode)
 
     def step_eager():
         if sync:
@@ -623,7 +623,7 @@ def run_afno(args, wl, rank, world, local_rank):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "global_batch": B * world, "grid": [H, W], "parallelism": f"dp{world}",
                            "step": "fwd+MSE+bwd+Adam(fused)", "cuda_graph": step is not step_eager,
-                           "tc_mode": int(lib.sb200_get_tc_mode()),
+                           "tc_mode": int(_lib.tc_mode()),
                            "l2": "working set (saved activations of 8 blocks incl. the 4x hidden tensors, > 2 GB) exceeds the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",
@@ -745,7 +745,7 @@ def run_b200(args, wl, rank, world, local_rank):
     from dlwp_benchmark_b200 import _lib
     lib = _lib.load()
     if args.tc_mode is not None:
-        lib.sb200_set_tc_mode(args.tc_mode)
+        _lib.set_tc_mode(args.tc_mode)
     step_eager()                                   # also the first-touch of plans / workspaces
     torch.cuda.synchronize()
     n0 = lib.sb200_kernel_launches()
@@ -902,7 +902,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(wl, world),
-            "run": {"cuda_graph": bool(use_graph), "graph_scope": graph_mode, "tc_mode": int(lib.sb200_get_tc_mode()),
+            "run": {"cuda_graph": bool(use_graph), "graph_scope": graph_mode, "tc_mode": int(_lib.tc_mode()),
                     "optimizer": "Adam(fused, capturable)", "grad_sync": "GradSync(direct sinks, 1 AVG all-reduce)" if sync else None},
             "clocks": clocks,
             "e2e": {"value": B * world * args.steps / t_e2e, "unit": "samples/s",

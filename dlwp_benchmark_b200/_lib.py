@@ -23,28 +23,26 @@ SIGNATURES = {
     "sb200_last_error": (ctypes.c_char_p, []),
     "sb200_kernel_launches": (_i64, []),
     "sb200_device_arch": (_i, []),
-    "sb200_set_tc_mode": (_i, [_i]),
-    "sb200_get_tc_mode": (_i, []),
     "sb200_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _d, _d]),
     "sb200_plan_destroy": (_i, [_vp]),
-    "sb200_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "sb200_rowdft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _i]),
     "sb200_coldft_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "sb200_coldft_inv": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "sb200_analysis_scratch": (_i64, [_vp, _i64]),
-    "sb200_analysis": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "sb200_analysis": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i]),
     "sb200_modes_gemm": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
-    "sb200_mlp_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_mlp_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _i]),
     "sb200_mlp_head_bwd_workspace": (_i64, []),
-    "sb200_mlp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
-    "sb200_lift_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
-    "sb200_lift_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
-    "sb200_lift_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "sb200_mlp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _i]),
+    "sb200_lift_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _i]),
+    "sb200_lift_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _i]),
+    "sb200_lift_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _i]),
     "sb200_cgemm_workspace": (_i64, [_vp, _i]),
     "sb200_cgemm_grouped": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb200_cgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
-    "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64]),
-    "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "sb200_rowidft_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
+    "sb200_pointwise_wgrad_workspace": (_i64, [_i, _i, _i, _i64, _i]),
+    "sb200_pointwise_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _i]),
     "sb200_pointwise_small_n": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp]),
     "sb200_wgrad_small_workspace": (_i64, [_i, _i, _i, _i64]),
     "sb200_wgrad_small": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp]),
@@ -59,9 +57,9 @@ SIGNATURES = {
     "sb200_afno_blocklinear_wgrad": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "sb200_gelu_fwd": (_i, [_vp, _vp, _i64, _vp]),
     "sb200_gelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "sb200_gemm_workspace": (_i64, [_i, _i, _i, _i, _i]),
+    "sb200_gemm_workspace": (_i64, [_i, _i, _i, _i, _i, _i]),
     "sb200_gemm": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64,
-                        _i, _i, _i, _vp, _vp]),
+                        _i, _i, _i, _vp, _vp, _i]),
     "sb200_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp]),
     "sb200_layernorm_bwd_workspace": (_i64, [_i64, _i]),
     "sb200_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
@@ -96,6 +94,24 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+# Precision mode of the tensor-core stages (0 = CUDA-core fp32, 1 = single-pass TF32, 3 = 3xTF32 parity mode): host-side
+# state, handed to the library as an argument of every call (the library itself is stateless).
+_tc_mode = 3
+
+
+def set_tc_mode(mode: int) -> int:
+    """Set the precision mode used by every later call (forward and backward); returns the previous mode."""
+    global _tc_mode
+    if mode not in (0, 1, 3):
+        raise SpectralB200Error(f"tc mode must be 0, 1 or 3, got {mode!r}")
+    prev, _tc_mode = _tc_mode, int(mode)
+    return prev
+
+
+def tc_mode() -> int:
+    return _tc_mode
 
 
 def on_tensor_device(fn):

@@ -65,6 +65,18 @@ extern unsigned long long g_sb200_launches;
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Precision mode of the tensor-core stages (0 = CUDA-core fp32 kernels only, 1 = single-pass TF32, 3 = 3xTF32 parity
+// mode).  It is an ARGUMENT of every entry point that has tensor-core kernels behind it: the library keeps no mode of
+// its own.  Inside a call the value travels in a thread-local that the entry point sets and restores (SbModeScope), so
+// internal helpers need no extra parameter and concurrent calls from different threads cannot see each other's mode.
+extern thread_local int sb200_tl_mode;
+struct SbModeScope {
+    int prev;
+    explicit SbModeScope(int m) : prev(sb200_tl_mode) { sb200_tl_mode = (m == 0 || m == 1 || m == 3) ? m : 3; }
+    ~SbModeScope() { sb200_tl_mode = prev; }
+};
+static inline int sb_tc_mode() { return sb200_tl_mode; }
+
 // SM count of the CURRENT device (per-device cache; the library is used from one process per GPU, but nothing
 // stops a caller from driving several devices from one process).  Defined in plan.cu.
 int sb200_num_sms();

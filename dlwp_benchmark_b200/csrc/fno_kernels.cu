@@ -85,7 +85,8 @@ rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab, f
 int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, cudaStream_t st,
                         int* handled);   // tc_rowdft.cu
 
-extern "C" int sb200_rowdft_fwd(sb200_plan_t p, int pass, const float* x, float* T, int64_t rows, void* stream) {
+extern "C" int sb200_rowdft_fwd(sb200_plan_t p, int pass, const float* x, float* T, int64_t rows, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(p && x && T, "rowdft_fwd: NULL argument");
     SB_REQUIRE(pass == 0 || pass == 1, "rowdft_fwd: pass must be 0 or 1");
     if (rows <= 0) return 0;
@@ -358,7 +359,8 @@ extern "C" int64_t sb200_analysis_scratch(sb200_plan_t p, int64_t nimg) {
     return nimg * p->H * p->Mx * 2;
 }
 
-extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream) {
+extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(p && x && Xh, "analysis: NULL argument");
     SB_REQUIRE(pass == 0 || pass == 1, "analysis: pass must be 0 or 1");
     if (nimg <= 0) return 0;
@@ -372,7 +374,7 @@ extern "C" int sb200_analysis(sb200_plan_t p, int pass, const float* x, float* X
     SB_REQUIRE(scratch != nullptr, "analysis: this grid needs sb200_analysis_scratch() floats of scratch");
     if (int rc = sb200_tc_analysis(p, pass, x, Xh, nimg, scratch, (cudaStream_t)stream, &handled)) return rc;   // tc_rowdft.cu
     if (handled) return 0;
-    if (int rc = sb200_rowdft_fwd(p, pass, x, scratch, nimg * p->H, stream)) return rc;
+    if (int rc = sb200_rowdft_fwd(p, pass, x, scratch, nimg * p->H, stream, sb_tc_mode())) return rc;
     return sb200_coldft_fwd(p, pass, scratch, Xh, nimg, stream);
 }
 

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+thread_local int sb200_tl_mode = 3;
 
 void sb200_set_error(const char* fmt, ...) {
     va_list ap;

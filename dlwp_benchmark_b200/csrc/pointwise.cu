@@ -159,7 +159,8 @@ static int launch_small_m(const PwParams& p, cudaStream_t st);
 extern "C" int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float* Phi, const float* A, const float* Wp,
                                        int64_t w_sn, int64_t w_sm, const float* bias, const float* zprev,
                                        float* z_out, float* y_out, int B, int M, int N, int mode, int apply_act,
-                                       void* stream) {
+                                       void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(plan && y_out, "rowidft_pointwise: NULL plan/output");
     SB_REQUIRE(pass == 0 || pass == 1, "rowidft_pointwise: pass must be 0 or 1");
     SB_REQUIRE(mode == 0 || mode == 1, "rowidft_pointwise: mode must be 0 or 1");
@@ -330,7 +331,8 @@ int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);         
 int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
                              int64_t HW, float* workspace, cudaStream_t st, int* handled);
 
-extern "C" int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
+extern "C" int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     int64_t px; int cpb;
     wgrad_chunking(B, HW, &px, &cpb);
     const int64_t a = (int64_t)B * cpb * ((int64_t)Cout * Cin + Cout);
@@ -339,7 +341,8 @@ extern "C" int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int
 }
 
 extern "C" int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias, int B, int Cout, int Cin,
-                                     int64_t HW, float* workspace, void* stream) {
+                                     int64_t HW, float* workspace, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(g && x && gW && workspace, "pointwise_wgrad: NULL argument");
     SB_REQUIRE(HW % 4 == 0, "pointwise_wgrad: H*W=%lld must be a multiple of 4", (long long)HW);
     if (B <= 0) return 0;

@@ -23,7 +23,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-extern "C" int sb200_get_tc_mode(void);
 
 namespace {
 
@@ -546,15 +545,16 @@ __global__ void __launch_bounds__(256) tg_presplit_kernel(const float* __restric
     out[n + i] = tc::tf32_lo(v, h);
 }
 
-extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k) {
+extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     if (!split_k) {
-        if (sb200_get_tc_mode() != 3) return 0;
+        if (sb_tc_mode() != 3) return 0;
         TgGeom g;
         if (!tg_geometry(M, N, K, b_mn, 3, 0, 0, &g) || !g.b_pre) return 0;
         return 2 * (int64_t)N * K;                           // pre-split copy of B (hi plane, lo plane)
     }
     TgGeom g;
-    const int passes = sb200_get_tc_mode() == 1 ? 1 : 3;
+    const int passes = sb_tc_mode() == 1 ? 1 : 3;
     if (!tg_geometry(M, N, K, b_mn, passes, 1, 0, &g)) return 0;
     return g.nsplit > 1 ? (int64_t)g.nsplit * M * N : 0;
 }
@@ -562,7 +562,8 @@ extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split
 extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
                           int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
                           const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform,
-                          int b_xform, int split_k, float* workspace, void* stream) {
+                          int b_xform, int split_k, float* workspace, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(A && B && (D || zout), "gemm: NULL operand");
     SB_REQUIRE(D || !split_k, "gemm: split-K needs D");
     SB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive size");
@@ -570,7 +571,7 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     SB_REQUIRE(act != 2 || aux, "gemm: act 2 needs aux");
     SB_REQUIRE(!split_k || (!bias && act == 0 && !resid && !zout), "gemm: split-K has no fused epilogue");
     cudaStream_t st = (cudaStream_t)stream;
-    const int mode = sb200_get_tc_mode();
+    const int mode = sb_tc_mode();
     TgGeom g;
     const int passes = mode == 1 ? 1 : 3;
     bool tc_ok = mode != 0 && tg_operand_ok(A, lda, a_mn, M, K) && tg_operand_ok(B, ldb, b_mn, N, K) &&

@@ -64,16 +64,7 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
     return 0;
 }
 
-// Precision mode of the tensor-core kernels: a process-wide DEFAULT (atomic), read once at the top of every entry
-// point.  0 = CUDA-core kernels only, 1 = TF32 single pass, 3 = 3xTF32 (fp32 parity).
-static int g_tc_mode_default = 3;
-extern "C" int sb200_set_tc_mode(int mode) {
-    SB_REQUIRE(mode == 0 || mode == 1 || mode == 3, "set_tc_mode: mode must be 0, 1 or 3");
-    __atomic_store_n(&g_tc_mode_default, mode, __ATOMIC_RELAXED);
-    return 0;
-}
-extern "C" int sb200_get_tc_mode(void) { return __atomic_load_n(&g_tc_mode_default, __ATOMIC_RELAXED); }
-#define g_tc_mode (sb200_get_tc_mode())
+#define g_tc_mode (sb_tc_mode())
 
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent, warp-specialised
@@ -949,7 +940,8 @@ static int tp_sms() {
 }
 
 extern "C" int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
-                                  float* y, int B, int M, int N, int64_t HW, void* stream) {
+                                  float* y, int B, int M, int N, int64_t HW, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(h && W1 && b1 && w2 && y, "mlp_head_fwd: NULL argument");
     if (B <= 0) return 0;
     unsigned grid;
@@ -960,7 +952,8 @@ extern "C" int64_t sb200_mlp_head_bwd_workspace(void) { return (int64_t)tp_sms()
 
 extern "C" int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const float* w2, const float* gy,
                                   float* gz1, float* gb1, float* gw2, float* gb2, float* workspace, int B, int M, int N,
-                                  int64_t HW, void* stream) {
+                                  int64_t HW, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(h && W1 && b1 && w2 && gy && gz1 && gb1 && gw2 && workspace, "mlp_head_bwd: NULL argument");
     if (B <= 0) return 0;
     unsigned grid;
@@ -975,7 +968,8 @@ extern "C" int sb200_mlp_head_bwd(const float* h, const float* W1, const float* 
 //   gb1[n] = sum gz1 and gw1[n] = sum gz1 x leave.   g [B,C,HW], W2 [C,256] (row-major), x [B,HW].
 extern "C" int sb200_lift_tail_bwd(const float* g, const float* W2, const float* w1, const float* b1, const float* x,
                                    float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW,
-                                   void* stream) {
+                                   void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(g && W2 && w1 && b1 && x && gw1 && gb1 && workspace, "lift_tail_bwd: NULL argument");
     if (B <= 0) return 0;
     unsigned grid;
@@ -991,7 +985,8 @@ extern "C" int sb200_lift_tail_bwd(const float* g, const float* W2, const float*
 //      y[b,c,p] = sum_n W2[c,n] gelu(w1[n] x[b,p] + b1[n]) + b2[c]
 // the hidden operand is generated tile by tile in shared memory (ASRC = 1), so it never reaches HBM.
 extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, float* y,
-                              int B, int N, int C, int64_t HW, void* stream) {
+                              int B, int N, int C, int64_t HW, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(x && w1 && b1 && W2 && y, "lift_fwd: NULL argument");
     SB_REQUIRE(g_tc_mode != 0, "lift_fwd: runs on the tcgen05 path (tc mode 1 or 3)");
     SB_REQUIRE(N == 256, "lift_fwd: hidden width must be 256 (got %d)", N);

@@ -26,7 +26,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-extern "C" int sb200_get_tc_mode(void);
 
 namespace {
 
@@ -307,7 +306,7 @@ static int tr_launch(const float* in, const float2* tab, float* out, int64_t row
 
 static bool tr_enabled() {
     static const bool disabled = sb_env_flag("SB200_TC_ROWDFT_OFF");      // experiments: force the FFMA kernels
-    return !disabled && sb200_get_tc_mode() != 0;
+    return !disabled && sb_tc_mode() != 0;
 }
 
 // public row stage (sb200_rowdft_fwd): x [rows][W] -> T [rows][Mx] interleaved complex
@@ -315,7 +314,7 @@ int sb200_tc_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, i
                         int* handled) {
     *handled = 0;
     if (!tr_enabled()) return 0;
-    const int passes = sb200_get_tc_mode();
+    const int passes = sb_tc_mode();
     int N, stages;
     size_t smem;
     if (!tr_fits(plan->W, 2 * plan->Mx, passes, &N, &stages, &smem)) return 0;
@@ -335,7 +334,7 @@ int sb200_tc_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, in
     if (!tr_enabled() || scratch == nullptr) return 0;
     static const bool col_off = sb_env_flag("SB200_TC_COLDFT_OFF");       // experiments: tensor-core row stage only
     if (col_off) return 0;
-    const int passes = sb200_get_tc_mode();
+    const int passes = sb_tc_mode();
     const int H = plan->H, W = plan->W, Mx = plan->Mx, My = plan->My;
     int N, stages;
     size_t smem;

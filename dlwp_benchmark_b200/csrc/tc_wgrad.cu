@@ -10,7 +10,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-extern "C" int sb200_get_tc_mode(void);
 
 constexpr int TW_WORKER_WARPS = 16;
 constexpr int TW_THREADS = 32 * (2 + TW_WORKER_WARPS);
@@ -328,7 +327,7 @@ static bool tw_geometry(int Cout, int Cin, int64_t HW, int* Pc, int* Qc, int* tr
 
 int64_t sb200_tc_wgrad_workspace(int B, int Cout, int Cin, int64_t HW) {
     int Pc, Qc, tr;
-    if (sb200_get_tc_mode() == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
+    if (sb_tc_mode() == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
     const int mblocks = (Pc + 127) / 128;
     return (int64_t)tw_num_sms() * mblocks * 128 * (Qc + 16) + (int64_t)B * Cout;
 }
@@ -338,7 +337,7 @@ static int tw_launch(const float* g, const float* x, float* gW, float* gbias, in
                      const float* gen_b1) {
     *handled = 0;
     const bool gen = gen_x != nullptr;
-    const int passes = sb200_get_tc_mode();
+    const int passes = sb_tc_mode();
     int Pc, Qc, tr;
     if (passes == 0 || !tw_geometry(Cout, Cin, HW, &Pc, &Qc, &tr)) return 0;
     if ((reinterpret_cast<uintptr_t>(g) & 15) || (!gen && (reinterpret_cast<uintptr_t>(x) & 15))) return 0;
@@ -426,9 +425,10 @@ int sb200_tc_pointwise_wgrad(const float* g, const float* x, float* gW, float* g
 // the hidden activations are regenerated on chip (ASRC = 1) instead of being re-read from HBM.
 // workspace: sb200_pointwise_wgrad_workspace(B, C, 256, HW) floats.
 extern "C" int sb200_lift_wgrad(const float* g, const float* x, const float* w1, const float* b1, float* gW2, float* gb2,
-                                float* workspace, int B, int C, int N, int64_t HW, void* stream) {
+                                float* workspace, int B, int C, int N, int64_t HW, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
     SB_REQUIRE(g && x && w1 && b1 && gW2 && workspace, "lift_wgrad: NULL argument");
-    SB_REQUIRE(sb200_get_tc_mode() != 0, "lift_wgrad: runs on the tcgen05 path (tc mode 1 or 3)");
+    SB_REQUIRE(sb_tc_mode() != 0, "lift_wgrad: runs on the tcgen05 path (tc mode 1 or 3)");
     SB_REQUIRE(N > C, "lift_wgrad: the hidden width (%d) must exceed the output channels (%d)", N, C);
     if (B <= 0) return 0;
     int handled = 0;

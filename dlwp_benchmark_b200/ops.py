@@ -59,7 +59,7 @@ def rowdft_fwd(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
     assert x.shape[-1] == plan.W
     rows = x.numel() // plan.W
     T = torch.empty(*x.shape[:-1], plan.Mx, 2, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.load().sb200_rowdft_fwd(plan.handle, pas, _p(x), _p(T), rows, _stream()), "rowdft_fwd")
+    _lib.check(_lib.load().sb200_rowdft_fwd(plan.handle, pas, _p(x), _p(T), rows, _stream(), _lib.tc_mode()), "rowdft_fwd")
     return T
 
 
@@ -94,7 +94,7 @@ def analysis(plan: Plan, pas: int, x: torch.Tensor) -> torch.Tensor:
         n = nimg * plan.H * plan.Mx * 2       # the fused kernel declines such inputs at launch: two-stage scratch
     scratch = torch.empty(n, device=x.device, dtype=torch.float32) if n > 0 else None
     Xh = torch.empty(*x.shape[:-2], plan.My, plan.Mx, 2, device=x.device, dtype=torch.float32)
-    _lib.check(lib.sb200_analysis(plan.handle, pas, _p(x), _p(Xh), nimg, _p(scratch), _stream()), "analysis")
+    _lib.check(lib.sb200_analysis(plan.handle, pas, _p(x), _p(Xh), nimg, _p(scratch), _stream(), _lib.tc_mode()), "analysis")
     return Xh
 
 
@@ -142,7 +142,7 @@ def rowidft_pointwise(plan: Plan, pas: int, Phi, A, Wp, w_sn, w_sm, bias, zprev,
     y = torch.empty(B, N, plan.H, plan.W, device=dev, dtype=torch.float32)
     z = torch.empty_like(y) if want_z else None
     _lib.check(_lib.load().sb200_rowidft_pointwise(plan.handle, pas, _p(Phi), _p(A), _p(Wp), w_sn, w_sm, _p(bias),
-                                                   _p(zprev), _p(z), _p(y), B, M, N, mode, int(apply_act), _stream()),
+                                                   _p(zprev), _p(z), _p(y), B, M, N, mode, int(apply_act), _stream(), _lib.tc_mode()),
                "rowidft_pointwise")
     return y, z
 
@@ -154,11 +154,11 @@ def pointwise_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True, ou
     Cin = x.shape[1]
     HW = g.shape[2] * g.shape[3]
     lib = _lib.load()
-    n = lib.sb200_pointwise_wgrad_workspace(B, Cout, Cin, HW)
+    n = lib.sb200_pointwise_wgrad_workspace(B, Cout, Cin, HW, _lib.tc_mode())
     ws = torch.empty(n, device=g.device, dtype=torch.float32)
     gW = _out(out_w, (Cout, Cin), g.device)
     gb = _out(out_b, (Cout,), g.device) if want_bias else None
-    _lib.check(lib.sb200_pointwise_wgrad(_p(g), _p(x), _p(gW), _p(gb), B, Cout, Cin, HW, _p(ws), _stream()),
+    _lib.check(lib.sb200_pointwise_wgrad(_p(g), _p(x), _p(gW), _p(gb), B, Cout, Cin, HW, _p(ws), _stream(), _lib.tc_mode()),
                "pointwise_wgrad")
     return gW, gb
 
@@ -253,7 +253,7 @@ def cgemm(A, B, C, *, M: int, N: int, K: int, sAm, sAk, sBk, sBn, sCm, sCn,
 def mlp_head_supported(M: int, N: int, n_out: int, HW: int) -> bool:
     """Shapes the fused head kernels cover (sb200_mlp_head_fwd / _bwd)."""
     return (n_out == 1 and N == 256 and M % 8 == 0 and (M <= 32 or M % 32 == 0) and HW % 4 == 0
-            and _lib.load().sb200_get_tc_mode() != 0)
+            and _lib.tc_mode() != 0)
 
 
 def mlp_head_fwd(h, W1, b1, w2, b2):
@@ -263,7 +263,7 @@ def mlp_head_fwd(h, W1, b1, w2, b2):
     B, M, H, W = h.shape
     y = torch.empty(B, 1, H, W, device=h.device, dtype=torch.float32)
     _lib.check(_lib.load().sb200_mlp_head_fwd(_p(h), _p(W1), _p(b1), _p(w2), _p(b2), _p(y), B, M, W1.shape[0], H * W,
-                                              _stream()), "mlp_head_fwd")
+                                              _stream(), _lib.tc_mode()), "mlp_head_fwd")
     return y
 
 
@@ -281,7 +281,7 @@ def mlp_head_bwd(h, W1, b1, w2, gy, want_gb2: bool = True, out_gb1=None, out_gw2
     gb2 = _out(out_gb2, (1,), dev) if want_gb2 else None
     ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=dev, dtype=torch.float32)
     _lib.check(lib.sb200_mlp_head_bwd(_p(h), _p(W1), _p(b1), _p(w2), _p(gy), _p(gz1), _p(gb1), _p(gw2), _p(gb2), _p(ws),
-                                      B, M, N, H * W, _stream()), "mlp_head_bwd")
+                                      B, M, N, H * W, _stream(), _lib.tc_mode()), "mlp_head_bwd")
     return gz1, gb1, gw2, gb2
 
 
@@ -297,13 +297,13 @@ def lift_tail_bwd(g, W2, w1, b1, x, out_gw1=None, out_gb1=None):
     gb1 = _out(out_gb1, (N,), g.device)
     ws = torch.empty(lib.sb200_mlp_head_bwd_workspace(), device=g.device, dtype=torch.float32)
     _lib.check(lib.sb200_lift_tail_bwd(_p(g), _p(W2), _p(w1), _p(b1), _p(x), _p(gw1), _p(gb1), _p(ws), B, C, N, H * W,
-                                       _stream()), "lift_tail_bwd")
+                                       _stream(), _lib.tc_mode()), "lift_tail_bwd")
     return gw1, gb1
 
 
 def lift_supported(C: int, N: int, HW: int) -> bool:
     """Shapes the generated-operand lifting kernels cover (1 input channel, hidden 256)."""
-    return (N == 256 and C % 16 == 0 and 16 <= C < N and HW % 4 == 0 and _lib.load().sb200_get_tc_mode() != 0)
+    return (N == 256 and C % 16 == 0 and 16 <= C < N and HW % 4 == 0 and _lib.tc_mode() != 0)
 
 
 def lift_fwd(x, w1, b1, W2, b2):
@@ -313,7 +313,7 @@ def lift_fwd(x, w1, b1, W2, b2):
     B, _, H, W = x.shape
     C, N = W2.shape
     y = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.load().sb200_lift_fwd(_p(x), _p(w1), _p(b1), _p(W2), _p(b2), _p(y), B, N, C, H * W, _stream()),
+    _lib.check(_lib.load().sb200_lift_fwd(_p(x), _p(w1), _p(b1), _p(W2), _p(b2), _p(y), B, N, C, H * W, _stream(), _lib.tc_mode()),
                "lift_fwd")
     return y
 
@@ -325,10 +325,10 @@ def lift_wgrad(g, x, w1, b1, want_bias: bool = True, out_w=None, out_b=None):
     B, C, H, W = g.shape
     N = w1.numel()
     lib = _lib.load()
-    ws = torch.empty(lib.sb200_pointwise_wgrad_workspace(B, C, N, H * W), device=g.device, dtype=torch.float32)
+    ws = torch.empty(lib.sb200_pointwise_wgrad_workspace(B, C, N, H * W, _lib.tc_mode()), device=g.device, dtype=torch.float32)
     gW2 = _out(out_w, (C, N), g.device)
     gb2 = _out(out_b, (C,), g.device) if want_bias else None
-    _lib.check(lib.sb200_lift_wgrad(_p(g), _p(x), _p(w1), _p(b1), _p(gW2), _p(gb2), _p(ws), B, C, N, H * W, _stream()),
+    _lib.check(lib.sb200_lift_wgrad(_p(g), _p(x), _p(w1), _p(b1), _p(gW2), _p(gb2), _p(ws), B, C, N, H * W, _stream(), _lib.tc_mode()),
                "lift_wgrad")
     return gW2, gb2
 
@@ -357,11 +357,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     D = None if z_only else _out(out, (M, N), dev)
     z = torch.empty(M, N, device=dev, dtype=torch.float32) if (want_z or z_only) else None
     lib = _lib.load()
-    nws = lib.sb200_gemm_workspace(M, N, K, int(b_mn), int(split_k))
+    nws = lib.sb200_gemm_workspace(M, N, K, int(b_mn), int(split_k), _lib.tc_mode())
     ws = torch.empty(nws, device=dev, dtype=torch.float32) if nws > 0 else None
     _lib.check(lib.sb200_gemm(_p(A), A.shape[1], int(a_mn), _p(B), B.shape[1], int(b_mn), _p(D), N, M, N, K, _p(bias), act,
                               _p(aux), N, _p(resid), N, res_rows, _p(z), N, int(a_gelu), int(b_gelu), int(split_k), _p(ws),
-                              _stream()), "gemm")
+                              _stream(), _lib.tc_mode()), "gemm")
     if z_only:
         return z
     return (D, z) if want_z else D

@@ -18,7 +18,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-extern "C" int sb200_get_tc_mode(void);
 
 namespace {
 
@@ -296,7 +295,7 @@ bool at_geometry(const sb200_plan_s* pl, int passes, AtGeom* g) {
 }  // namespace
 
 bool sb200_analysis_tc_supported(sb200_plan_t plan) {
-    const int mode = sb200_get_tc_mode();
+    const int mode = sb_tc_mode();
     if (mode == 0) return false;
     AtGeom g;
     return at_geometry(plan, mode == 1 ? 1 : 3, &g);
@@ -304,7 +303,7 @@ bool sb200_analysis_tc_supported(sb200_plan_t plan) {
 
 int sb200_analysis_tc(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, cudaStream_t st, int* handled) {
     *handled = 0;
-    const int mode = sb200_get_tc_mode();
+    const int mode = sb_tc_mode();
     if (mode == 0) return 0;
     const int passes = mode == 1 ? 1 : 3;
     AtGeom g;

@@ -41,13 +41,11 @@ const char* sb200_last_error(void);
 /* compute capability major*10+minor of the current device, or <0 when no device */
 int sb200_device_arch(void);
 
-/* Tensor-core mode of the GEMM-shaped stages: 0 = CUDA-core (exact fp32 FFMA) kernels only,
- * 1 = tcgen05 kind::tf32 single pass (parity ~1e-3), 3 = tcgen05 3xTF32 split (parity <= 1e-5; default).
- * Shapes the tcgen05 kernels do not cover always run on the CUDA-core kernels.
- * This is a process-wide DEFAULT (stored atomically, read once per entry point); it is the only mutable
- * library state besides the plan cache and the launch counter. */
-int sb200_set_tc_mode(int mode);
-int sb200_get_tc_mode(void);
+/* Precision mode of the GEMM-shaped stages -- the trailing `tc_mode` argument of every entry point that has
+ * tensor-core kernels behind it:  0 = CUDA-core (exact fp32 FFMA) kernels only, 1 = tcgen05 kind::tf32 single pass
+ * (parity <= 1e-2 over a 20-step rollout), 3 = tcgen05 3xTF32 split (parity <= 1e-5; any other value means 3).
+ * Shapes the tcgen05 kernels do not cover always run on the CUDA-core kernels.  The library keeps NO mode of its own:
+ * the only mutable library state is the plan cache, a launch counter and a thread-local error string. */
 
 
 /* ---- plans ---------------------------------------------------------------------------
@@ -70,7 +68,7 @@ int sb200_plan_destroy(sb200_plan_t plan);
  * replaces torch.fft.rfftn + fftshift + slice (neuralop SpectralConv.forward) */
 /* x [rows, W] real  ->  T [rows, Mx] complex   (rows = B*C*H).  With tc mode 1 / 3 and W a multiple of 32 (>= 64) this
  * is a tcgen05 GEMM against the twiddle matrix (tc_rowdft.cu), else the fp32 FFMA kernel. */
-int sb200_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, void* stream);
+int sb200_rowdft_fwd(sb200_plan_t plan, int pass, const float* x, float* T, int64_t rows, void* stream, int tc_mode);
 /* T [nimg, H, Mx] complex -> Xh [nimg, My, Mx] complex */
 int sb200_coldft_fwd(sb200_plan_t plan, int pass, const float* T, float* Xh, int64_t nimg, void* stream);
 /* Yh [nimg, My, Mx] complex -> Phi [nimg, H, Mx] complex
@@ -84,7 +82,7 @@ int sb200_coldft_inv(sb200_plan_t plan, int pass, const float* Yh, float* Phi, i
  * transposed intermediate in `scratch` (layout private to the library).
  * replaces torch.fft.rfftn + fftshift + slice (pass 0) / the adjoint of irfftn (pass 1). */
 int64_t sb200_analysis_scratch(sb200_plan_t plan, int64_t nimg);
-int sb200_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream);
+int sb200_analysis(sb200_plan_t plan, int pass, const float* x, float* Xh, int64_t nimg, float* scratch, void* stream, int tc_mode);
 
 /* Batched-over-modes complex contraction
  *      out[p,q,k] = sum_r opA(A[r,p,k]) * opB(B[r,q,k]),   k contiguous,
@@ -103,7 +101,7 @@ int sb200_modes_gemm(const float* A, int64_t sAr, int64_t sAp,
  * Restrictions (else non-zero return, caller uses the two-kernel path): N == 256, M % 8 == 0 (M % 32 == 0
  * above 32), HW % 4 == 0, tc mode != 0. */
 int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const float* w2, const float* b2,
-                       float* y, int B, int M, int N, int64_t HW, void* stream);
+                       float* y, int B, int M, int N, int64_t HW, void* stream, int tc_mode);
 /* Backward, stage 1: recomputes z1 = W1 h + b1 on the tensor cores and writes
  *      gz1[b,n,p] = w2[n] gy[b,p] gelu'(z1[b,n,p])          (input of the W1 weight / data gradient kernels)
  *      gb1[n] = sum_{b,p} gz1,   gw2[n] = sum_{b,p} gy gelu(z1),   gb2 = sum gy   (gb2 may be NULL)
@@ -111,7 +109,7 @@ int sb200_mlp_head_fwd(const float* h, const float* W1, const float* b1, const f
 int64_t sb200_mlp_head_bwd_workspace(void);
 int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const float* w2, const float* gy,
                        float* gz1, float* gb1, float* gw2, float* gb2, float* workspace, int B, int M, int N,
-                       int64_t HW, void* stream);
+                       int64_t HW, void* stream, int tc_mode);
 
 /* Backward of the first lifting layer when the model has ONE input channel (neuralop FNO.lifting =
  * MLP(in_channels=1, hidden=256, out=C); src/nsbench/configs/model/fno.yaml): with g = gradient wrt the lifting
@@ -120,19 +118,19 @@ int sb200_mlp_head_bwd(const float* h, const float* W1, const float* b1, const f
  *      gb1[n] = sum_{b,p} gz1,     gw1[n] = sum_{b,p} gz1 x[b,p]
  * Same restrictions and workspace as sb200_mlp_head_bwd (N == 256, C % 8 == 0, ...). */
 int sb200_lift_tail_bwd(const float* g, const float* W2, const float* w1, const float* b1, const float* x,
-                        float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW, void* stream);
+                        float* gw1, float* gb1, float* workspace, int B, int C, int N, int64_t HW, void* stream, int tc_mode);
 
 /* Lifting MLP of a ONE-input-channel model, forward:   y[b,c,p] = sum_n W2[c,n] gelu(w1[n] x[b,p] + b1[n]) + b2[c]
  * (neuralop FNO.lifting = MLP(1 -> 256 -> C)).  The 256-channel hidden operand is generated tile by tile in
  * shared memory and consumed by tcgen05.mma: it never exists in HBM.  x [B,HW], W2 [C,256], y [B,C,HW];
  * N == 256, C % 16 == 0, HW % 4 == 0, tc mode != 0. */
 int sb200_lift_fwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, float* y,
-                   int B, int N, int C, int64_t HW, void* stream);
+                   int B, int N, int C, int64_t HW, void* stream, int tc_mode);
 /* ... and the weight gradient of its second layer with the hidden activations regenerated on chip:
  *      gW2[c,n] = sum_{b,p} g[b,c,p] gelu(w1[n] x[b,p] + b1[n]),   gb2[c] = sum_{b,p} g[b,c,p]   (gb2 may be NULL)
  * workspace: sb200_pointwise_wgrad_workspace(B, C, N, HW) floats. */
 int sb200_lift_wgrad(const float* g, const float* x, const float* w1, const float* b1, float* gW2, float* gb2,
-                     float* workspace, int B, int C, int N, int64_t HW, void* stream);
+                     float* workspace, int B, int C, int N, int64_t HW, void* stream, int tc_mode);
 
 /* Strided complex GEMM   C[m,n] = sum_k opA(A[m,k]) * opB(B[k,n])   (complex64, strides in complex elements).
  * m and k may be two-level composite indices: m -> (m / M2, m % M2) addressed with (s?m1, s?m2), likewise k
@@ -168,15 +166,15 @@ int sb200_rowidft_pointwise(sb200_plan_t plan, int pass, const float* Phi,
                             const float* A, const float* Wp, int64_t w_sn, int64_t w_sm,
                             const float* bias, const float* zprev,
                             float* z_out, float* y_out,
-                            int B, int M, int N, int mode, int apply_act, void* stream);
+                            int B, int M, int N, int mode, int apply_act, void* stream, int tc_mode);
 
 /* Weight / bias gradient of the pointwise (1x1) channel mix:
  *   gW[o,i] = sum_{b,p} g[b,o,p] * x[b,i,p]      gbias[o] = sum_{b,p} g[b,o,p]   (gbias may be NULL)
  * `workspace` must hold sb200_pointwise_wgrad_workspace(...) floats.  Deterministic (two-phase).
  * replaces the Conv2d weight-grad and bias-sum autograd nodes. */
-int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW);
+int64_t sb200_pointwise_wgrad_workspace(int B, int Cout, int Cin, int64_t HW, int tc_mode);
 int sb200_pointwise_wgrad(const float* g, const float* x, float* gW, float* gbias,
-                          int B, int Cout, int Cin, int64_t HW, float* workspace, void* stream);
+                          int B, int Cout, int Cin, int64_t HW, float* workspace, void* stream, int tc_mode);
 
 /* Pointwise layer with few output channels (N <= 8), e.g. the FNO projection's last 1x1 conv
  * (neuralop MLP.fcs[1], 256 -> out_channels):  acc[b,n,p] = sum_m Wp[n,m] A[b,m,p] + bias[n];
@@ -243,11 +241,11 @@ int sb200_gelu_bwd(const float* gy, const float* z, float* gz, int64_t n, void* 
  *   (sb200_gemm_workspace floats) are reduced in a fixed order; no fused epilogue.
  *   Bases and leading dimensions must be 16-byte multiples for the tensor-core path; anything else (and tc mode 0)
  *   runs the exact-fp32 CUDA-core kernel. */
-int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k);
+int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k, int tc_mode);
 int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
                int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
                const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform, int b_xform,
-               int split_k, float* workspace, void* stream);
+               int split_k, float* workspace, void* stream, int tc_mode);
 
 /* LayerNorm over the last (channel) axis of x [T, C] (biased variance, eps inside the sqrt: torch.nn.LayerNorm as
  * built at fourcastnet.py:236 norm_layer = partial(nn.LayerNorm, eps=1e-6)); mean / rstd [T] are saved for the backward.

@@ -26,7 +26,7 @@ x = torch.randn(B, 1, wl["H"], wl["W"], generator=torch.Generator().manual_seed(
 with torch.no_grad():
     y64, i64 = so.fno_forward({k: v.double() for k, v in sd.items()}, x.double(), wl["n_modes"], wl["L"], return_intermediates=True)
     y32, i32 = so.fno_forward(sd, x, wl["n_modes"], wl["L"], return_intermediates=True)
-    _lib.load().sb200_set_tc_mode(mode)
+    _lib.set_tc_mode(mode)
     m = m.cuda()
     xd = x.cuda()
     h = m.lifting(xd)

@@ -47,7 +47,7 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     wl = bench.WORKLOADS[name]
     if os.environ.get("SB200_TC_MODE"):
-        _lib.load().sb200_set_tc_mode(int(os.environ["SB200_TC_MODE"]))
+        _lib.set_tc_mode(int(os.environ["SB200_TC_MODE"]))
     table = {}
     B, C, H, W = wl["batch"], wl["hidden"], wl["H"], wl["W"]
     P = B * C * H * W

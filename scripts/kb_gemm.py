@@ -24,7 +24,7 @@ cases = {
 }
 lib = _lib.load()
 for mode in (3, 1):
-    lib.sb200_set_tc_mode(mode)
+    _lib.set_tc_mode(mode)
     for name, (fn, fl) in cases.items():
         for _ in range(2):
             fn()
@@ -36,7 +36,7 @@ for mode in (3, 1):
             ts.append(e0.elapsed_time(e1) * 1e3)
         t = sorted(ts)[len(ts) // 2]
         print(f"mode {mode}  {name:55s} {t:8.1f} us  {fl / t / 1e6:7.1f} TFLOP/s (fp32-equivalent)", flush=True)
-lib.sb200_set_tc_mode(3)
+_lib.set_tc_mode(3)
 a = torch.randn(T, C, device=dev)
 g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 y, m, r = ops.layernorm_fwd(a, g, b, 1e-6)

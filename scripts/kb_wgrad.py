@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dlwp_benchmark_b200 import ops, _lib
 if os.environ.get('SB200_TC_MODE'):
-    _lib.load().sb200_set_tc_mode(int(os.environ['SB200_TC_MODE']))
+    _lib.set_tc_mode(int(os.environ['SB200_TC_MODE']))
 B, C, H, W = 64, 64, 64, 64
 gs = [torch.randn(B, C, H, W, device='cuda') for _ in range(4)]
 xs = [torch.randn(B, C, H, W, device='cuda') for _ in range(4)]

@@ -11,8 +11,8 @@ for (B, Co, Ci, H, W) in ((64, 64, 64, 64, 64), (8, 64, 64, 64, 64), (64, 256, 6
     ref32 = torch.einsum("bop,bip->oi", g.flatten(2), x.flatten(2)).double()
     out = {}
     for mode in (0, 3, 1):
-        lib.sb200_set_tc_mode(mode)
+        _lib.set_tc_mode(mode)
         gW, gb = ops.pointwise_wgrad(g.to(dev), x.to(dev))
         out[mode] = rel(gW, ref)
-    lib.sb200_set_tc_mode(3)
+    _lib.set_tc_mode(3)
     print((B, Co, Ci, H, W), "ffma", out[0], "3xtf32", out[3], "tf32", out[1], "torch-cpu-fp32", rel(ref32, ref))

@@ -368,7 +368,7 @@ def test_odd_height_is_rejected_loudly():
 # tensor-core (tcgen05) pointwise kernel vs the CUDA-core kernel and the fp64 reference
 # ----------------------------------------------------------------------------------------------
 def _set_tc(mode):
-    pkg._lib.check(pkg._lib.load().sb200_set_tc_mode(mode), "set_tc_mode")
+    pkg._lib.set_tc_mode(mode)
 
 
 TC_SHAPES = [

@@ -158,9 +158,9 @@ def test_tf32_single_pass_mode_20_step_rollout_and_train_step():
     y = _rand(2, 1, 64, 64, seed=52)
     yo, lo, go = _oracle_step(sd, x0, y, (16, 16), 4)
     m = m.to(DEV)
-    old = lib.sb200_get_tc_mode()
+    old = _lib.tc_mode()
     try:
-        lib.sb200_set_tc_mode(1)
+        _lib.set_tc_mode(1)
         outs, x = [], x0.to(DEV)
         with torch.no_grad():
             for _ in range(20):
@@ -172,7 +172,7 @@ def test_tf32_single_pass_mode_20_step_rollout_and_train_step():
         F.mse_loss(out, y.to(DEV)).backward()
         worst = _check_grads(m, go, 1e-2)
     finally:
-        lib.sb200_set_tc_mode(old)
+        _lib.set_tc_mode(old)
     print(f"tf32 single pass: step-1 {e1:.2e}, step-20 {e20:.2e}, all {eall:.2e}, worst grad {worst}")
     assert e1 < 3e-3 and e20 < 1e-2 and eall < 1e-2
     assert e1 > 1e-6, "mode 1 produced fp32-exact results: the single-pass TF32 path did not run"

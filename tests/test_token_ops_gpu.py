@@ -34,12 +34,12 @@ def test_gemm_all_majors(M, N, K, a_mn, b_mn, mode, tol):
     want = A.double() @ B.double().t()
     Ad = (A.t().contiguous() if a_mn else A).to(DEV)
     Bd = (B.t().contiguous() if b_mn else B).to(DEV)
-    old = lib.sb200_get_tc_mode()
+    old = _lib.tc_mode()
     try:
-        lib.sb200_set_tc_mode(mode)
+        _lib.set_tc_mode(mode)
         got = ops.gemm(Ad, Bd, a_mn=a_mn, b_mn=b_mn)
     finally:
-        lib.sb200_set_tc_mode(old)
+        _lib.set_tc_mode(old)
     assert rel_l2(got, want) < tol
 
 
@@ -106,10 +106,10 @@ def test_gemm_gelu_operand_transform_and_z_only():
     zz = ops.gemm(x.to(DEV), W1.to(DEV), bias=b1.to(DEV), z_only=True)
     assert rel_l2(zz, x.double() @ W1.double().t() + b1.double()) < 2e-6
     lib = _lib.load()
-    old = lib.sb200_get_tc_mode()
+    old = _lib.tc_mode()
     try:
         for mode, tol in ((1, 2e-3), (0, 2e-6)):
-            lib.sb200_set_tc_mode(mode)
+            _lib.set_tc_mode(mode)
             assert rel_l2(ops.gemm(z.to(DEV), W2.to(DEV), a_gelu=True), h @ W2.double().t()) < tol
     finally:
-        lib.sb200_set_tc_mode(old)
+        _lib.set_tc_mode(old)
