@@ -60,6 +60,11 @@ SIGNATURES = {
     "sb200_gemm_workspace": (_i64, [_i, _i, _i, _i, _i, _i]),
     "sb200_gemm": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64,
                         _i, _i, _i, _vp, _vp, _i]),
+    "sb200_gemm_batched_workspace": (_i64, [_vp, _i]),
+    "sb200_gemm_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "sb200_afno_embed": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "sb200_afno_unembed": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "sb200_mask_mul": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "sb200_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, ctypes.c_float, _vp]),
     "sb200_layernorm_bwd_workspace": (_i64, [_i64, _i]),
     "sb200_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),

@@ -545,3 +545,72 @@ extern "C" int sb200_afno_blocklinear_wgrad(const float* a, const float* gout, c
     SB_LAUNCH_CHECK();
     return 0;
 }
+
+// ======================================================================================
+// Real embedding of the complex block weights for the tensor-core path (tc_gemm.cu, sb200_gemm_batched):
+//   out[(j,c'')] = sum_{(i,c)} in[(i,c)] * E[(j,c'')][(i,c)]  reproduces  out = in * (wr + i wi)  on interleaved (re, im) data
+// ======================================================================================
+__global__ void __launch_bounds__(256) afno_embed_kernel(const float* __restrict__ w, float* __restrict__ E, int nb, int Ni, int No) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;      // over E: [nb][No][2][Ni][2]
+    const int64_t total = (int64_t)nb * No * 2 * Ni * 2;
+    if (idx >= total) return;
+    const int c = (int)(idx & 1);
+    const int i = (int)((idx >> 1) % Ni);
+    const int cc = (int)((idx / (2 * Ni)) & 1);
+    const int j = (int)((idx / (4 * Ni)) % No);
+    const int b = (int)(idx / ((int64_t)4 * Ni * No));
+    const int64_t plane = (int64_t)nb * Ni * No;
+    const int64_t wi_ = ((int64_t)b * Ni + i) * No + j;
+    const float wr = __ldg(w + wi_), wim = __ldg(w + plane + wi_);
+    E[idx] = cc == 0 ? (c == 0 ? wr : -wim) : (c == 0 ? wim : wr);
+}
+__global__ void __launch_bounds__(256) afno_unembed_kernel(const float* __restrict__ gE, float* __restrict__ gw, int nb, int Ni, int No) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;      // over gw planes: [nb][Ni][No]
+    const int64_t plane = (int64_t)nb * Ni * No;
+    if (idx >= plane) return;
+    const int j = (int)(idx % No);
+    const int i = (int)((idx / No) % Ni);
+    const int b = (int)(idx / ((int64_t)Ni * No));
+    const float* e = gE + (((int64_t)b * No + j) * 2) * Ni * 2;      // E[b][j][cc][i][c]
+    const float e00 = __ldg(e + (0 * Ni + i) * 2 + 0), e01 = __ldg(e + (0 * Ni + i) * 2 + 1);
+    const float e10 = __ldg(e + (1 * Ni + i) * 2 + 0), e11 = __ldg(e + (1 * Ni + i) * 2 + 1);
+    gw[idx] = e00 + e11;
+    gw[plane + idx] = e10 - e01;
+}
+__global__ void __launch_bounds__(256) mask_mul_kernel(const float* __restrict__ g, const float* __restrict__ src, float* __restrict__ out,
+                                                       int64_t n, int kind) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g + i)), s = __ldg(reinterpret_cast<const float4*>(src + i));
+        float4 o;
+        o.x = (kind == 1 ? s.x > 0.f : s.x != 0.f) ? a.x : 0.f;
+        o.y = (kind == 1 ? s.y > 0.f : s.y != 0.f) ? a.y : 0.f;
+        o.z = (kind == 1 ? s.z > 0.f : s.z != 0.f) ? a.z : 0.f;
+        o.w = (kind == 1 ? s.w > 0.f : s.w != 0.f) ? a.w : 0.f;
+        *reinterpret_cast<float4*>(out + i) = o;
+    } else {
+        for (int64_t k = i; k < n; ++k) out[k] = (kind == 1 ? src[k] > 0.f : src[k] != 0.f) ? g[k] : 0.f;
+    }
+}
+extern "C" int sb200_afno_embed(const float* w, float* E, int nb, int Ni, int No, void* stream) {
+    SB_REQUIRE(w && E && nb > 0 && Ni > 0 && No > 0, "afno_embed: bad argument");
+    const int64_t total = (int64_t)nb * No * 2 * Ni * 2;
+    sb_launch(afno_embed_kernel, (unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream, w, E, nb, Ni, No);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int sb200_afno_unembed(const float* gE, float* gw, int nb, int Ni, int No, void* stream) {
+    SB_REQUIRE(gE && gw && nb > 0 && Ni > 0 && No > 0, "afno_unembed: bad argument");
+    const int64_t plane = (int64_t)nb * Ni * No;
+    sb_launch(afno_unembed_kernel, (unsigned)ceil_div64(plane, 256), 256, 0, (cudaStream_t)stream, gE, gw, nb, Ni, No);
+    SB_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int sb200_mask_mul(const float* g, const float* src, float* out, int64_t n, int kind, void* stream) {
+    SB_REQUIRE(g && src && out && n > 0 && (kind == 1 || kind == 2), "mask_mul: bad argument");
+    SB_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "mask_mul: pointers must be 16-byte aligned");
+    sb_launch(mask_mul_kernel, (unsigned)ceil_div64(n, 1024), 256, 0, (cudaStream_t)stream, g, src, out, n, kind);
+    SB_LAUNCH_CHECK();
+    return 0;
+}

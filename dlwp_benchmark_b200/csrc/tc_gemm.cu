@@ -49,10 +49,18 @@ struct TgParams {
     // direct epilogue (nsplit == 1)
     float* D; int64_t ldd;
     const float* bias;            // [N] or NULL
-    int act;                      // 0 none | 1 GELU | 2 multiply by GELU'(aux[m][n])
+    int act;                      // 0 none | 1 GELU | 2 multiply by GELU'(aux[m][n]) | 3 ReLU | 4 soft-shrink(lam) |
+                                  // 5 multiply by (aux > 0) | 6 multiply by (aux != 0)   (ReLU / soft-shrink backward masks)
     const float* aux; int64_t ld_aux;
     const float* resid; int64_t ld_res; int res_rows;   // residual row = m % res_rows when res_rows > 0 (pos_embed broadcast)
     float* zout; int64_t ld_z;    // pre-activation store or NULL
+    // batch of independent GEMMs of identical geometry (block-diagonal layers): batch bi shifts the TMA coordinates of the
+    // operands and the epilogue pointers; nothing is copied or gathered
+    int nbatch; uint32_t units_per_batch;
+    int a_off;                    // A: added to the dim-0 coordinate (K-major: k, MN-major: m) per batch
+    int b_off0, b_off1;           // B: added to the dim-0 / dim-1 coordinates per batch
+    int64_t d_off, bias_off;      // elements added to D / zout / aux / resid pointers, and to bias, per batch
+    float lam;                    // soft-shrink threshold (act 4)
     int a_xform, b_xform;         // 1: the operand is GELU(what lies in HBM), applied in the split pass (h = GELU(z) never stored)
     int vec_ok;                   // every epilogue pointer / leading dimension allows 16-byte accesses
     // split-K epilogue (nsplit > 1): ws[split][M][N]
@@ -117,6 +125,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
     // unit -> (m-tile, n-tile, k-split); n-tiles fastest so that concurrently running CTAs share the A rows in L2
     auto decode = [&](uint32_t u, int& m0, int& n0, int& kc0, int& kcn, uint32_t& split) {
+        u %= p.units_per_batch;
         split = u % (uint32_t)p.nsplit;
         const uint32_t t = u / (uint32_t)p.nsplit;
         n0 = (int)(t % (uint32_t)p.ntiles) * BN;
@@ -132,6 +141,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             for (uint32_t it = 0; it < my_units; ++it) {
                 int m0, n0, kc0, kcn; uint32_t split;
                 decode(first + it * stride, m0, n0, kc0, kcn, split);
+                const int bi = (int)((first + it * stride) / p.units_per_batch);
+                // batch shifts: K-major operands carry k in dim 0, MN-major operands carry the m / n index in dim 0
+                const int ak = p.a_mn ? 0 : bi * p.a_off, am = p.a_mn ? bi * p.a_off : 0;
+                const int bk = p.b_mn ? bi * p.b_off1 : bi * p.b_off0, bn = p.b_mn ? bi * p.b_off0 : bi * p.b_off1;
                 for (int kc = 0; kc < kcn; ++kc) {
                     const int k0 = (kc0 + kc) * 32;
                     TG_TRACE(0, gc, 0);
@@ -142,14 +155,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     tc::mbar_expect_tx(full_bar + s, stage_bytes + (p.b_pre ? b_bytes : 0u));
                     if (p.a_mn) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) tc::tma_load_2d(dA + i * 4096, &tmapA, m0 + 32 * i, k0, full_bar + s);
+                        for (int i = 0; i < 4; ++i) tc::tma_load_2d(dA + i * 4096, &tmapA, am + m0 + 32 * i, k0, full_bar + s);
                     } else {
-                        tc::tma_load_2d(dA, &tmapA, k0, m0, full_bar + s);
+                        tc::tma_load_2d(dA, &tmapA, ak + k0, m0, full_bar + s);
                     }
                     if (p.b_mn) {
-                        for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(dB + j * 4096, &tmapB, n0 + 32 * j, k0, full_bar + s);
+                        for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(dB + j * 4096, &tmapB, bn + n0 + 32 * j, bk + k0, full_bar + s);
                     } else {
-                        tc::tma_load_2d(dB, &tmapB, k0, n0, full_bar + s);
+                        tc::tma_load_2d(dB, &tmapB, bk + k0, bn + n0, full_bar + s);
                     }
                     if (p.b_pre) {                          // lo plane of B straight into the lo slot of this stage (nlo == S)
                         uint8_t* dL = Lo + s * stage_bytes + TG_A_BYTES;
@@ -291,6 +304,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             tc::tc_fence_after_sync();
             const int m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
+            const int64_t bi = (int64_t)((first + it * stride) / p.units_per_batch);
+            const int64_t eoff = bi * p.d_off;                 // D / zout / aux / resid shift of this batch
+            const float* bias_b = p.bias ? p.bias + bi * p.bias_off : nullptr;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * acc_cols;
             const uint32_t nacc = min(R, (uint32_t)kcn);     // main accumulators this unit actually wrote
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -315,7 +331,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 if (!row_ok || n >= p.N) continue;
                 const bool full16 = n + 16 <= p.N;
                 if (p.nsplit > 1) {
-                    float* dst = p.ws + ((int64_t)split * p.M + m) * p.N + n;
+                    float* dst = p.ws + (((int64_t)split * p.nbatch + bi) * p.M + m) * p.N + n;
                     if (full16 && (p.N & 3) == 0) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -330,16 +346,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_b + n + j));
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                        for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(bias_b + n + j);
                     }
                 }
                 if (p.zout) {
-                    float* zd = p.zout + (int64_t)m * p.ld_z + n;
+                    float* zd = p.zout + eoff + (int64_t)m * p.ld_z + n;
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(zd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -351,8 +367,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 if (p.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = gelu_f(v[j]);
+                } else if (p.act == 3) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] > p.lam ? v[j] - p.lam : (v[j] < -p.lam ? v[j] + p.lam : 0.f);
+                } else if (p.act == 5 || p.act == 6) {
+                    const float* ax = p.aux + eoff + (int64_t)m * p.ld_aux + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n + j < p.N) {
+                            const float q = __ldg(ax + j);
+                            v[j] = (p.act == 5 ? q > 0.f : q != 0.f) ? v[j] : 0.f;
+                        }
+                    }
                 } else if (p.act == 2) {
-                    const float* ax = p.aux + (int64_t)m * p.ld_aux + n;
+                    const float* ax = p.aux + eoff + (int64_t)m * p.ld_aux + n;
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
@@ -366,7 +397,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     }
                 }
                 if (p.resid) {
-                    const float* rs = p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n;
+                    const float* rs = p.resid + eoff + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n;
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
@@ -379,7 +410,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     }
                 }
                 if (p.D) {
-                    float* dst = p.D + (int64_t)m * p.ldd + n;
+                    float* dst = p.D + eoff + (int64_t)m * p.ldd + n;
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -402,12 +433,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
 // out[m][n] = sum_s ws[s][m][n]  (fixed order: deterministic)
 __global__ void __launch_bounds__(256) tg_splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int64_t ldd,
-                                                               int M, int N, int nsplit) {
+                                                               int M, int N, int nsplit, int nbatch, int64_t d_off) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (int64_t)M * N) return;
+    const int64_t per = (int64_t)M * N;
+    if (i >= per * nbatch) return;
     float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += ws[(int64_t)k * M * N + i];
-    out[(i / N) * ldd + (i % N)] = s;
+    for (int k = 0; k < nsplit; ++k) s += ws[(int64_t)k * per * nbatch + i];
+    const int64_t bi = i / per, r = i - bi * per;
+    out[bi * d_off + (r / N) * ldd + (r % N)] = s;
 }
 
 // exact-fp32 CUDA-core GEMM (tc mode 0 and shapes / alignments the tensor-core kernel does not take): 64 x 64 tile,
@@ -422,6 +455,7 @@ struct FgParams {
     const float* resid; int64_t ld_res; int res_rows;
     float* zout; int64_t ld_z;
     int a_xform, b_xform;
+    float lam;
 };
 __global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
     __shared__ float As[16][65], Bs[16][65];
@@ -467,6 +501,10 @@ __global__ void __launch_bounds__(256) ffma_gemm_kernel(const FgParams p) {
             if (p.zout) p.zout[(int64_t)m * p.ld_z + n] = v;
             if (p.act == 1) v = gelu_f(v);
             else if (p.act == 2) v *= gelu_grad_f(__ldg(p.aux + (int64_t)m * p.ld_aux + n));
+            else if (p.act == 3) v = fmaxf(v, 0.f);
+            else if (p.act == 4) v = v > p.lam ? v - p.lam : (v < -p.lam ? v + p.lam : 0.f);
+            else if (p.act == 5) v = __ldg(p.aux + (int64_t)m * p.ld_aux + n) > 0.f ? v : 0.f;
+            else if (p.act == 6) v = __ldg(p.aux + (int64_t)m * p.ld_aux + n) != 0.f ? v : 0.f;
             if (p.resid) v += __ldg(p.resid + (int64_t)(p.res_rows > 0 ? m % p.res_rows : m) * p.ld_res + n);
             if (p.D) p.D[(int64_t)m * p.ldd + n] = v;
         }
@@ -545,40 +583,51 @@ __global__ void __launch_bounds__(256) tg_presplit_kernel(const float* __restric
     out[n + i] = tc::tf32_lo(v, h);
 }
 
-extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k, int tc_mode) {
-    SbModeScope _mode(tc_mode);
+namespace {
+
+struct TgCall {
+    const float* A; int64_t lda; int a_mn; int64_t a_ext0, a_ext1;     // tensor-map extents: dim 0 (contiguous), dim 1
+    const float* B; int64_t ldb; int b_mn; int64_t b_ext0, b_ext1;
+    float* D; int64_t ldd;
+    int M, N, K;
+    const float* bias; int act; const float* aux; int64_t ld_aux;
+    const float* resid; int64_t ld_res; int res_rows;
+    float* zout; int64_t ld_z;
+    int a_xform, b_xform, split_k;
+    int nbatch, a_off, b_off0, b_off1; int64_t d_off, bias_off;
+    float lam;
+};
+
+int64_t tg_workspace(int M, int N, int K, int b_mn, int split_k, int nbatch) {
+    if (sb_tc_mode() == 0) return 0;
+    const int passes = sb_tc_mode() == 1 ? 1 : 3;
+    TgGeom g;
     if (!split_k) {
-        if (sb_tc_mode() != 3) return 0;
-        TgGeom g;
+        if (passes != 3 || nbatch > 1) return 0;
         if (!tg_geometry(M, N, K, b_mn, 3, 0, 0, &g) || !g.b_pre) return 0;
         return 2 * (int64_t)N * K;                           // pre-split copy of B (hi plane, lo plane)
     }
-    TgGeom g;
-    const int passes = sb_tc_mode() == 1 ? 1 : 3;
     if (!tg_geometry(M, N, K, b_mn, passes, 1, 0, &g)) return 0;
-    return g.nsplit > 1 ? (int64_t)g.nsplit * M * N : 0;
+    return g.nsplit > 1 ? (int64_t)g.nsplit * nbatch * M * N : 0;
 }
 
-extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
-                          int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
-                          const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform,
-                          int b_xform, int split_k, float* workspace, void* stream, int tc_mode) {
-    SbModeScope _mode(tc_mode);
-    SB_REQUIRE(A && B && (D || zout), "gemm: NULL operand");
-    SB_REQUIRE(D || !split_k, "gemm: split-K needs D");
-    SB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive size");
-    SB_REQUIRE(act >= 0 && act <= 2, "gemm: act must be 0, 1 or 2");
-    SB_REQUIRE(act != 2 || aux, "gemm: act 2 needs aux");
-    SB_REQUIRE(!split_k || (!bias && act == 0 && !resid && !zout), "gemm: split-K has no fused epilogue");
-    cudaStream_t st = (cudaStream_t)stream;
+int tg_run(const TgCall& c, float* workspace, cudaStream_t st) {
+    SB_REQUIRE(c.A && c.B && (c.D || c.zout), "gemm: NULL operand");
+    SB_REQUIRE(c.D || !c.split_k, "gemm: split-K needs D");
+    SB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0 && c.nbatch > 0, "gemm: non-positive size");
+    SB_REQUIRE(c.act >= 0 && c.act <= 6, "gemm: act must be 0..6");
+    SB_REQUIRE(!(c.act == 2 || c.act == 5 || c.act == 6) || c.aux, "gemm: this activation needs aux");
+    SB_REQUIRE(!c.split_k || (!c.bias && c.act == 0 && !c.resid && !c.zout), "gemm: split-K has no fused epilogue");
+    const int M = c.M, N = c.N, K = c.K;
     const int mode = sb_tc_mode();
     TgGeom g;
     const int passes = mode == 1 ? 1 : 3;
-    bool tc_ok = mode != 0 && tg_operand_ok(A, lda, a_mn, M, K) && tg_operand_ok(B, ldb, b_mn, N, K) &&
-                 tg_geometry(M, N, K, b_mn, passes, split_k, b_xform, &g);
+    bool tc_ok = mode != 0 && tg_operand_ok(c.A, c.lda, c.a_mn, M, K) && tg_operand_ok(c.B, c.ldb, c.b_mn, N, K) &&
+                 tg_geometry(M, N, K, c.b_mn, passes, c.split_k, c.b_xform, &g);
+    if (tc_ok && c.nbatch > 1 && ((c.a_off | c.b_off0 | c.b_off1) & 3)) tc_ok = false;     // TMA coordinates, keep 16-byte granules
     if (tc_ok && g.nsplit > 1 && workspace == nullptr) tc_ok = false;
-    if (tc_ok && g.b_pre && (workspace == nullptr || (ldb != (b_mn ? N : K)))) {
-        // no room for the pre-split copy (or a strided B): per-tile split instead
+    if (tc_ok && g.b_pre && (c.nbatch > 1 || workspace == nullptr || (c.ldb != (c.b_mn ? N : K)))) {
+        // no pre-split copy (batched, no room, or a strided B): per-tile split instead
         g.b_pre = 0;
         const size_t stage = TG_A_BYTES + (size_t)g.BN * 128;
         const size_t fixed = 1024 + TG_NLO * stage + 512;
@@ -587,32 +636,42 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
         g.stages = stages; g.nlo = TG_NLO; g.smem = fixed + stages * stage;
     }
     if (!tc_ok) {
-        FgParams f;
-        f.A = A; f.a_sm = a_mn ? 1 : lda; f.a_sk = a_mn ? lda : 1;
-        f.B = B; f.b_sn = b_mn ? 1 : ldb; f.b_sk = b_mn ? ldb : 1;
-        f.M = M; f.N = N; f.K = K; f.D = D; f.ldd = ldd; f.bias = bias; f.act = act; f.aux = aux; f.ld_aux = ld_aux;
-        f.resid = resid; f.ld_res = ld_res; f.res_rows = res_rows; f.zout = zout; f.ld_z = ld_z;
-        f.a_xform = a_xform; f.b_xform = b_xform;
-        dim3 grid((N + 63) / 64, (M + 63) / 64);
-        SB_REQUIRE(grid.y <= 65535, "gemm: M too large for the CUDA-core kernel");
-        sb_launch(ffma_gemm_kernel, grid, 256, 0, st, f);
-        SB_LAUNCH_CHECK();
+        // exact-fp32 CUDA-core kernel, one launch per batch
+        for (int bi = 0; bi < c.nbatch; ++bi) {
+            FgParams f;
+            f.A = c.A + (int64_t)bi * c.a_off; f.a_sm = c.a_mn ? 1 : c.lda; f.a_sk = c.a_mn ? c.lda : 1;
+            f.B = c.B + (int64_t)bi * ((int64_t)c.b_off1 * c.ldb + c.b_off0); f.b_sn = c.b_mn ? 1 : c.ldb; f.b_sk = c.b_mn ? c.ldb : 1;
+            f.M = M; f.N = N; f.K = K; f.D = c.D ? c.D + bi * c.d_off : nullptr; f.ldd = c.ldd;
+            f.bias = c.bias ? c.bias + bi * c.bias_off : nullptr; f.act = c.act;
+            f.aux = c.aux ? c.aux + bi * c.d_off : nullptr; f.ld_aux = c.ld_aux;
+            f.resid = c.resid ? c.resid + bi * c.d_off : nullptr; f.ld_res = c.ld_res; f.res_rows = c.res_rows;
+            f.zout = c.zout ? c.zout + bi * c.d_off : nullptr; f.ld_z = c.ld_z;
+            f.a_xform = c.a_xform; f.b_xform = c.b_xform; f.lam = c.lam;
+            dim3 grid((N + 63) / 64, (M + 63) / 64);
+            SB_REQUIRE(grid.y <= 65535, "gemm: M too large for the CUDA-core kernel");
+            sb_launch(ffma_gemm_kernel, grid, 256, 0, st, f);
+            SB_LAUNCH_CHECK();
+        }
         return 0;
     }
     TgParams p;
     memset(&p, 0, sizeof(p));
-    p.M = M; p.N = N; p.K = K; p.BN = g.BN; p.a_mn = a_mn; p.b_mn = b_mn;
+    p.M = M; p.N = N; p.K = K; p.BN = g.BN; p.a_mn = c.a_mn; p.b_mn = c.b_mn;
     p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.nsplit = g.nsplit; p.kc_total = g.kc_total; p.kc_per_split = g.kc_per_split;
-    p.nunits = (uint32_t)g.mtiles * (uint32_t)g.ntiles * (uint32_t)g.nsplit;
+    p.units_per_batch = (uint32_t)g.mtiles * (uint32_t)g.ntiles * (uint32_t)g.nsplit;
+    p.nunits = p.units_per_batch * (uint32_t)c.nbatch;
+    p.nbatch = c.nbatch; p.a_off = c.a_off; p.b_off0 = c.b_off0; p.b_off1 = c.b_off1; p.d_off = c.d_off; p.bias_off = c.bias_off;
+    p.lam = c.lam;
     p.stages = g.stages; p.R = g.R; p.nlo = g.nlo; p.b_pre = g.b_pre;
-    p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.aux = aux; p.ld_aux = ld_aux; p.resid = resid; p.ld_res = ld_res;
-    p.res_rows = res_rows; p.a_xform = a_xform; p.b_xform = b_xform;
+    p.D = c.D; p.ldd = c.ldd; p.bias = c.bias; p.act = c.act; p.aux = c.aux; p.ld_aux = c.ld_aux; p.resid = c.resid; p.ld_res = c.ld_res;
+    p.res_rows = c.res_rows; p.a_xform = c.a_xform; p.b_xform = c.b_xform;
     {
         auto al = [](const void* q, int64_t ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld & 3) == 0); };
-        p.vec_ok = al(D, ldd) && al(bias, 0) && al(aux, ld_aux) && al(resid, ld_res) && al(zout, ld_z);
+        p.vec_ok = al(c.D, c.ldd) && al(c.bias, 0) && al(c.aux, c.ld_aux) && al(c.resid, c.ld_res) && al(c.zout, c.ld_z) &&
+                   (c.d_off & 3) == 0 && (c.bias_off & 3) == 0;
     }
-    p.zout = zout; p.ld_z = ld_z; p.ws = workspace;
-    p.idesc = tc::make_idesc_tf32(128, g.BN, a_mn, b_mn);
+    p.zout = c.zout; p.ld_z = c.ld_z; p.ws = workspace;
+    p.idesc = tc::make_idesc_tf32(128, g.BN, c.a_mn, c.b_mn);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * g.BN * (g.R + (passes == 3 ? 1 : 0)))) cols <<= 1;
     p.tmem_cols = cols;
@@ -620,21 +679,21 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     memset(&tmA, 0, sizeof(tmA));
     memset(&tmB, 0, sizeof(tmB));
     memset(&tmBlo, 0, sizeof(tmBlo));
-    const float* Bhi = B;
+    const float* Bhi = c.B;
     if (g.b_pre) {
         const int64_t nb = (int64_t)N * K;
-        sb_launch(tg_presplit_kernel, (unsigned)ceil_div64(nb, 256), 256, 0, st, B, workspace, nb);
+        sb_launch(tg_presplit_kernel, (unsigned)ceil_div64(nb, 256), 256, 0, st, c.B, workspace, nb);
         SB_LAUNCH_CHECK();
         Bhi = workspace;
     }
-    // K-major: dims {K, rows}, box {32, rows of the tile}.  MN-major: dims {rows, K}, box {32, 32}.
-    if (a_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, 32, 32, 2)) return rc; }
-    else      { if (int rc = sb200_make_tmap_2d_f32(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, 32, 128, 1)) return rc; }
+    // K-major: dims {K extent, rows}, box {32, rows of the tile}.  MN-major: dims {rows extent, K extent}, box {32, 32}.
+    if (c.a_mn) { if (int rc = sb200_make_tmap_2d_f32(&tmA, c.A, (uint64_t)c.a_ext0, (uint64_t)c.a_ext1, (uint64_t)c.lda * 4, 32, 32, 2)) return rc; }
+    else        { if (int rc = sb200_make_tmap_2d_f32(&tmA, c.A, (uint64_t)c.a_ext0, (uint64_t)c.a_ext1, (uint64_t)c.lda * 4, 32, 128, 1)) return rc; }
     for (int pl = 0; pl < (g.b_pre ? 2 : 1); ++pl) {
         CUtensorMap* tm = pl ? &tmBlo : &tmB;
         const float* bp = Bhi + (pl ? (int64_t)N * K : 0);
-        if (b_mn) { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, 32, 32, 2)) return rc; }
-        else      { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 4, 32, (uint32_t)g.BN, 1)) return rc; }
+        if (c.b_mn) { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)c.b_ext0, (uint64_t)c.b_ext1, (uint64_t)c.ldb * 4, 32, 32, 2)) return rc; }
+        else        { if (int rc = sb200_make_tmap_2d_f32(tm, bp, (uint64_t)c.b_ext0, (uint64_t)c.b_ext1, (uint64_t)c.ldb * 4, 32, (uint32_t)g.BN, 1)) return rc; }
     }
     if (!g.b_pre) tmBlo = tmB;
     const unsigned nsm = (unsigned)sb200_num_sms();
@@ -677,9 +736,52 @@ extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B,
     }
 #endif
     if (g.nsplit > 1) {
-        sb_launch(tg_splitk_reduce_kernel, (unsigned)ceil_div64((int64_t)M * N, 256), 256, 0, st, (const float*)workspace, D, ldd,
-                  M, N, g.nsplit);
+        sb_launch(tg_splitk_reduce_kernel, (unsigned)ceil_div64((int64_t)M * N * c.nbatch, 256), 256, 0, st, (const float*)workspace,
+                  c.D, c.ldd, M, N, g.nsplit, c.nbatch, c.d_off);
         SB_LAUNCH_CHECK();
     }
     return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t sb200_gemm_workspace(int M, int N, int K, int b_mn, int split_k, int tc_mode) {
+    SbModeScope _mode(tc_mode);
+    return tg_workspace(M, N, K, b_mn, split_k, 1);
+}
+
+extern "C" int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* D, int64_t ldd,
+                          int M, int N, int K, const float* bias, int act, const float* aux, int64_t ld_aux,
+                          const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform,
+                          int b_xform, int split_k, float* workspace, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
+    SB_REQUIRE(act >= 0 && act <= 2, "gemm: act must be 0, 1 or 2");
+    TgCall c;
+    memset(&c, 0, sizeof(c));
+    c.A = A; c.lda = lda; c.a_mn = a_mn; c.a_ext0 = a_mn ? M : K; c.a_ext1 = a_mn ? K : M;
+    c.B = B; c.ldb = ldb; c.b_mn = b_mn; c.b_ext0 = b_mn ? N : K; c.b_ext1 = b_mn ? K : N;
+    c.D = D; c.ldd = ldd; c.M = M; c.N = N; c.K = K; c.bias = bias; c.act = act; c.aux = aux; c.ld_aux = ld_aux;
+    c.resid = resid; c.ld_res = ld_res; c.res_rows = res_rows; c.zout = zout; c.ld_z = ld_z;
+    c.a_xform = a_xform; c.b_xform = b_xform; c.split_k = split_k; c.nbatch = 1;
+    return tg_run(c, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int64_t sb200_gemm_batched_workspace(const sb200_gemm_desc* d, int tc_mode) {
+    SbModeScope _mode(tc_mode);
+    if (!d) return 0;
+    return tg_workspace(d->M, d->N, d->K, d->b_mn, d->split_k, d->nbatch);
+}
+
+extern "C" int sb200_gemm_batched(const sb200_gemm_desc* d, const float* A, const float* B, float* D, const float* bias,
+                                  const float* aux, float* workspace, void* stream, int tc_mode) {
+    SbModeScope _mode(tc_mode);
+    SB_REQUIRE(d != nullptr, "gemm_batched: NULL descriptor");
+    TgCall c;
+    memset(&c, 0, sizeof(c));
+    c.A = A; c.lda = d->lda; c.a_mn = d->a_mn; c.a_ext0 = d->a_ext0; c.a_ext1 = d->a_ext1;
+    c.B = B; c.ldb = d->ldb; c.b_mn = d->b_mn; c.b_ext0 = d->b_ext0; c.b_ext1 = d->b_ext1;
+    c.D = D; c.ldd = d->ldd; c.M = d->M; c.N = d->N; c.K = d->K; c.bias = bias; c.act = d->act; c.aux = aux; c.ld_aux = d->ldd;
+    c.split_k = d->split_k; c.nbatch = d->nbatch; c.a_off = d->a_off; c.b_off0 = d->b_off0; c.b_off1 = d->b_off1;
+    c.d_off = d->d_off; c.bias_off = d->bias_off; c.lam = d->lam;
+    return tg_run(c, workspace, (cudaStream_t)stream);
 }

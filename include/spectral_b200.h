@@ -247,6 +247,34 @@ int sb200_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ld
                const float* resid, int64_t ld_res, int res_rows, float* zout, int64_t ld_z, int a_xform, int b_xform,
                int split_k, float* workspace, void* stream, int tc_mode);
 
+/* A batch of independent GEMMs of identical geometry in ONE launch (block-diagonal layers: the AFNO2D block MLP of
+ * src/nsbench/models/fourcastnet/fourcastnet.py:95-121 as nb real-embedded complex GEMMs).  Batch bi shifts the operand
+ * coordinates and the output pointers; nothing is gathered or copied:
+ *   A: element (m,k) of batch bi at A[m*lda + k + bi*a_off] (a_mn = 0) or A[k*lda + m + bi*a_off] (a_mn = 1);
+ *   B: element (n,k) at B[(n + bi*b_off1)*ldb + k + bi*b_off0] (b_mn = 0) or B[(k + bi*b_off1)*ldb + n + bi*b_off0] (b_mn = 1);
+ *   D, aux (leading dimension ldd): + bi*d_off;  bias: + bi*bias_off.
+ * a_ext0/a_ext1, b_ext0/b_ext1: full extents of the arrays the operands are windows of (dim 0 = contiguous axis).
+ * act: 0 none | 3 ReLU | 4 soft-shrink(lam) | 5 multiply by (aux > 0) | 6 multiply by (aux != 0). */
+typedef struct sb200_gemm_desc {
+    int32_t M, N, K, nbatch;
+    int32_t a_mn, b_mn, act, split_k;
+    int32_t a_off, b_off0, b_off1, reserved;
+    int64_t lda, ldb, ldd;
+    int64_t a_ext0, a_ext1, b_ext0, b_ext1;
+    int64_t d_off, bias_off;
+    float lam; float reserved2;
+} sb200_gemm_desc;
+int64_t sb200_gemm_batched_workspace(const sb200_gemm_desc* d, int tc_mode);
+int sb200_gemm_batched(const sb200_gemm_desc* d, const float* A, const float* B, float* D, const float* bias,
+                       const float* aux, float* workspace, void* stream, int tc_mode);
+
+/* AFNO2D block weights w [2,nb,Ni,No] (index 0 real, 1 imaginary) <-> the real embedding E [nb][2*No][2*Ni] of the complex
+ * matrices (E[(j,0)][(i,0)] = wr, E[(j,0)][(i,1)] = -wi, E[(j,1)][(i,0)] = wi, E[(j,1)][(i,1)] = wr), and the adjoint map
+ * for gradients; out = g * mask(src) with kind 1: src > 0 (ReLU), 2: src != 0 (soft-shrink). */
+int sb200_afno_embed(const float* w, float* E, int nb, int Ni, int No, void* stream);
+int sb200_afno_unembed(const float* gE, float* gw, int nb, int Ni, int No, void* stream);
+int sb200_mask_mul(const float* g, const float* src, float* out, int64_t n, int kind, void* stream);
+
 /* LayerNorm over the last (channel) axis of x [T, C] (biased variance, eps inside the sqrt: torch.nn.LayerNorm as
  * built at fourcastnet.py:236 norm_layer = partial(nn.LayerNorm, eps=1e-6)); mean / rstd [T] are saved for the backward.
  * Backward: dx (+ dres, a gradient that bypasses the norm, added in the same pass), dgamma, dbeta.

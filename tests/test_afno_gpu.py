@@ -102,3 +102,31 @@ def test_afno_linear_when_mlp_is_dead():
         m.b2.zero_(); m.b1.zero_()
     x = 1e-3 * torch.randn(2, 32, 64, 256, device=DEV)
     assert torch.equal(m(x), x)
+
+
+@pytest.mark.parametrize("B,h,w,C,nb,fac,frac", [(2, 16, 32, 64, 2, 1, 1.0), (1, 32, 64, 128, 8, 1, 1.0), (2, 8, 8, 64, 4, 2, 1.0),
+                                                  (3, 16, 16, 256, 8, 1, 0.5)])
+def test_block_mlp_on_tensor_cores_vs_oracle(B, h, w, C, nb, fac, frac):
+    """Blocks of >= 16 channels: the block-diagonal complex MLP runs as batched real-embedded tcgen05 GEMMs
+    (sb200_gemm_batched) -- forward, input gradient and all four parameter gradients against the fp64 oracle."""
+    from oracle import afno_oracle as ao
+    torch.manual_seed(3)
+    m = pkg.AFNO2D(C, num_blocks=nb, hard_thresholding_fraction=frac, hidden_size_factor=fac)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(10.0)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, h, w, C, generator=g)
+    gy = torch.randn(B, h, w, C, generator=g)
+    leaves = [p.detach().double().requires_grad_(True) for p in (m.w1, m.b1, m.w2, m.b2)]
+    xo = x.double().requires_grad_(True)
+    yo = ao.afno2d_fft(xo, *leaves, nb, 0.01, frac)
+    yo.backward(gy.double())
+    m = m.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    y = m(xd)
+    y.backward(gy.to(DEV))
+    assert rel_l2(y, yo) < 1e-5
+    assert rel_l2(xd.grad, xo.grad) < 1e-5
+    for p, q in zip((m.w1, m.b1, m.w2, m.b2), leaves):
+        assert rel_l2(p.grad, q.grad) < 2e-5
