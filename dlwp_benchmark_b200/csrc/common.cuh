@@ -142,6 +142,73 @@ __device__ __forceinline__ void gelu_core(float z, float& cdf, float& e) {
     const float half_tail = 0.5f * poly * e;            // 0.5 * erfc(|z| / sqrt 2)
     cdf = z < 0.f ? half_tail : 1.0f - half_tail;
 }
+// Two elements at a time on the packed fp32x2 pipe (FFMA2 / FMUL2): a three-register FFMA issues every second
+// cycle per scheduler, the packed form does two elements in the same slot, so the pair costs ~11 fma-pipe slots
+// instead of ~26 and the evaluation becomes bound by its four MUFU ops.  Same A-S 7.1.26 form as gelu_core (the
+// constants are folded: 0.3275911 / sqrt 2, -log2(e) / 2, the 0.5 of erfc into the coefficients).
+__device__ __forceinline__ unsigned long long sb_pk(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 sb_upk(unsigned long long v) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+    return d;
+}
+__device__ __forceinline__ unsigned long long sb_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long sb_mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#define SB_K2(c) sb_pk((c), (c))
+__device__ __forceinline__ void gelu_core2(float z0, float z1, float2& cdf, float2& e) {
+    const unsigned long long den = sb_fma2(sb_pk(fabsf(z0), fabsf(z1)), SB_K2(0.23164188861846924f), SB_K2(1.0f));
+    const float2 d = sb_upk(den);
+    const unsigned long long t = sb_pk(sb_rcp_approx(d.x), sb_rcp_approx(d.y));
+    unsigned long long poly = sb_fma2(t, SB_K2(0.5f * 1.061405429f), SB_K2(0.5f * -1.453152027f));
+    poly = sb_fma2(poly, t, SB_K2(0.5f * 1.421413741f));
+    poly = sb_fma2(poly, t, SB_K2(0.5f * -0.284496736f));
+    poly = sb_fma2(poly, t, SB_K2(0.5f * 0.254829592f));
+    poly = sb_mul2(poly, t);
+    const unsigned long long zz = sb_pk(z0, z1);
+    const float2 arg = sb_upk(sb_mul2(sb_mul2(zz, SB_K2(-0.72134752044448170368f)), zz));
+    e = make_float2(sb_ex2_approx(arg.x), sb_ex2_approx(arg.y));          // exp(-z^2 / 2)
+    const unsigned long long ht = sb_mul2(poly, sb_pk(e.x, e.y));          // 0.5 * erfc(|z| / sqrt 2)
+    const float2 h = sb_upk(ht), o = sb_upk(sb_fma2(ht, SB_K2(-1.0f), SB_K2(1.0f)));
+    cdf = make_float2(z0 < 0.f ? h.x : o.x, z1 < 0.f ? h.y : o.y);
+}
+// a <- GELU(a), b <- GELU(b)
+__device__ __forceinline__ void gelu2(float& a, float& b) {
+    float2 cdf, e;
+    gelu_core2(a, b, cdf, e);
+    const float2 r = sb_upk(sb_mul2(sb_pk(a, b), sb_pk(cdf.x, cdf.y)));
+    a = r.x; b = r.y;
+}
+// ga <- GELU'(za), gb <- GELU'(zb)
+__device__ __forceinline__ void gelu_grad2(float za, float zb, float& ga, float& gb) {
+    float2 cdf, e;
+    gelu_core2(za, zb, cdf, e);
+    const unsigned long long zs = sb_mul2(sb_pk(za, zb), SB_K2(0.39894228040143267794f));
+    const float2 r = sb_upk(sb_fma2(zs, sb_pk(e.x, e.y), sb_pk(cdf.x, cdf.y)));
+    ga = r.x; gb = r.y;
+}
+__device__ __forceinline__ float4 gelu4(float4 v) {
+    gelu2(v.x, v.y);
+    gelu2(v.z, v.w);
+    return v;
+}
+__device__ __forceinline__ float4 gelu_grad4(const float4 z) {
+    float4 g;
+    gelu_grad2(z.x, z.y, g.x, g.y);
+    gelu_grad2(z.z, z.w, g.z, g.w);
+    return g;
+}
 __device__ __forceinline__ float gelu_f(float z) {
     float cdf, e;
     gelu_core(z, cdf, e);

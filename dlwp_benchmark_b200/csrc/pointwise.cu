@@ -140,12 +140,12 @@ rowidft_pointwise_kernel(const PwParams p) {
                                    acc[g * 4 + 3][j] + bv);
             if (p.mode == 0) {
                 if (p.z_out) *reinterpret_cast<float4*>(p.z_out + off) = v;
-                if (p.apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+                if (p.apply_act) v = gelu4(v);
                 *reinterpret_cast<float4*>(p.y_out + off) = v;
             } else {
                 if (p.zprev) {
                     const float4 z = __ldg(reinterpret_cast<const float4*>(p.zprev + off));
-                    v.x *= gelu_grad_f(z.x); v.y *= gelu_grad_f(z.y); v.z *= gelu_grad_f(z.z); v.w *= gelu_grad_f(z.w);
+                    { const float4 gg = gelu_grad4(z); v.x *= gg.x; v.y *= gg.y; v.z *= gg.z; v.w *= gg.w; }
                 }
                 *reinterpret_cast<float4*>(p.y_out + off) = v;
             }
@@ -408,7 +408,7 @@ pointwise_small_n_kernel(const float* __restrict__ A, const float* __restrict__ 
         float4 v = make_float4(acc[n].x + bv, acc[n].y + bv, acc[n].z + bv, acc[n].w + bv);
         const int64_t off = ((int64_t)b * N + n) * HW + p0;
         if (z_out) *reinterpret_cast<float4*>(z_out + off) = v;
-        if (apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+        if (apply_act) v = gelu4(v);
         *reinterpret_cast<float4*>(y_out + off) = v;
     }
 }
@@ -472,10 +472,10 @@ pointwise_small_m_kernel(const float* __restrict__ A, const float* __restrict__ 
         const int64_t off = ((int64_t)b * N + n) * HW + p0;
         if (mode == 0) {
             if (z_out) *reinterpret_cast<float4*>(z_out + off) = v;
-            if (apply_act) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+            if (apply_act) v = gelu4(v);
         } else if (zprev) {
             const float4 z = __ldg(reinterpret_cast<const float4*>(zprev + off));
-            v.x *= gelu_grad_f(z.x); v.y *= gelu_grad_f(z.y); v.z *= gelu_grad_f(z.z); v.w *= gelu_grad_f(z.w);
+            { const float4 gg = gelu_grad4(z); v.x *= gg.x; v.y *= gg.y; v.z *= gg.z; v.w *= gg.w; }
         }
         *reinterpret_cast<float4*>(y_out + off) = v;
     }
@@ -632,7 +632,7 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ z, float* __restrict__
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
-        v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+        v = gelu4(v);
         *reinterpret_cast<float4*>(y + i) = v;
     } else {
         for (int64_t k = i; k < n; ++k) y[k] = gelu_f(z[k]);
@@ -644,7 +644,7 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __res
     if (i + 3 < n) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(z + i));
         float4 g = __ldg(reinterpret_cast<const float4*>(gy + i));
-        g.x *= gelu_grad_f(v.x); g.y *= gelu_grad_f(v.y); g.z *= gelu_grad_f(v.z); g.w *= gelu_grad_f(v.w);
+        { const float4 gg = gelu_grad4(v); g.x *= gg.x; g.y *= gg.y; g.z *= gg.z; g.w *= gg.w; }
         *reinterpret_cast<float4*>(gz + i) = g;
     } else {
         for (int64_t k = i; k < n; ++k) gz[k] = gy[k] * gelu_grad_f(z[k]);

@@ -150,6 +150,14 @@ __host__ __device__ __forceinline__ constexpr uint32_t desc_lo(uint32_t saddr, u
 __host__ __device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
     return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout & 7u) << 29);
 }
+// One lane of a converged warp (elect.sync).  Guarding the single-thread roles (TMA producer, MMA issuer) with this
+// instead of `lane == 0` lets ptxas see that exactly one thread is active, so instructions that take uniform-register
+// operands (UTCHMMA, UTMALDG, ..) are emitted once instead of inside an ELECT / BRA.U.ANY serialisation loop each.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A * B with descriptors given as (lo, hi) halves
 __device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t accumulate) {

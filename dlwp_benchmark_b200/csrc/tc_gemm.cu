@@ -136,7 +136,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             uint32_t s = 0, ph = 0, gc = 0;
             for (uint32_t it = 0; it < my_units; ++it) {
                 int m0, n0, kc0, kcn; uint32_t split;
@@ -179,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             // K-major tile: 8-row atoms of 1024 B (SBO), k-step = +32 B.  MN-major tile: 32-row (mn) blocks 4096 B apart
             // (LBO), 4-k-row atoms of 512 B (SBO), k-step (8 k rows) = +1024 B.
             const uint32_t a_hi32 = p.a_mn ? tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B) : tc::desc_hi(1024, tc::LAYOUT_SW128);
@@ -257,6 +257,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         float4 v = ah[idx];
                         const bool xf = idx < nA4 ? p.a_xform : p.b_xform;
                         if (xf) {                                      // operand = GELU(stored pre-activation): never in HBM
+                            // (scalar form on purpose: with the packed gelu4 here the cfg4-width AFNO backward GEMMs of this same
+                            //  kernel lose their correction terms -- tests/test_fourcastnet_gpu.py::test_cfg4_width_vs_oracle,
+                            //  1e-3 instead of 5e-7 -- although this branch is not taken there; not understood, see NOTES.md)
                             v = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
                             if (PASSES != 3 || p.b_pre) ah[idx] = v;
                         }
@@ -366,7 +369,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 }
                 if (p.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = gelu_f(v[j]);
+                    for (int j = 0; j < 16; j += 2) gelu2(v[j], v[j + 1]);
                 } else if (p.act == 3) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -388,8 +391,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 z4 = __ldg(reinterpret_cast<const float4*>(ax + j));
-                            v[j] *= gelu_grad_f(z4.x); v[j + 1] *= gelu_grad_f(z4.y);
-                            v[j + 2] *= gelu_grad_f(z4.z); v[j + 3] *= gelu_grad_f(z4.w);
+                            const float4 gg = gelu_grad4(z4);
+                            v[j] *= gg.x; v[j + 1] *= gg.y; v[j + 2] *= gg.z; v[j + 3] *= gg.w;
                         }
                     } else {
 #pragma unroll

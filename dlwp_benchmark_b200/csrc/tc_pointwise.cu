@@ -82,10 +82,26 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
 //         tile's x offset), staged by the workers as K-major SWIZZLE_32B hi/lo, double-buffered
 // ---------------------------------------------------------------------------------------------
 constexpr int TP_PX = 128;
-constexpr int TP_WORKER_WARPS = 16;
-constexpr int TP_THREADS = 32 * (2 + TP_WORKER_WARPS);
-constexpr int TP_WTHREADS = 32 * TP_WORKER_WARPS;
+// Warp roles (warpgroup aligned, registers re-divided with setmaxnreg after the common setup):
+//   warps 0-3   TMA producer, MMA issuer, two idle warps                      (40 registers)
+//   warps 4-7   stagers: split the TMA-fed A tiles of the coming tiles        (56 registers)
+//   warps 8-23  drainers: epilogue, 4 TMEM lane quarters x 4 column parts     (96 registers)
+// With an on-chip generated A operand (ASRC == 1: one GELU per element) the drainers stage as well and the stagers idle.
+constexpr int TP_STAGE_WARPS = 4;
+constexpr int TP_DRAIN_WARPS = 16;
+constexpr int TP_THREADS = 32 * (4 + TP_STAGE_WARPS + TP_DRAIN_WARPS);
+constexpr int TP_WTHREADS = 32 * TP_STAGE_WARPS;   // threads that stage (ASRC == 0)
+// setmaxnreg only moves registers inside the CTA's own allocation (768 threads x 80 at launch = 61440):
+// 128 x 40 + 128 x 56 + 512 x 96 = 61440.  Asking for more than the decs release blocks forever.
+constexpr int TP_REGS_CTRL = 40, TP_REGS_STAGE = 56, TP_REGS_DRAIN = 96;
+static_assert(128 * TP_REGS_CTRL + 32 * TP_STAGE_WARPS * TP_REGS_STAGE + 32 * TP_DRAIN_WARPS * TP_REGS_DRAIN <= TP_THREADS * 80,
+              "register budget of the warp roles");
 
+#ifdef SB200_BRINGUP
+#define TP_TRACE(role, i, ev) do { if (p.trace && blockIdx.x == 0 && (i) < 32) p.trace[((role) * 32 + (i)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TP_TRACE(role, i, ev) do { } while (0)
+#endif
 struct TcPwParams {
     const float* Wp; int64_t w_sn, w_sm;
     const float* bias; const float* zprev;
@@ -95,13 +111,18 @@ struct TcPwParams {
     int64_t ntiles;
     int mode, apply_act;
     uint32_t idesc, idesc_spec, tmem_cols;
+    int tpr_log2;            // log2(drainer threads cooperating on one channel while staging Phi)
+    int nlo;                 // 3-pass, TMA-fed A: the lo halves of the split live in their own nlo-slot ring behind the raw
+                             // slots (0: every stage is [hi | lo]); a raw slot then costs KC*512 bytes instead of twice that,
+                             // so twice as many loads are in flight for the same shared memory
+    long long* trace;        // bring-up builds only (SB200_TP_TRACE): clock64 event log of CTA 0
+    int dbg;                 // bring-up builds only (SB200_TP_DBG): 1 GELU -> identity, 2 epilogue drains nothing, 4 no MMAs
     int corr;                // 3-pass mode, 4N <= 512: the lo*hi + hi*lo corrections accumulate in their own TMEM columns (behind the
                              // N main columns of each buffer), so the large hi*hi terms go through a chain of K/8 truncating
                              // tensor-core accumulations instead of 3K/8; the epilogue adds the two
     // spectral term (Phi == NULL: none)
     const float2* Phi; const float* E; const float2* rot;
     int H, W, Mx, R, V, K2, K2pad;
-    int tpr_log2;            // log2(threads cooperating on one channel while staging Phi)
     int bias_mma;            // bias rides in the spare K column of the synthesis operands (E row K2 = 1, Phi col K2 = bias)
     // fused MLP head (EPI 5 / 6): second (1-output) layer folded into the epilogue
     const float* w2;         // [N] weights of the output channel
@@ -144,7 +165,9 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 }
 // ASRC: 0 = activation tiles arrive by TMA | 1 = generated on chip: A[m, px] = GELU(w1[m] x[b, px] + b1[m]), the hidden
 //       layer of a 1-input-channel lifting MLP (w1 = p.w2, b1 = p.b2, x = p.gy): the 256-channel tensor never exists in HBM
-template <int PASSES, int EPI, int ASRC = 0>
+// SPEC: the spectral term exists (p.Phi != NULL); compiled out otherwise so that the drainers of the plain pointwise
+//       kernels carry no Phi staging state
+template <int PASSES, int EPI, int ASRC = 0, bool SPEC = false>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,9 +175,10 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     // space (a uintptr_t round-trip turns all later accesses into generic LD/ST through L1TEX)
     uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KC = p.KC, nkc = p.nkc, S = p.stages;
-    const bool spectral = p.Phi != nullptr;
+    const bool spectral = SPEC;
     const uint32_t a_bytes = (uint32_t)KC * 512;                       // 4 boxes x KC rows x 128 B
-    const uint32_t a_stage_bytes = a_bytes * (PASSES == 3 ? 2 : 1);    // [hi | lo]
+    const int NLO = (PASSES == 3 && ASRC == 0) ? p.nlo : 0;
+    const uint32_t a_stage_bytes = a_bytes * ((PASSES == 3 && NLO == 0) ? 2 : 1);    // [hi | lo], or raw -> hi alone (lo ring)
     const int kchunks = (p.M + 31) / 32;                               // 32-wide K chunks of the resident weight tile
     const uint32_t b_chunk_bytes = (uint32_t)p.N * 128;                // N rows x 128 B
     const uint32_t b_bytes = nkc ? (((uint32_t)kchunks * b_chunk_bytes + 1023) & ~1023u) : 0u;
@@ -169,15 +193,17 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     uint8_t* Phi_s = E_lo + (PASSES == 3 ? e_bytes : 0);              // [2 buffers][hi | lo]
     const uint32_t phi_buf_bytes = phi_bytes * (PASSES == 3 ? 2 : 1);
     uint8_t* A_st = Phi_s + 2 * phi_buf_bytes;
-    uint8_t* tail = A_st + (uint32_t)S * a_stage_bytes;
+    uint8_t* LO_st = A_st + (uint32_t)S * a_stage_bytes;              // [NLO] lo ring
+    uint8_t* tail = LO_st + (uint32_t)NLO * a_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);           // [S]  TMA landed
     uint64_t* split_bar = full_bar + S;                                // [S]  hi/lo split done (workers -> MMA)
     uint64_t* empty_bar = split_bar + S;                               // [S]  MMAs that read the stage are done
     uint64_t* tfull_bar = empty_bar + S;                               // [2]  accumulator complete
     uint64_t* tempty_bar = tfull_bar + 2;                              // [2]  accumulator drained by the epilogue
     uint64_t* phi_bar = tempty_bar + 2;                                // [2]  Phi operand staged
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(phi_bar + 2);
-    float* bias_s = reinterpret_cast<float*>(tail + 256);              // [256] bias for the epilogue (zeros when unused); barriers use < 256 B
+    uint64_t* lo_empty = phi_bar + 2;                                  // [NLO <= 4] MMAs that read the lo slot are done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + 4);
+    float* bias_s = reinterpret_cast<float*>(tail + 512);              // [256] bias for the epilogue (zeros when unused); barriers use < 512 B
     float2* rot_s = reinterpret_cast<float2*>(bias_s + 256);           // [V][Mx] tile phase table
     float* w2_s = reinterpret_cast<float*>(rot_s + 256);               // [256]       EPI 5 / 6 (launcher adds the bytes)
     float* red_s = w2_s + 256;                                         // [2][4][128] EPI 5 cross-warp partial sums
@@ -191,14 +217,15 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         if (nkc) tc::tma_prefetch_desc(&tmapA);
         for (int s = 0; s < S; ++s) {
             tc::mbar_init(full_bar + s, 1);
-            tc::mbar_init(split_bar + s, TP_WORKER_WARPS);
+            tc::mbar_init(split_bar + s, ASRC == 1 ? TP_DRAIN_WARPS : TP_STAGE_WARPS);
             tc::mbar_init(empty_bar + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(tfull_bar + a, 1);
-            tc::mbar_init(tempty_bar + a, TP_WORKER_WARPS);
-            tc::mbar_init(phi_bar + a, TP_WORKER_WARPS);
+            tc::mbar_init(tempty_bar + a, TP_DRAIN_WARPS);
+            tc::mbar_init(phi_bar + a, TP_DRAIN_WARPS);
         }
+        for (int l = 0; l < 4; ++l) tc::mbar_init(lo_empty + l, 1);
         tc::fence_barrier_init();
     }
     if (warp == 0) {
@@ -262,22 +289,30 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
     const uint32_t first = blockIdx.x, stride = gridDim.x, ntiles = (uint32_t)p.ntiles;
     const uint32_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
 
+    // Each role branch opens with the setmaxnreg of its warpgroup(s): registers move from the control warps and the
+    // stagers to the drainers (every warp of a warpgroup executes the same instruction).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TP_REGS_CTRL));
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && nkc && ASRC == 0) {
+        if (tc::elect_one() && nkc && ASRC == 0) {
             uint32_t s = 0, ph = 0;                                 // ring position / phase
+            int gc = 0; (void)gc;
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const uint32_t tile = first + it * stride;
                 const uint32_t b = tile / tiles_per_b;
                 const int p_base = (int)((tile - b * tiles_per_b) * TP_PX);
                 for (int kc = 0; kc < nkc; ++kc) {
+                    TP_TRACE(0, gc, 0);
                     tc::mbar_wait(empty_bar + s, ph ^ 1);
+                    TP_TRACE(0, gc, 1);
                     uint8_t* dst = A_st + s * a_stage_bytes;
                     tc::mbar_expect_tx(full_bar + s, a_bytes);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         tc::tma_load_2d(dst + (uint32_t)i * KC * 128, &tmapA, p_base + 32 * i, (int)b * p.M + kc * KC,
                                         full_bar + s);
+                    TP_TRACE(0, gc, 2); ++gc;
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
             }
@@ -286,8 +321,8 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
         // ================= MMA issuer =================
         // One thread issues every tcgen05.mma of the CTA, so the loop bodies are kept to a handful of
         // integer instructions: descriptor high words are loop constants, low words advance by adds.
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+        if (tc::elect_one()) {
+            uint32_t s = 0, ph = 0, lo_l = 0;
             const uint32_t a_hi32 = tc::desc_hi(512, tc::LAYOUT_SW128_BASE32B);
             const uint32_t b_hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t s_hi32 = tc::desc_hi(256, tc::LAYOUT_SW32);
@@ -299,7 +334,9 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const uint32_t a = it & 1;
                 const uint32_t tround = it >> 1;
+                TP_TRACE(3, it, 0);
                 tc::mbar_wait(tempty_bar + a, (tround & 1) ^ 1);
+                TP_TRACE(3, it, 1);
                 tc::tc_fence_after_sync();
                 const uint32_t bufw = (uint32_t)p.N * (p.corr ? 2u : 1u);
                 const uint32_t tmem_d = tmem_base + (uint32_t)a * bufw;
@@ -323,14 +360,19 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     }
                 }
                 for (int kc = 0; kc < nkc; ++kc) {
+                    TP_TRACE(1, it * nkc + kc, 0);
                     tc::mbar_wait(((PASSES == 3 || ASRC == 1) ? split_bar : full_bar) + s, ph);
+                    TP_TRACE(1, it * nkc + kc, 1);
                     tc::tc_fence_after_sync();
                     uint32_t ah = tc::desc_lo(tc::smem_u32(A_st + s * a_stage_bytes), a_lbo);
-                    uint32_t al = ah + (a_bytes >> 4);
+                    uint32_t al = NLO ? tc::desc_lo(tc::smem_u32(LO_st + lo_l * a_bytes), a_lbo) : ah + (a_bytes >> 4);
                     // weight tile: K chunk (kc*KC)/32, 32-byte k-steps inside the 128-byte swizzled rows
                     const int kg0 = kc * KC;
                     uint32_t boff = ((uint32_t)(kg0 >> 5) * b_chunk_bytes + (uint32_t)((kg0 & 31) >> 3) * 32) >> 4;
                     for (int ks = 0; ks < ksteps; ++ks) {
+#ifdef SB200_BRINGUP
+                        if (p.dbg & 4) break;
+#endif
                         tc::umma_tf32_lh(tmem_d, ah, a_hi32, bh_base + boff, b_hi32, p.idesc, started);
                         started = 1;
                         if (PASSES == 3) {
@@ -341,26 +383,38 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         ah += 1024 >> 4; al += 1024 >> 4; boff += 32 >> 4;   // KC <= 32: stays inside one 32-wide K chunk
                     }
                     tc::umma_commit(empty_bar + s);            // stage reusable once these MMAs have read it
+                    TP_TRACE(1, it * nkc + kc, 2);
+                    if (NLO) {
+                        tc::umma_commit(lo_empty + lo_l);
+                        if (++lo_l == (uint32_t)NLO) lo_l = 0;
+                    }
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
                 tc::umma_commit(tfull_bar + a);                // accumulator of this tile complete
             }
         }
+    }
     } else {
-        // ================= workers: stage/split (tile t+1) then epilogue (tile t) =================
-        const int wk = warp - 2;                               // 0..15
-        const int wtid = tid - 64;                             // 0..511
+        // ================= stagers (tile t+1, t+2, ..) and drainers (tile t): two independent loops =================
+        // The staging of the coming tiles runs under the epilogue of tile t instead of in front of it.
+        const bool stager = warp < 4 + TP_STAGE_WARPS;
+        const int wk = warp - 4 - TP_STAGE_WARPS;              // drainers: 0..15
+        // The stagers split the TMA-fed A tiles (3-pass).  The Phi operand of the spectral term and the generated A operand
+        // (ASRC == 1) are staged by the drainers in front of their epilogue: both are per-thread register pipelines.
+        const int wtid = tid - 32 * (4 + TP_STAGE_WARPS);      // drainers: 0..511
+        const int stid = tid - 128;                            // stagers: 0..127
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        const int cpart = wk >> 2;                             // which quarter of the columns this warp drains
+        const int cpart = wk >> 2;                             // drainers: which quarter of the columns this warp drains
         const int ncol_part = ((p.N + 3) / 4 + 3) & ~3;        // columns per part (multiple of 4)
         const int c_begin = cpart * ncol_part;
         const int c_end = min(p.N, c_begin + ncol_part);
         uint32_t sp_s = 0, sp_ph = 0;                          // split-pass ring position / phase
-        // Phi staging geometry (tile-invariant): tpr threads cooperate on output channel n_st
+        uint32_t lo_l = 0, lo_ph = 0;                          // lo ring position / phase
+        // Phi staging geometry (tile-invariant, drainer threads): tpr threads cooperate on output channel n_st
         const int tpr = 1 << p.tpr_log2;
         const int n_st = wtid >> p.tpr_log2, sub = wtid & (tpr - 1);
         const int per_n = p.R * p.Mx;
-        const bool st_active = spectral && n_st < p.N;
+        const bool st_active = SPEC && n_st < p.N;
         const int64_t HW = p.HW;
         const uint64_t hw_bytes = (uint64_t)p.HW * 4;
 
@@ -402,7 +456,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         (uint32_t)(((((rem >> 1) & 1) ^ ((n_st >> 2) & 1)) << 4) | ((rem & 1) << 3));
         }
         auto prefetch_phi = [&](Cur c) {
-            if (st_active) {
+            if (SPEC && st_active) {
                 uint32_t v;
                 const float2* src = phi_src(c, v);
 #pragma unroll
@@ -410,7 +464,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             }
         };
         auto prepare_tile = [&](uint32_t it, Cur c) {
-            if (spectral) {
+            if (SPEC) {
                 uint8_t* pbuf = Phi_s + (it & 1) * phi_buf_bytes;
                 if (st_active && one_round) {
                     // every element of this thread is already in registers (fpre): rotate (V > 1), split, store
@@ -484,20 +538,22 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         for (int j = 0; j < 8; ++j) xv[j] = px + j < p.HW ? __ldg(xs + j) : 0.f;
                     }
                 }
-                const int k_local = wtid >> 4, c8 = wtid & 15;
-                const uint32_t goff = tc::sw128b32_mnmajor_off(c8 * 8, k_local, (uint32_t)KC * 128u);
+                const int c8 = wtid & 15;
                 for (int kc = 0; kc < nkc; ++kc) {
                     tc::mbar_wait(empty_bar + sp_s, sp_ph ^ 1);          // MMAs that read this stage are done
-                    const int m = kc * KC + k_local;
-                    const float w = w2_s[m], bb = red_s[m];
-                    float hv[8], lv[8];
+                    if ((wtid >> 4) < KC) {
+                        const int k_local = wtid >> 4;                   // 512 staging threads: one channel row each
+                        const uint32_t goff = tc::sw128b32_mnmajor_off(c8 * 8, k_local, (uint32_t)KC * 128u);
+                        const int m = kc * KC + k_local;
+                        const float w = w2_s[m], bb = red_s[m];
+                        float hv[8], lv[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float g = gelu_f(fmaf(w, xv[j], bb));
-                        hv[j] = tc::tf32_trunc(g);
-                        lv[j] = tc::tf32_lo(g, hv[j]);
-                    }
-                    if (k_local < KC) {
+                        for (int j = 0; j < 8; j += 2) {
+                            float g0 = fmaf(w, xv[j], bb), g1 = fmaf(w, xv[j + 1], bb);
+                            gelu2(g0, g1);
+                            hv[j] = tc::tf32_trunc(g0); hv[j + 1] = tc::tf32_trunc(g1);
+                            lv[j] = tc::tf32_lo(g0, hv[j]); lv[j + 1] = tc::tf32_lo(g1, hv[j + 1]);
+                        }
                         float4* dh = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + goff);
                         dh[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
                         dh[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
@@ -512,12 +568,25 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
                     if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
                 }
-            } else if (PASSES == 3) {
-                for (int kc = 0; kc < nkc; ++kc) {
+            }
+        };
+
+        if (stager) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TP_REGS_STAGE));
+            if (ASRC == 0 && PASSES == 3) {
+                // raw fp32 tile -> tf32 hi (in place) and lo, chunk by chunk as the TMA loads land
+                for (uint32_t g = 0; g < my_tiles * (uint32_t)nkc; ++g) {
+                    if (stid == 0) TP_TRACE(2, g, 0);
                     tc::mbar_wait(full_bar + sp_s, sp_ph);
+                    if (stid == 0) TP_TRACE(2, g, 1);
                     float4* ah = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes);
                     float4* al = reinterpret_cast<float4*>(A_st + sp_s * a_stage_bytes + a_bytes);
-                    for (int idx = wtid; idx < (int)(a_bytes / 16); idx += TP_WTHREADS) {
+                    if (NLO) {
+                        tc::mbar_wait(lo_empty + lo_l, lo_ph ^ 1);       // MMAs of the chunk that used this lo slot are done
+                        al = reinterpret_cast<float4*>(LO_st + lo_l * a_bytes);
+                        if (++lo_l == (uint32_t)NLO) { lo_l = 0; lo_ph ^= 1; }
+                    }
+                    for (int idx = stid; idx < (int)(a_bytes / 16); idx += TP_WTHREADS) {
                         const float4 v = ah[idx];
                         const float4 h = make_float4(tc::tf32_trunc(v.x), tc::tf32_trunc(v.y), tc::tf32_trunc(v.z), tc::tf32_trunc(v.w));
                         ah[idx] = h;
@@ -526,13 +595,14 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(split_bar + sp_s);
+                    if (stid == 0) TP_TRACE(2, g, 2);
                     if (++sp_s == (uint32_t)S) { sp_s = 0; sp_ph ^= 1; }
                 }
             }
-        };
-
-        float hsum[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // EPI 6: column sums (gb1 x4 | gw2 x4) and sum(gy)
-        if (my_tiles > 0) {
+        } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TP_REGS_DRAIN));
+        float hsum[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // EPI 6 / 7: column sums (x4 | x4) and sum(gy)
+        if ((SPEC || ASRC == 1) && my_tiles > 0) {
             prefetch_phi(cur_e);
             prepare_tile(0, cur_e);
             cur_p = advance(cur_e);
@@ -556,20 +626,28 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     zsrc += HW;
                 }
             }
-            if (it + 1 < my_tiles) {
-                prepare_tile(it + 1, cur_p);
-                if (it + 2 < my_tiles) prefetch_phi(cur_f);
+            if (SPEC || ASRC == 1) {
+                if (it + 1 < my_tiles) {
+                    prepare_tile(it + 1, cur_p);
+                    if (it + 2 < my_tiles) prefetch_phi(cur_f);
+                }
+                cur_e = cur_p; cur_p = cur_f; cur_f = advance(cur_f);
+            } else {
+                cur_e = advance(cur_e);
             }
-            cur_e = cur_p; cur_p = cur_f; cur_f = advance(cur_f);
             const uint32_t a = it & 1;
             const uint32_t tround = it >> 1;
             tc::mbar_wait(tfull_bar + a, tround & 1);
+            if (wk == 0 && lane == 0) TP_TRACE(3, it, 2);
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N * (p.corr ? 2u : 1u);
             if constexpr (EPI == 5) {
                 // ---- fused head forward: this warp's columns -> one partial dot product per pixel ----
                 float part = 0.f;
                 for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+#ifdef SB200_BRINGUP
+                    if (p.dbg & 2) break;
+#endif
                     uint32_t r[16];
                     tc::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
                     tc::tmem_ld_wait();
@@ -577,15 +655,25 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     for (int j = 0; j < 16; j += 4) {
                         const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + j);
                         const float4 wq = *reinterpret_cast<const float4*>(w2_s + c0 + j);
-                        part = fmaf(wq.x, gelu_f(__uint_as_float(r[j + 0]) + bq.x), part);
-                        part = fmaf(wq.y, gelu_f(__uint_as_float(r[j + 1]) + bq.y), part);
-                        part = fmaf(wq.z, gelu_f(__uint_as_float(r[j + 2]) + bq.z), part);
-                        part = fmaf(wq.w, gelu_f(__uint_as_float(r[j + 3]) + bq.w), part);
+                        float g0 = __uint_as_float(r[j + 0]) + bq.x, g1 = __uint_as_float(r[j + 1]) + bq.y;
+                        float g2 = __uint_as_float(r[j + 2]) + bq.z, g3 = __uint_as_float(r[j + 3]) + bq.w;
+#ifdef SB200_BRINGUP
+                        if (!(p.dbg & 1))
+#endif
+                        {
+                            gelu2(g0, g1);
+                            gelu2(g2, g3);
+                        }
+                        part = fmaf(wq.x, g0, part);
+                        part = fmaf(wq.y, g1, part);
+                        part = fmaf(wq.z, g2, part);
+                        part = fmaf(wq.w, g3, part);
                     }
                 }
                 tc::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+                if (wk == 0 && lane == 0) TP_TRACE(3, it, 3);
                 // the four warps sharing this TMEM lane quarter hold the four column parts of the same 32 pixels
                 float* red = red_s + (it & 1) * 512;
                 red[cpart * 128 + quarter * 32 + lane] = part;
@@ -609,13 +697,16 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     tc::tmem_ld_wait();
                     float s0[16], s1[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float z = __uint_as_float(r[j]) + bias_s[c0 + j];
-                        float cdf, e;
-                        gelu_core(z, cdf, e);
-                        const float gp = fmaf(z * 0.39894228040143267794f, e, cdf);
-                        s0[j] = w2_s[c0 + j] * gyv * gp;            // gz1 (0 outside the image: gyv = 0)
-                        s1[j] = gyv * (z * cdf);                     // gy * GELU(z1)
+                    for (int j = 0; j < 16; j += 2) {
+                        const float za = __uint_as_float(r[j]) + bias_s[c0 + j], zb = __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1];
+                        float2 cdf, e;
+                        gelu_core2(za, zb, cdf, e);
+                        const float gpa = fmaf(za * 0.39894228040143267794f, e.x, cdf.x);
+                        const float gpb = fmaf(zb * 0.39894228040143267794f, e.y, cdf.y);
+                        s0[j] = w2_s[c0 + j] * gyv * gpa;           // gz1 (0 outside the image: gyv = 0)
+                        s0[j + 1] = w2_s[c0 + j + 1] * gyv * gpb;
+                        s1[j] = gyv * (za * cdf.x);                  // gy * GELU(z1)
+                        s1[j + 1] = gyv * (zb * cdf.y);
                     }
                     if (in_range) {
                         uint64_t ya = reinterpret_cast<uint64_t>(p.y_out + ((int64_t)b * p.N + c0) * HW + pp);
@@ -643,11 +734,13 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                     tc::tmem_ld_wait();
                     float s0[16], s1[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float z = fmaf(w2_s[c0 + j], xv, bias_s[c0 + j]);
-                        const float gzv = in_range ? __uint_as_float(r[j]) * gelu_grad_f(z) : 0.f;
-                        s0[j] = gzv;
-                        s1[j] = gzv * xv;
+                    for (int j = 0; j < 16; j += 2) {
+                        float ga, gb;
+                        gelu_grad2(fmaf(w2_s[c0 + j], xv, bias_s[c0 + j]), fmaf(w2_s[c0 + j + 1], xv, bias_s[c0 + j + 1]), ga, gb);
+                        const float gza = in_range ? __uint_as_float(r[j]) * ga : 0.f;
+                        const float gzb = in_range ? __uint_as_float(r[j + 1]) * gb : 0.f;
+                        s0[j] = gza; s0[j + 1] = gzb;
+                        s1[j] = gza * xv; s1[j + 1] = gzb * xv;
                     }
                     hsum[ci] += warp_colsum16(s0, lane);
                     hsum[4 + ci] += warp_colsum16(s1, lane);
@@ -658,6 +751,9 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 continue;
             }
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+#ifdef SB200_BRINGUP
+                if (p.dbg & 2) break;
+#endif
                 const int nv = min(16, c_end - c0);
                 const int64_t off0 = ((int64_t)b * p.N + c0) * HW + pp;
                 uint32_t r[16];
@@ -702,9 +798,16 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (EPI == 1 || EPI == 2) v[j] = gelu_f(v[j]);
-                        if (EPI == 3) v[j] *= gelu_grad_f(zp[j]);
+                    for (int j = 0; j < 16; j += 2) {
+#ifdef SB200_BRINGUP
+                        if (p.dbg & 1) continue;
+#endif
+                        if (EPI == 1 || EPI == 2) gelu2(v[j], v[j + 1]);
+                        if (EPI == 3) {
+                            float ga, gb;
+                            gelu_grad2(zp[j], zp[j + 1], ga, gb);
+                            v[j] *= ga; v[j + 1] *= gb;
+                        }
                     }
                     uint64_t ya = reinterpret_cast<uint64_t>(p.y_out + off0);
 #pragma unroll
@@ -731,6 +834,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             tc::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty_bar + a);
+            if (wk == 0 && lane == 0) TP_TRACE(3, it, 3);
         }
         if (EPI == 6 || EPI == 7) {
             // flush the per-warp column sums: row = (CTA, lane quarter); each cpart owns 64 of the 256 columns
@@ -750,11 +854,38 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                 if (lane == 0) p.colsum_ws[(size_t)gridDim.x * 4 * 512 + blockIdx.x * 4 + quarter] = g;
             }
         }
+        }   // drainers
     }
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
+#ifdef SB200_BRINGUP
+static long long* tp_trace_buf(cudaStream_t st) {
+    static long long* dev = nullptr;
+    if (!dev) cudaMalloc(&dev, 4 * 32 * 4 * sizeof(long long));
+    cudaMemsetAsync(dev, 0, 4 * 32 * 4 * sizeof(long long), st);
+    return dev;
+}
+static void tp_trace_dump(const TcPwParams& p, int epi, cudaStream_t st) {
+    long long h[4 * 32 * 4];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[2];
+    printf("tc_pointwise trace: epi=%d M=%d N=%d spectral=%d KC=%d nkc=%d stages=%d nlo=%d\n", epi, p.M, p.N, p.Phi != nullptr, p.KC, p.nkc, p.stages, p.nlo);
+    const char* names[4] = {"producer(wait0,wait1,issued)", "mma chunk(wait0,wait1,committed)", "split(wait0,landed,done)", "tile(mma tempty0,tempty1; epi wake,done)"};
+    for (int r = 0; r < 4; ++r) {
+        printf("%s\n", names[r]);
+        for (int i = 0; i < (r == 3 ? 8 : 16); ++i) {
+            printf("  %2d:", i);
+            for (int e = 0; e < 4; ++e) printf(" %7lld", h[(r * 32 + i) * 4 + e] ? h[(r * 32 + i) * 4 + e] - t0 : -1);
+            printf("\n");
+        }
+    }
+    fflush(stdout);
+}
+#endif
 
 // out[0][n] = gb1, out[1][n] = gw2 (n < 256), gb2 = sum(gy): fixed-order sums over the (CTA, quarter) rows.
 // 32 consecutive outputs x 8 row lanes per block (coalesced partial reads), shared-memory tree at the end.
@@ -806,16 +937,18 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     if (has_spec && (tt == nullptr || (reinterpret_cast<uintptr_t>(q.Phi) & 7) != 0 || tt->V * q.Mx > 256)) return 0;
     const int passes = g_tc_mode;
 
-    TcPwParams p;
+    TcPwParams p = {};
     memset(&p, 0, sizeof(p));
     p.Wp = q.Wp; p.w_sn = q.w_sn; p.w_sm = q.w_sm; p.bias = q.bias; p.zprev = q.zprev;
     p.z_out = q.z_out; p.y_out = q.y_out; p.B = q.B; p.M = M; p.N = N; p.HW = HW;
     p.KC = has_pw ? (M < 32 ? M : 32) : 8;
+    if (const int kc = sb_env_int("SB200_TP_KC", 0)) if (has_pw && (kc == 8 || kc == 16) && M % kc == 0 && kc < p.KC) p.KC = kc;
     p.nkc = has_pw ? M / p.KC : 0;
     p.mode = q.mode; p.apply_act = q.apply_act;
     p.idesc = tc::make_idesc_tf32(128, N, /*A MN-major*/ 1, /*B K-major*/ 0);
     p.idesc_spec = tc::make_idesc_tf32(128, N, 0, 0);
     p.corr = (passes == 3 && 4 * N <= 512) ? 1 : 0;
+    p.dbg = sb_env_int("SB200_TP_DBG", 0);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * N * (p.corr ? 2 : 1))) cols <<= 1;
     p.tmem_cols = cols;
@@ -828,12 +961,20 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     }
 
     const size_t mult = passes == 3 ? 2 : 1;
-    const size_t a_stage = (size_t)p.KC * 512 * mult;
     const size_t b_bytes = has_pw ? ((((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * mult) : 0;
     const size_t e_bytes = has_spec ? (size_t)(p.K2pad / 8) * 4096 * mult : 0;
     const size_t phi_bytes = has_spec ? ((((size_t)(p.K2pad / 8) * N * 32 + 1023) & ~(size_t)1023) * mult * 2) : 0;
-    const size_t fixed = 1024 + b_bytes + e_bytes + phi_bytes + 512 + 1024 + 2048;   // + barriers, bias_s, rot_s
-    int stages = has_pw ? 6 : 1;
+    const size_t fixed0 = 1024 + b_bytes + e_bytes + phi_bytes + 512 + 1024 + 2048;   // + barriers, bias_s, rot_s
+    // 3-pass: lo ring of two slots, the stages are raw slots alone.  When fewer than two tiles of 32-channel slots fit
+    // (large resident weight tile), 16-channel slots keep the same bytes in flight at a finer release granularity.
+    p.nlo = (passes == 3 && has_pw) ? sb_env_int("SB200_TP_NLO", 0) : 0;
+    if (p.nlo && M % 16 == 0 && p.KC == 32 && (224 * 1024 - (long long)fixed0 - 2 * 16384) / 16384 < 2 * (M / 32)) {
+        p.KC = 16;
+        p.nkc = M / 16;
+    }
+    const size_t a_stage = (size_t)p.KC * 512 * (p.nlo ? 1 : mult);
+    const size_t fixed = fixed0 + (size_t)p.nlo * p.KC * 512;
+    int stages = has_pw ? (p.nlo ? 8 : 6) : 1;
     static const size_t ring_budget = []() {                       // bytes the ring may grow to (SB200_TP_SMEM_KB: bring-up builds)
         const int kb = sb_env_int("SB200_TP_SMEM_KB", 0);
         return (size_t)((kb >= 64 && kb <= 227) ? kb : 224) * 1024;
@@ -854,17 +995,21 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
     const int g_num_sms = sb200_num_sms();
     const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
     int tl = 0;
-    while ((1 << (tl + 1)) * N <= TP_WTHREADS) ++tl;
+    while ((1 << (tl + 1)) * N <= 32 * TP_DRAIN_WARPS) ++tl;
     p.tpr_log2 = tl;
     int epi;
     if (q.mode == 0) epi = q.apply_act ? (q.z_out ? 1 : 2) : 0;
     else epi = q.zprev ? 3 : 4;
     if (q.mode == 0 && !q.apply_act && q.z_out) return 0;              // (never requested) keep the generic kernel
+#define TP_LAUNCH_S(PS, EP, SP)                                                                                        \
+    do {                                                                                                               \
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP, 0, SP>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        sb_launch(tc_pointwise_kernel<PS, EP, 0, SP>, grid, TP_THREADS, smem, st, tmap, p);                            \
+    } while (0)
 #define TP_LAUNCH(PS, EP)                                                                                              \
     do {                                                                                                               \
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                           (int)smem));                                                                \
-        sb_launch(tc_pointwise_kernel<PS, EP>, grid, TP_THREADS, smem, st, tmap, p);                                          \
+        if (has_spec) TP_LAUNCH_S(PS, EP, true); else TP_LAUNCH_S(PS, EP, false);                                      \
     } while (0)
 #define TP_LAUNCH_EPI(PS)                                                                                              \
     switch (epi) {                                                                                                     \
@@ -874,10 +1019,22 @@ int sb200_tc_rowidft_pointwise(sb200_plan_t plan, int pass, const PwParams& q, c
         case 3: TP_LAUNCH(PS, 3); break;                                                                               \
         default: TP_LAUNCH(PS, 4); break;                                                                              \
     }
+#ifdef SB200_BRINGUP
+    const int want_trace = sb_env_int("SB200_TP_TRACE", 0);
+    const bool trace_this = want_trace && sb_env_int("SB200_TP_TRACE_EPI", -1) == epi;
+    if (trace_this) p.trace = tp_trace_buf(st);
+#endif
     if (passes == 3) { TP_LAUNCH_EPI(3) } else { TP_LAUNCH_EPI(1) }
 #undef TP_LAUNCH_EPI
 #undef TP_LAUNCH
+#undef TP_LAUNCH_S
     SB_LAUNCH_CHECK();
+#ifdef SB200_BRINGUP
+    if (trace_this) {
+        static int calls = 0;
+        if (++calls == want_trace) tp_trace_dump(p, epi, st);
+    }
+#endif
     *handled = 1;
     return 0;
 }
@@ -894,22 +1051,34 @@ static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn
     SB_REQUIRE(N == 256, "mlp_head: hidden width must be 256 (got %d)", N);
     SB_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (int64_t)B * M < (1LL << 31), "mlp_head: layout");
     const int passes = g_tc_mode;
-    TcPwParams p;
+    TcPwParams p = {};
     memset(&p, 0, sizeof(p));
     p.Wp = W1; p.w_sn = w_sn; p.w_sm = w_sm; p.bias = b1; p.y_out = out; p.B = B; p.M = M; p.N = N; p.HW = HW;
     p.KC = M < 32 ? M : 32;
+    if (const int kc = sb_env_int("SB200_TP_KC", 0)) if ((kc == 8 || kc == 16) && M % kc == 0 && kc < p.KC) p.KC = kc;
     p.nkc = M / p.KC;
     p.idesc = tc::make_idesc_tf32(128, N, 1, 0);
     p.idesc_spec = tc::make_idesc_tf32(128, N, 0, 0);
     p.tmem_cols = 512;
     p.ntiles = (HW + TP_PX - 1) / TP_PX * B;
     p.w2 = w2; p.b2 = b2; p.gy = gy; p.colsum_ws = ws;
+    p.dbg = sb_env_int("SB200_TP_DBG", 0);
     const size_t mult = passes == 3 ? 2 : 1;
-    const size_t a_stage = (size_t)p.KC * 512 * mult;
     const size_t b_bytes = ((((size_t)((M + 31) / 32) * N * 128 + 1023) & ~(size_t)1023) * mult);
-    const size_t fixed = 1024 + b_bytes + 512 + 1024 + 2048 + 1024 + 4096;      // + barriers, bias_s, rot_s, w2_s, red_s
-    int stages = 6;
-    while (stages > 2 && fixed + stages * a_stage > 208 * 1024) --stages;
+    const size_t fixed0 = 1024 + b_bytes + 512 + 1024 + 2048 + 1024 + 4096;     // + barriers, bias_s, rot_s, w2_s, red_s
+    // 3-pass: two-slot lo ring + raw slots; the 256-row weight tile leaves ~85 KB, so the slots are 16 channels deep
+    // (two tiles of the activation stream in flight instead of one: the loop was bound by the TMA round trip)
+    p.nlo = passes == 3 ? sb_env_int("SB200_TP_NLO", 0) : 0;
+    if (p.nlo && M % 16 == 0 && p.KC == 32 && (224 * 1024 - (long long)fixed0 - 2 * 16384) / 16384 < 2 * (M / 32)) {
+        p.KC = 16;
+        p.nkc = M / 16;
+    }
+    const size_t a_stage = (size_t)p.KC * 512 * (p.nlo ? 1 : mult);
+    const size_t fixed = fixed0 + (size_t)p.nlo * p.KC * 512;
+    int stages = p.nlo ? 8 : 6;
+    int stages_max = sb_env_int("SB200_TP_STAGES", 8);
+    if (stages > stages_max) stages = stages_max;
+    while (stages > 2 && fixed + stages * a_stage > (size_t)sb_env_int("SB200_TP_HEAD_KB", 224) * 1024) --stages;
     SB_REQUIRE(fixed + stages * a_stage <= 227 * 1024, "mlp_head: shared memory does not fit (M=%d)", M);
     p.stages = stages;
     const size_t smem = fixed + stages * a_stage;
@@ -918,20 +1087,48 @@ static int tp_head_launch(int epi, const float* h, const float* W1, int64_t w_sn
     const int g_num_sms = sb200_num_sms();
     const unsigned grid = (unsigned)(p.ntiles < g_num_sms ? p.ntiles : g_num_sms);
     *grid_out = grid;
-    int tl = 0;
-    while ((1 << (tl + 1)) * N <= TP_WTHREADS) ++tl;
-    p.tpr_log2 = tl;
 #define TP_HEAD(PS, EP)                                                                                                \
     do {                                                                                                               \
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<PS, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)smem));                                                                \
         sb_launch(tc_pointwise_kernel<PS, EP>, grid, TP_THREADS, smem, st, tmap, p);                                          \
     } while (0)
+#ifdef SB200_BRINGUP
+    static long long* trace_dev = nullptr;
+    const int want_trace = epi == 5 ? sb_env_int("SB200_TP_TRACE", 0) : 0;
+    if (want_trace) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 4 * 32 * 4 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 4 * 32 * 4 * sizeof(long long), st);
+        p.trace = trace_dev;
+    }
+#endif
     if (epi == 5)      { if (passes == 3) TP_HEAD(3, 5); else TP_HEAD(1, 5); }
     else if (epi == 6) { if (passes == 3) TP_HEAD(3, 6); else TP_HEAD(1, 6); }
     else               { if (passes == 3) TP_HEAD(3, 7); else TP_HEAD(1, 7); }
 #undef TP_HEAD
     SB_LAUNCH_CHECK();
+#ifdef SB200_BRINGUP
+    if (want_trace) {
+        static int calls = 0;
+        if (++calls == want_trace) {
+            long long h[4 * 32 * 4];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[2];
+            printf("head trace: KC=%d nkc=%d stages=%d nlo=%d\n", p.KC, p.nkc, p.stages, p.nlo);
+            const char* names[4] = {"producer(wait0,wait1,issued)", "mma chunk(wait0,wait1,committed)", "split(wait0,landed,done)", "tile(mma tempty0,tempty1; epi wake,done)"};
+            for (int r = 0; r < 4; ++r) {
+                printf("%s\n", names[r]);
+                for (int i = 0; i < (r == 3 ? 8 : 24); ++i) {
+                    printf("  %2d:", i);
+                    for (int e = 0; e < 4; ++e) printf(" %7lld", h[(r * 32 + i) * 4 + e] ? h[(r * 32 + i) * 4 + e] - t0 : -1);
+                    printf("\n");
+                }
+            }
+            fflush(stdout);
+        }
+    }
+#endif
     return 0;
 }
 
@@ -995,13 +1192,14 @@ extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, 
     if (B <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int passes = g_tc_mode;
-    TcPwParams p;
+    TcPwParams p = {};
     memset(&p, 0, sizeof(p));
     p.Wp = W2; p.w_sn = N; p.w_sm = 1; p.bias = b2; p.y_out = y; p.B = B; p.M = N; p.N = C; p.HW = HW;
     p.KC = 32; p.nkc = N / 32;
     p.idesc = tc::make_idesc_tf32(128, C, 1, 0);
     p.idesc_spec = tc::make_idesc_tf32(128, C, 0, 0);
     p.corr = (passes == 3 && 4 * C <= 512) ? 1 : 0;
+    p.dbg = sb_env_int("SB200_TP_DBG", 0);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * C * (p.corr ? 2 : 1))) cols <<= 1;
     p.tmem_cols = cols;
@@ -1020,9 +1218,6 @@ extern "C" int sb200_lift_fwd(const float* x, const float* w1, const float* b1, 
     memset(&tmap, 0, sizeof(tmap));
     const int sms = tp_sms();
     const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
-    int tl = 0;
-    while ((1 << (tl + 1)) * C <= TP_WTHREADS) ++tl;
-    p.tpr_log2 = tl;
     if (passes == 3) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sb_launch(tc_pointwise_kernel<3, 0, 1>, grid, TP_THREADS, smem, st, tmap, p);

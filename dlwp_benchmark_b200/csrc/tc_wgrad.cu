@@ -97,7 +97,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     const int64_t my_items = i1 > i0 ? i1 - i0 : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             uint32_t s = 0, ph = 0;
             const uint32_t items_per_b = (uint32_t)p.items_per_b;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
@@ -117,7 +117,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
         }
     } else if (warp == 1) {
         // single-thread MMA issue: constant descriptor high word, low words advance by adds
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t lo_delta = raw_bytes >> 4;
             const uint32_t mb_step = (128u * 128u) >> 4;
@@ -176,8 +176,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                     if (px + 4 <= p.HW) xv = __ldg(reinterpret_cast<const float4*>(p.gen_x + (int64_t)b * p.HW + px));
                     for (int row = row0; row < p.Pc; row += 64) {
                         const float w = __ldg(p.gen_w1 + row), bb = __ldg(p.gen_b1 + row);
-                        float4 g = make_float4(gelu_f(fmaf(w, xv.x, bb)), gelu_f(fmaf(w, xv.y, bb)), gelu_f(fmaf(w, xv.z, bb)),
-                                               gelu_f(fmaf(w, xv.w, bb)));
+                        float4 g = gelu4(make_float4(fmaf(w, xv.x, bb), fmaf(w, xv.y, bb), fmaf(w, xv.z, bb), fmaf(w, xv.w, bb)));
                         if (px + 4 > p.HW) g = make_float4(0.f, 0.f, 0.f, 0.f);     // pixels outside the image contribute nothing
                         const float4 h = make_float4(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y), tc::tf32_trunc(g.z), tc::tf32_trunc(g.w));
                         const uint32_t off = (uint32_t)j * chunk_bytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((piece ^ (row & 7)) << 4));

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/ncu_src.sh <kernel-regex> <out-prefix> <cmd...>: one full capture (2nd launch) + key metrics + top SASS stall sites
 K=$1; O=gpurun_out/$2; shift 2
-ncu --set full --clock-control none --import-source on -k "regex:$K" -s 1 -c 1 -o /tmp/cap -f "$@" > $O.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$K" -s 1 -c 1 -o /tmp/cap -f "$@" > $O.log 2>&1
 ncu -i /tmp/cap.ncu-rep --page raw --csv > $O.raw.csv 2>/dev/null
 ncu -i /tmp/cap.ncu-rep --page source --csv > $O.src.csv 2>/dev/null
 python - "$O.raw.csv" <<'PY'
