@@ -220,13 +220,17 @@ coldft_inv_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, 
 // v2 of the zero-padded inverse column transform: one thread owns one (image, kx) pair and a segment of output rows;
 // its My input modes live in registers (plus the (-im, re) rotated copy, so that a complex MAC is two FFMA2 with a
 // warp-uniform twiddle broadcast from shared memory).  Reads and writes are kx-contiguous per image.
+// fold != 0 (H even): rows y and y + H/2 share their twiddles up to (-1)^ky, so one pass over the modes gives both:
+// out[y] = E + O, out[y + H/2] = fold * (E - O) with E / O the sums over the even- / odd-indexed modes (fold = +1 when the
+// first retained frequency is even, -1 when odd).  The block then owns yseg rows of the first half and their partners.
 template <int MYP>
 __global__ void __launch_bounds__(128)
 coldft_inv2_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI, float2* __restrict__ Phi,
-                   int64_t nitems, int H, int My, int Mx, int yseg) {
+                   int64_t nitems, int H, int My, int Mx, int yseg, float fold) {
     extern __shared__ __align__(16) float2 tw[];          // [yseg][MYP] twiddles of this block's rows
     const int y0 = blockIdx.y * yseg;
-    const int ny = min(yseg, H - y0);
+    const int Hr = fold != 0.f ? H / 2 : H;               // rows that are computed
+    const int ny = min(yseg, Hr - y0);
     for (int idx = threadIdx.x; idx < yseg * MYP; idx += blockDim.x) {
         const int yy = idx / MYP, ky = idx % MYP;
         tw[idx] = (yy < ny && ky < My) ? __ldg(CI + (int64_t)(y0 + yy) * My + ky) : make_float2(0.f, 0.f);
@@ -256,23 +260,27 @@ coldft_inv2_kernel(const float2* __restrict__ Yh, const float2* __restrict__ CI,
             a2 = ffma2(make_float2(t.z, t.z), v[2 * h + 1], a2);
             a3 = ffma2(make_float2(t.w, t.w), vr[2 * h + 1], a3);
         }
-        dst[(int64_t)yy * Mx] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+        const float2 e = make_float2(a0.x + a1.x, a0.y + a1.y), o = make_float2(a2.x + a3.x, a2.y + a3.y);
+        dst[(int64_t)yy * Mx] = make_float2(e.x + o.x, e.y + o.y);
+        if (fold != 0.f) dst[(int64_t)(yy + Hr) * Mx] = make_float2(fold * (e.x - o.x), fold * (e.y - o.y));
     }
 }
 
 template <int MYP>
 static int coldft_inv2_launch(const float2* Yh, const float2* CI, float2* Phi, int64_t nimg, int H, int My, int Mx,
-                              cudaStream_t st) {
+                              int ky0, cudaStream_t st) {
     const int64_t nitems = nimg * Mx;
+    const float fold = (H % 2 == 0) ? ((((ky0 % 2) + 2) % 2) ? -1.f : 1.f) : 0.f;
+    const int Hr = fold != 0.f ? H / 2 : H;
     // enough row segments to give every SM sub-partition several warps
     int segs = 1;
-    while (segs < 8 && (nitems / 32) * segs < 4 * 4 * 148 && H / (segs * 2) >= 8) segs *= 2;
-    const int yseg = (H + segs - 1) / segs;
-    dim3 grid((unsigned)ceil_div64(nitems, 128), (unsigned)((H + yseg - 1) / yseg));
+    while (segs < 8 && (nitems / 32) * segs < 4 * 4 * 148 && Hr / (segs * 2) >= 4) segs *= 2;
+    const int yseg = (Hr + segs - 1) / segs;
+    dim3 grid((unsigned)ceil_div64(nitems, 128), (unsigned)((Hr + yseg - 1) / yseg));
     const size_t smem = (size_t)yseg * MYP * sizeof(float2);
     if (smem > 48 * 1024)
         SB_CHECK_CUDA(cudaFuncSetAttribute(coldft_inv2_kernel<MYP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sb_launch(coldft_inv2_kernel<MYP>, grid, 128, smem, st, Yh, CI, Phi, nitems, H, My, Mx, yseg);
+    sb_launch(coldft_inv2_kernel<MYP>, grid, 128, smem, st, Yh, CI, Phi, nitems, H, My, Mx, yseg, fold);
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -318,10 +326,10 @@ extern "C" int sb200_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float
         const float2* Y2 = reinterpret_cast<const float2*>(Yh);
         float2* P2 = reinterpret_cast<float2*>(Phi);
         cudaStream_t st = (cudaStream_t)stream;
-        if (My <= 8) return coldft_inv2_launch<8>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
-        if (My <= 16) return coldft_inv2_launch<16>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
-        if (My <= 24) return coldft_inv2_launch<24>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
-        return coldft_inv2_launch<32>(Y2, p->colI[pass], P2, nimg, H, My, Mx, st);
+        if (My <= 8) return coldft_inv2_launch<8>(Y2, p->colI[pass], P2, nimg, H, My, Mx, p->ky0, st);
+        if (My <= 16) return coldft_inv2_launch<16>(Y2, p->colI[pass], P2, nimg, H, My, Mx, p->ky0, st);
+        if (My <= 24) return coldft_inv2_launch<24>(Y2, p->colI[pass], P2, nimg, H, My, Mx, p->ky0, st);
+        return coldft_inv2_launch<32>(Y2, p->colI[pass], P2, nimg, H, My, Mx, p->ky0, st);
     }
     int YGB, IPB, threads;
     SB_REQUIRE(col_launch_cfg((H + 3) / 4, Mx, &YGB, &IPB, &threads) == 0, "coldft_inv: Mx=%d too large", Mx);
