@@ -867,14 +867,14 @@ def run_b200(args, wl, rank, world, local_rank):
             top = max(share, key=share.get)
             ncu_name = {"analysis": ("analysis_fused", None), "modes_gemm(mix_fwd)": ("modes_gemm2", None),
                         "modes_gemm(wgrad)": ("modes_gemm2", None), "coldft_inv": ("coldft_inv2", None),
-                        "rowidft_pointwise(fwd)": ("tc_pointwise_kernel<3, 1, 0>", None),
-                        "rowidft_pointwise(bwd)": ("tc_pointwise_kernel<3, 3, 0>", None),
+                        "rowidft_pointwise(fwd)": ("tc_pointwise_kernel<3, 1, 0", None),
+                        "rowidft_pointwise(bwd)": ("tc_pointwise_kernel<3, 3, 0", None),
                         "pointwise_wgrad": ("tc_wgrad_kernel<3, 0>", 8 * wl["batch"] * wl["hidden"] * wl["H"] * wl["W"])}
-            ncu_name.update({"lift_fwd": ("tc_pointwise_kernel<3, 0, 1>", None), "lift_wgrad": ("tc_wgrad_kernel<3, 1>", None),
-                             "lift_tail_bwd": ("tc_pointwise_kernel<3, 7, 0>", None),
-                             "mlp_head_fwd": ("tc_pointwise_kernel<3, 5, 0>", None),
-                             "mlp_head_bwd(gz1 out)": ("tc_pointwise_kernel<3, 6, 0>", None),
-                             "head_dgrad(256->C)": ("tc_pointwise_kernel<3, 4, 0>", None),
+            ncu_name.update({"lift_fwd": ("tc_pointwise_kernel<3, 0, 1", None), "lift_wgrad": ("tc_wgrad_kernel<3, 1>", None),
+                             "lift_tail_bwd": ("tc_pointwise_kernel<3, 7, 0", None),
+                             "mlp_head_fwd": ("tc_pointwise_kernel<3, 5, 0", None),
+                             "mlp_head_bwd(gz1 out)": ("tc_pointwise_kernel<3, 6, 0", None),
+                             "head_dgrad(256->C)": ("tc_pointwise_kernel<3, 4, 0", None),
                              "head_wgrad(256xC)": ("tc_wgrad_kernel<3, 0>", 4 * wl["batch"] * (wl["proj"] + wl["hidden"]) * wl["H"] * wl["W"])})
             traffic = _ncu_traffic(*ncu_name[top]) if args.workload == "cfg2" and top in ncu_name else None
             roof = {"bound": "hbm", "kernel": top, "achieved": kr[top]["achieved_gbs"], "peak": peak,

@@ -116,7 +116,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
     const uint32_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             uint32_t s = 0, ph = 0;
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const int row0 = (int)((first + it * stride) * TR_ROWS);
@@ -129,7 +129,7 @@ tc_rowdft_kernel(const __grid_constant__ CUtensorMap tmapX, const TcRdParams p) 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const uint32_t hi32 = tc::desc_hi(1024, tc::LAYOUT_SW128);
             const uint32_t bh_base = tc::desc_lo(tc::smem_u32(B_hi), 16), bl_base = tc::desc_lo(tc::smem_u32(B_lo), 16);
             uint32_t s = 0, ph = 0, lo = 0;
