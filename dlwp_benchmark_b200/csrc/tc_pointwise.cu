@@ -68,12 +68,13 @@ int sb200_make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, ui
 
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent, warp-specialised
-//   warp 0      TMA producer (one lane)          activation K-chunks (32 channels x 128 px) -> smem ring
-//   warp 1      MMA issuer (one lane)            tcgen05.mma into a double-buffered TMEM accumulator
-//   warps 2-17  workers: (a) stage the Phi operand of the NEXT tile (spectral term) and split its landed
-//               activation chunks into tf32 hi/lo parts, (b) epilogue of the CURRENT tile:
-//               TMEM -> registers -> bias / GELU / GELU' -> global
-// so the MMAs of tile t+1 execute while tile t is being written out; TMA runs ahead by the ring depth.
+//   warp 0      TMA producer (one elected lane)  activation K-chunks (32 channels x 128 px) -> smem ring
+//   warp 1      MMA issuer (one elected lane)    tcgen05.mma into a double-buffered TMEM accumulator
+//   warps 4-7   stagers: split the landed activation chunks of the coming tiles into tf32 hi / lo parts, in their own loop
+//   warps 8-23  drainers: stage the Phi operand of the NEXT tile (spectral term; or generate the A operand, ASRC == 1),
+//               then the epilogue of the CURRENT tile: TMEM -> registers -> bias / GELU / GELU' -> global
+// so the MMAs and the split of tile t+1 execute while tile t is being written out; TMA runs ahead by the ring depth.
+// (Until round 2 the same 16 warps did split and epilogue one after the other; see "Warp roles" below.)
 //
 // Spectral term (row synthesis):  D[p, n] += sum_kk E[p, kk] * Phi[b, n, y(p), kk]
 //   E   : constant [128 px][K2pad] operand (plan table; block-diagonal over the R image rows of a tile),
