@@ -153,7 +153,7 @@ def test_bench_reads_traffic_from_the_committed_capture():
     """bench.py fills roofline.traffic from profiles/: the file it names must exist and hold the kernels it looks up."""
     import bench
     for name, approx in (("analysis_fused", None), ("modes_gemm2", None), ("coldft_inv2", None),
-                         ("tc_pointwise_kernel<3, 1, 0>", None), ("tc_pointwise_kernel<3, 3, 0>", None),
+                         ("tc_pointwise_kernel<3, 1, 0", None), ("tc_pointwise_kernel<3, 3, 0", None),
                          ("tc_wgrad_kernel<3, 0>", 8 * 64 * 64 * 64 * 64)):
         t = bench._ncu_traffic(name, approx)
         assert isinstance(t, int) and t > 0, name
