@@ -99,6 +99,9 @@ ANALYSIS_SHAPES = STAGE_SHAPES + [
     (7, 1, 16, 32, (12, 12)),    # fused, G = 16, My = 12, Mx = 7
     (1, 3, 64, 64, (20, 12)),    # fused, My = 20
     (1, 3, 64, 64, (18, 16)),    # fused, My not a multiple of 4
+    (2, 4, 64, 64, (10, 12)),    # fused, first retained frequency odd (ky0 = -5): the radix-2 column fold flips its sign
+    (2, 4, 32, 32, (6, 8)),      # fused, W = 32 (two folded row chunks), ky0 = -3
+    (1, 2, 64, 32, (14, 16)),    # fused, W = 32, H = 64, Mx = 9, ky0 = -7
 ]
 
 
