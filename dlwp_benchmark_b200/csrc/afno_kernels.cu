@@ -30,32 +30,42 @@ cl_rowdft_fwd_kernel(const float* __restrict__ x, const float2* __restrict__ tab
         for (int k = 0; k < KG; ++k)
 #pragma unroll
             for (int c = 0; c < CPT; ++c) acc[k][c] = make_float2(0.f, 0.f);
-        for (int w0 = 0; w0 < W; w0 += CLR_WC) {
+        // real input: samples n and W - n share the cosine and negate the sine, so only e = x[n] + x[W-n] (real part)
+        // and o = x[n] - x[W-n] (imaginary part) enter, n <= W/2: half the multiply-adds
+        const int nh = W / 2;                                    // last folded sample
+        for (int w0 = 0; w0 <= nh; w0 += CLR_WC) {
             __syncthreads();
             for (int idx = threadIdx.x; idx < CLR_WC * KG; idx += 128) {
                 const int ww = idx / KG, k = idx % KG;
                 float2 v = make_float2(0.f, 0.f);
-                if (w0 + ww < W && kb + k < Mx) v = __ldg(tab + (int64_t)(w0 + ww) * Mx + kb + k);
+                if (w0 + ww <= nh && kb + k < Mx) v = __ldg(tab + (int64_t)(w0 + ww) * Mx + kb + k);
                 ts[ww][k] = v;
             }
             __syncthreads();
             if (active) {
-                const int wn = min(CLR_WC, W - w0);
+                const int wn = min(CLR_WC, nh + 1 - w0);
                 for (int ww = 0; ww < wn; ++ww) {
-                    float a[CPT];
+                    const int n = w0 + ww;
+                    const bool paired = n > 0 && 2 * n != W;     // x[0] and (W even) x[W/2] have no partner
+                    float e[CPT], o[CPT];
                     if (CPT == 2) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(xr + (int64_t)(w0 + ww) * C + c0));
-                        a[0] = v.x; a[CPT - 1] = v.y;
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(xr + (int64_t)n * C + c0));
+                        float2 u = make_float2(0.f, 0.f);
+                        if (paired) u = __ldg(reinterpret_cast<const float2*>(xr + (int64_t)(W - n) * C + c0));
+                        e[0] = v.x + u.x; e[CPT - 1] = v.y + u.y;
+                        o[0] = paired ? v.x - u.x : 0.f; o[CPT - 1] = paired ? v.y - u.y : 0.f;
                     } else {
-                        a[0] = __ldg(xr + (int64_t)(w0 + ww) * C + c0);
+                        const float v = __ldg(xr + (int64_t)n * C + c0);
+                        const float u = paired ? __ldg(xr + (int64_t)(W - n) * C + c0) : 0.f;
+                        e[0] = v + u; o[0] = paired ? v - u : 0.f;
                     }
 #pragma unroll
                     for (int k = 0; k < KG; ++k) {
                         const float2 t = ts[ww][k];
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) {
-                            acc[k][c].x = fmaf(a[c], t.x, acc[k][c].x);
-                            acc[k][c].y = fmaf(a[c], t.y, acc[k][c].y);
+                            acc[k][c].x = fmaf(e[c], t.x, acc[k][c].x);
+                            acc[k][c].y = fmaf(o[c], t.y, acc[k][c].y);
                         }
                     }
                 }
@@ -137,30 +147,46 @@ cl_rowidft_res_kernel(const float2* __restrict__ Phi, const float2* __restrict__
             for (int c = 0; c < CPT; ++c) ph[k][c] = make_float2(0.f, 0.f);
         }
     }
-    for (int w = 0; w < W; ++w) {
+    // real output: y[w] = A + B and y[W - w] = A - B with A = sum Re(Phi) cos-part, B = sum Im(Phi) sin-part (the cosine is
+    // even in w, the sine odd), so one pass over the modes gives two samples
+    auto emit = [&](int w, const float (&v)[CPT]) {
         float o[CPT];
         const int64_t off = (row * W + w) * (int64_t)C + c0;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) o[c] = 0.f;
+        for (int c = 0; c < CPT; ++c) o[c] = v[c];
         if (resid != nullptr && blockIdx.z == 0) {
-            if (CPT == 2) { const float2 r = __ldg(reinterpret_cast<const float2*>(resid + off)); o[0] = r.x; o[CPT - 1] = r.y; }
-            else o[0] = __ldg(resid + off);
+            if (CPT == 2) { const float2 r = __ldg(reinterpret_cast<const float2*>(resid + off)); o[0] += r.x; o[CPT - 1] += r.y; }
+            else o[0] += __ldg(resid + off);
         }
         if (resid2 != nullptr && blockIdx.z == 0) {      // second skip connection of the FourCastNet block (double_skip)
             if (CPT == 2) { const float2 r = __ldg(reinterpret_cast<const float2*>(resid2 + off)); o[0] += r.x; o[CPT - 1] += r.y; }
             else o[0] += __ldg(resid2 + off);
         }
+        if (CPT == 2) *reinterpret_cast<float2*>(y + off) = make_float2(o[0], o[CPT - 1]);
+        else y[off] = o[0];
+    };
+    for (int w = 0; w <= W / 2; ++w) {
+        float A[CPT], Bv[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) { A[c] = 0.f; Bv[c] = 0.f; }
 #pragma unroll
         for (int k = 0; k < KG; ++k) {
             const float2 t = tsm[k * W + w];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                o[c] = fmaf(ph[k][c].x, t.x, o[c]);
-                o[c] = fmaf(ph[k][c].y, t.y, o[c]);
+                A[c] = fmaf(ph[k][c].x, t.x, A[c]);
+                Bv[c] = fmaf(ph[k][c].y, t.y, Bv[c]);
             }
         }
-        if (CPT == 2) *reinterpret_cast<float2*>(y + off) = make_float2(o[0], o[CPT - 1]);
-        else y[off] = o[0];
+        float v[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) v[c] = A[c] + Bv[c];
+        emit(w, v);
+        if (w > 0 && 2 * w != W) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) v[c] = A[c] - Bv[c];
+            emit(W - w, v);
+        }
     }
 }
 
@@ -246,10 +272,113 @@ cl_coldft_kernel(const float2* __restrict__ in, const float2* __restrict__ tab /
     }
 }
 
-static int cl_coldft(const float2* in, const float2* tab, float2* out, int B, int I, int J, int Mx, int C, cudaStream_t st) {
+// Radix-2 folds of the column transform over a grid height H that is even (tab[j][i] = s exp(-+ 2 pi i ky_j y / H)):
+//   FOLD_IN  (analysis, I = H):  samples y and y + H/2 share their twiddles up to (-1)^ky, so the even frequencies see
+//            in[y] + in[y + H/2] and the odd ones in[y] - in[y + H/2] over half the samples
+//   FOLD_OUT (synthesis, J = H): out[y] = E + O and out[y + H/2] = +-(E - O) with E / O the sums over the even- / odd-indexed
+//            retained frequencies: one pass over the modes gives two rows
+// `first_odd`: the first retained frequency ky0 is odd (the parity then alternates with the index).
+template <int FOLD_IN>
+__global__ void __launch_bounds__(128)
+cl_coldft_fold_kernel(const float2* __restrict__ in, const float2* __restrict__ tab /*[J][I]*/, float2* __restrict__ out,
+                      int I, int J, int Mx, int C, int first_odd) {
+    __shared__ float2 ts[CLC_JG][CLC_IC + 1];
+    const int b = blockIdx.x / Mx, kx = blockIdx.x % Mx;
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    const bool active = c < C;
+    float2 acc[CLC_JG];
+#pragma unroll
+    for (int j = 0; j < CLC_JG; ++j) acc[j] = make_float2(0.f, 0.f);
+    if (FOLD_IN) {
+        const int j0 = blockIdx.z * CLC_JG;
+        const int Ih = I / 2;
+        for (int i0 = 0; i0 < Ih; i0 += CLC_IC) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < CLC_JG * CLC_IC; idx += 128) {
+                const int j = idx / CLC_IC, ii = idx % CLC_IC;
+                float2 v = make_float2(0.f, 0.f);
+                if (j0 + j < J && i0 + ii < Ih) v = __ldg(tab + (int64_t)(j0 + j) * I + i0 + ii);
+                ts[j][ii] = v;
+            }
+            __syncthreads();
+            if (active) {
+                const int in_ = min(CLC_IC, Ih - i0);
+                for (int ii = 0; ii < in_; ++ii) {
+                    const float2 t1 = __ldg(in + (((int64_t)b * I + i0 + ii) * Mx + kx) * C + c);
+                    const float2 t2 = __ldg(in + (((int64_t)b * I + i0 + ii + Ih) * Mx + kx) * C + c);
+                    const float2 sm = make_float2(t1.x + t2.x, t1.y + t2.y), df = make_float2(t1.x - t2.x, t1.y - t2.y);
+                    const float2 ve = first_odd ? df : sm, vo = first_odd ? sm : df;      // for even / odd output index
+#pragma unroll
+                    for (int j = 0; j < CLC_JG; ++j) cmac(acc[j], ts[j][ii], (j & 1) ? vo : ve);
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < CLC_JG; ++j)
+                if (j0 + j < J) out[(((int64_t)b * J + j0 + j) * Mx + kx) * C + c] = acc[j];
+        }
+    } else {
+        // acc[2r] / acc[2r + 1]: sums over the even- / odd-indexed inputs for output row j0 + r (r < CLC_JG / 2) of the first half
+        constexpr int RH = CLC_JG / 2;
+        const int j0 = blockIdx.z * RH;
+        const int Jh = J / 2;
+        for (int i0 = 0; i0 < I; i0 += CLC_IC) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < RH * CLC_IC; idx += 128) {
+                const int j = idx / CLC_IC, ii = idx % CLC_IC;
+                float2 v = make_float2(0.f, 0.f);
+                if (j0 + j < Jh && i0 + ii < I) v = __ldg(tab + (int64_t)(j0 + j) * I + i0 + ii);
+                ts[j][ii] = v;
+            }
+            __syncthreads();
+            if (active) {
+                const int in_ = min(CLC_IC, I - i0);               // CLC_IC is even: the index parity is that of ii
+                int ii = 0;
+                for (; ii + 1 < in_; ii += 2) {
+                    const float2 ta = __ldg(in + (((int64_t)b * I + i0 + ii) * Mx + kx) * C + c);
+                    const float2 tb = __ldg(in + (((int64_t)b * I + i0 + ii + 1) * Mx + kx) * C + c);
+#pragma unroll
+                    for (int r = 0; r < RH; ++r) {
+                        cmac(acc[2 * r], ts[r][ii], ta);
+                        cmac(acc[2 * r + 1], ts[r][ii + 1], tb);
+                    }
+                }
+                if (ii < in_) {
+                    const float2 ta = __ldg(in + (((int64_t)b * I + i0 + ii) * Mx + kx) * C + c);
+#pragma unroll
+                    for (int r = 0; r < RH; ++r) cmac(acc[2 * r], ts[r][ii], ta);
+                }
+            }
+        }
+        if (active) {
+            const float fs = first_odd ? -1.f : 1.f;
+#pragma unroll
+            for (int r = 0; r < RH; ++r) {
+                if (j0 + r < Jh) {
+                    const float2 e = acc[2 * r], o = acc[2 * r + 1];
+                    out[(((int64_t)b * J + j0 + r) * Mx + kx) * C + c] = make_float2(e.x + o.x, e.y + o.y);
+                    out[(((int64_t)b * J + j0 + r + Jh) * Mx + kx) * C + c] = make_float2(fs * (e.x - o.x), fs * (e.y - o.y));
+                }
+            }
+        }
+    }
+}
+
+// fold: 0 none, 1 inputs (I = H even), 2 outputs (J = H even)
+static int cl_coldft(const float2* in, const float2* tab, float2* out, int B, int I, int J, int Mx, int C, int fold, int first_odd,
+                     cudaStream_t st) {
     SB_REQUIRE((int64_t)B * Mx < (1LL << 31), "cl_coldft: too many columns");
-    dim3 grid((unsigned)(B * Mx), (unsigned)((C + 127) / 128), (unsigned)((J + CLC_JG - 1) / CLC_JG));
-    sb_launch(cl_coldft_kernel, grid, 128, 0, st, in, tab, out, I, J, Mx, C);
+    if (fold == 1) {
+        dim3 grid((unsigned)(B * Mx), (unsigned)((C + 127) / 128), (unsigned)((J + CLC_JG - 1) / CLC_JG));
+        sb_launch(cl_coldft_fold_kernel<1>, grid, 128, 0, st, in, tab, out, I, J, Mx, C, first_odd);
+    } else if (fold == 2) {
+        dim3 grid((unsigned)(B * Mx), (unsigned)((C + 127) / 128), (unsigned)((J / 2 + CLC_JG / 2 - 1) / (CLC_JG / 2)));
+        sb_launch(cl_coldft_fold_kernel<0>, grid, 128, 0, st, in, tab, out, I, J, Mx, C, first_odd);
+    } else {
+        dim3 grid((unsigned)(B * Mx), (unsigned)((C + 127) / 128), (unsigned)((J + CLC_JG - 1) / CLC_JG));
+        sb_launch(cl_coldft_kernel, grid, 128, 0, st, in, tab, out, I, J, Mx, C);
+    }
     SB_LAUNCH_CHECK();
     return 0;
 }
@@ -259,7 +388,7 @@ extern "C" int sb200_cl_coldft_fwd(sb200_plan_t p, int pass, const float* T, flo
     SB_REQUIRE(pass == 0 || pass == 1, "cl_coldft_fwd: pass must be 0 or 1");
     if (B <= 0 || C <= 0) return 0;
     return cl_coldft(reinterpret_cast<const float2*>(T), p->colF[pass], reinterpret_cast<float2*>(Xh), B, p->H, p->My,
-                     p->Mx, C, (cudaStream_t)stream);
+                     p->Mx, C, p->H % 2 == 0 ? 1 : 0, ((p->ky0 % 2) + 2) % 2, (cudaStream_t)stream);
 }
 
 extern "C" int sb200_cl_coldft_inv(sb200_plan_t p, int pass, const float* Yh, float* Phi, int B, int C, void* stream) {
@@ -267,7 +396,7 @@ extern "C" int sb200_cl_coldft_inv(sb200_plan_t p, int pass, const float* Yh, fl
     SB_REQUIRE(pass == 0 || pass == 1, "cl_coldft_inv: pass must be 0 or 1");
     if (B <= 0 || C <= 0) return 0;
     return cl_coldft(reinterpret_cast<const float2*>(Yh), p->colI[pass], reinterpret_cast<float2*>(Phi), B, p->My, p->H,
-                     p->Mx, C, (cudaStream_t)stream);
+                     p->Mx, C, p->H % 2 == 0 ? 2 : 0, ((p->ky0 % 2) + 2) % 2, (cudaStream_t)stream);
 }
 
 // ======================================================================================
