@@ -14,7 +14,13 @@
 constexpr int TW_WORKER_WARPS = 16;
 constexpr int TW_THREADS = 32 * (2 + TW_WORKER_WARPS);
 
+#ifdef SB200_BRINGUP
+#define TW_TRACE(role, i, ev) do { if (p.trace && blockIdx.x == 0 && (i) < 16) p.trace[((role) * 16 + (i)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TW_TRACE(role, i, ev) do { } while (0)
+#endif
 struct TcWgParams {
+    long long* trace;        // bring-up builds (SB200_WG_TRACE): clock64 log of CTA 0
     int Pc, Qc;              // channels of the A-side / B-side tensors
     int Qn;                  // UMMA N: Qc, or Qc + 16 when a constant ones-row is appended (bias gradient = sum of the A side)
     int mblocks;             // ceil(Pc / 128)
@@ -123,7 +129,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             const uint32_t mb_step = (128u * 128u) >> 4;
             uint32_t s = 0, ph = 0, ra = 0;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
+                TW_TRACE(1, q, 0);
                 tc::mbar_wait(((PASSES == 3 || ASRC == 1) ? split_bar : full_bar) + s, ph);
+                TW_TRACE(1, q, 1);
                 tc::tc_fence_after_sync();
                 const uint32_t base_lo = tc::desc_lo(tc::smem_u32(St + s * stage_bytes), 16);
                 const uint32_t dacc = tmem_base + ra * (uint32_t)(p.mblocks * p.Qn);
@@ -151,6 +159,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                     }
                 }
                 tc::umma_commit(empty_bar + s);
+                TW_TRACE(1, q, 2);
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 if (++ra == (uint32_t)p.R) ra = 0;
             }
@@ -163,19 +172,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             // thread -> 16-byte piece (4 px) `piece` of rows (wtid >> 3) + 64 i of every 32-px chunk
             const int piece = wtid & 7, row0 = wtid >> 3;
             const uint32_t items_per_b = (uint32_t)p.items_per_b;
+            // the rows of this thread (row0 + 64 i, Pc <= 256) never change: their w1 / b1 live in registers, and the row loop
+            // below is unrolled so that the four GELU chains of a chunk overlap (it was a serial loop with two global loads
+            // in front of every chain: 5600 cycles per 32-pixel item against ~1500 of MUFU + issue time)
+            float wv[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + 64 * i;
+                wv[i] = row < p.Pc ? __ldg(p.gen_w1 + row) : 0.f;
+                bv[i] = row < p.Pc ? __ldg(p.gen_b1 + row) : 0.f;
+            }
             uint32_t s = 0, ph = 0;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
                 const uint32_t item = (uint32_t)i0 + q;
                 const uint32_t b = item / items_per_b;
                 const int64_t px0 = (int64_t)(item - b * items_per_b) * 32 * CH;
+                if (wtid == 0) TW_TRACE(0, q, 0);
                 tc::mbar_wait(empty_bar + s, ph ^ 1);                 // MMAs that read this stage are done
+                if (wtid == 0) TW_TRACE(0, q, 1);
                 uint8_t* sb = St + s * stage_bytes;
                 for (int j = 0; j < CH; ++j) {
                     const int64_t px = px0 + 32 * j + piece * 4;
                     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (px + 4 <= p.HW) xv = __ldg(reinterpret_cast<const float4*>(p.gen_x + (int64_t)b * p.HW + px));
-                    for (int row = row0; row < p.Pc; row += 64) {
-                        const float w = __ldg(p.gen_w1 + row), bb = __ldg(p.gen_b1 + row);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = row0 + 64 * i;
+                        if (row >= p.Pc) break;
+                        const float w = wv[i], bb = bv[i];
                         float4 g = gelu4(make_float4(fmaf(w, xv.x, bb), fmaf(w, xv.y, bb), fmaf(w, xv.z, bb), fmaf(w, xv.w, bb)));
                         if (px + 4 > p.HW) g = make_float4(0.f, 0.f, 0.f, 0.f);     // pixels outside the image contribute nothing
                         const float4 h = make_float4(tc::tf32_trunc(g.x), tc::tf32_trunc(g.y), tc::tf32_trunc(g.z), tc::tf32_trunc(g.w));
@@ -185,7 +209,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
                             *reinterpret_cast<float4*>(sb + raw_bytes + off) = tc::tf32_lo4(g, h);
                     }
                 }
+                if (wtid == 0) TW_TRACE(0, q, 2);
                 tc::mbar_wait(full_bar + s, ph);                       // Q side landed
+                if (wtid == 0) TW_TRACE(0, q, 3);
                 if (PASSES == 3) {
                     for (int j = 0; j < CH; ++j) {
                         float4* ah = reinterpret_cast<float4*>(sb + (uint32_t)j * chunk_bytes + p_chunk);
@@ -346,6 +372,16 @@ static int tw_launch(const float* g, const float* x, float* gW, float* gbias, in
     const float* Qt = tr ? g : x;
 
     TcWgParams p;
+    p.trace = nullptr;
+#ifdef SB200_BRINGUP
+    static long long* trace_dev = nullptr;
+    const int want_trace = gen ? sb_env_int("SB200_WG_TRACE", 0) : 0;
+    if (want_trace) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 2 * 16 * 4 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 2 * 16 * 4 * sizeof(long long), st);
+        p.trace = trace_dev;
+    }
+#endif
     p.gen_x = gen_x; p.gen_w1 = gen_w1; p.gen_b1 = gen_b1;
     p.Pc = Pc; p.Qc = Qc; p.mblocks = (Pc + 127) / 128; p.HW = HW;
     // bias gradient = sum over pixels of g: free from the MMA when g is the A side (ones-row appended to the B side)
@@ -398,6 +434,27 @@ static int tw_launch(const float* g, const float* x, float* gW, float* gbias, in
         sb_launch(tc_wgrad_kernel<1>, grid, TW_THREADS, smem, st, tmP, tmQ, p);
     }
     SB_LAUNCH_CHECK();
+#ifdef SB200_BRINGUP
+    if (want_trace) {
+        static int calls = 0;
+        if (++calls == want_trace) {
+            long long h[2 * 16 * 4];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[0];
+            printf("tc_wgrad (generated A) trace, CTA 0, stages=%d CH=%d: workers(start, stage free, generated, Q landed) | mma(wait0, split ok, committed)\n", p.stages, p.CH);
+            for (int i = 0; i < 14; ++i) {
+                printf("  %2d:", i);
+                for (int r = 0; r < 2; ++r) {
+                    for (int e = 0; e < (r ? 3 : 4); ++e) printf(" %7lld", h[(r * 16 + i) * 4 + e] ? h[(r * 16 + i) * 4 + e] - t0 : -1);
+                    printf("   |");
+                }
+                printf("\n");
+            }
+            fflush(stdout);
+        }
+    }
+#endif
     const int64_t E = (int64_t)Pc * (bias_mma ? Qc + 1 : Qc);
     sb_launch(tc_wgrad_reduce_kernel, (unsigned)ceil_div64(E, 8), 256, 0, st, workspace, gW, bias_mma ? gbias : nullptr, Pc, Qc, p.Qn,
                                                                        p.mblocks * 128, (int)grid, tr);
