@@ -96,18 +96,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    // contiguous item range of this CTA
-    const int64_t per = (p.nitems + gridDim.x - 1) / gridDim.x;
-    const int64_t i0 = (int64_t)blockIdx.x * per;
-    const int64_t i1 = i0 + per < p.nitems ? i0 + per : p.nitems;
-    const int64_t my_items = i1 > i0 ? i1 - i0 : 0;
+    // items of this CTA: blockIdx.x, blockIdx.x + grid, ... (interleaved: at any moment the CTAs of the grid work on
+    // neighbouring 32-pixel chunks of the same channel rows, i.e. on the same DRAM pages, instead of 148 regions of their own)
+    const int64_t i0 = blockIdx.x, istride = gridDim.x;
+    const int64_t my_items = i0 < p.nitems ? (p.nitems - i0 + istride - 1) / istride : 0;
 
     if (warp == 0) {
         if (tc::elect_one()) {
             uint32_t s = 0, ph = 0;
             const uint32_t items_per_b = (uint32_t)p.items_per_b;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
-                const uint32_t item = (uint32_t)i0 + q;
+                const uint32_t item = (uint32_t)(i0 + (int64_t)q * istride);
                 const uint32_t b = item / items_per_b;
                 const int px0 = (int)((item - b * items_per_b) * 32u * (uint32_t)CH);
                 tc::mbar_wait(empty_bar + s, ph ^ 1);
@@ -184,7 +183,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapP, const __grid_constant
             }
             uint32_t s = 0, ph = 0;
             for (uint32_t q = 0; q < (uint32_t)my_items; ++q) {
-                const uint32_t item = (uint32_t)i0 + q;
+                const uint32_t item = (uint32_t)(i0 + (int64_t)q * istride);
                 const uint32_t b = item / items_per_b;
                 const int64_t px0 = (int64_t)(item - b * items_per_b) * 32 * CH;
                 if (wtid == 0) TW_TRACE(0, q, 0);
