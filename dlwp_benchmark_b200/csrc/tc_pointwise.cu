@@ -644,7 +644,7 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (uint32_t)p.N * (p.corr ? 2u : 1u);
             if constexpr (EPI == 5) {
                 // ---- fused head forward: this warp's columns -> one partial dot product per pixel ----
-                float part = 0.f;
+                float part = 0.f, part1 = 0.f, part2 = 0.f, part3 = 0.f;      // four chains instead of one 64-deep FMA chain
                 for (int c0 = c_begin; c0 < c_end; c0 += 16) {
 #ifdef SB200_BRINGUP
                     if (p.dbg & 2) break;
@@ -666,11 +666,12 @@ tc_pointwise_kernel(const __grid_constant__ CUtensorMap tmapA, const TcPwParams 
                             gelu2(g2, g3);
                         }
                         part = fmaf(wq.x, g0, part);
-                        part = fmaf(wq.y, g1, part);
-                        part = fmaf(wq.z, g2, part);
-                        part = fmaf(wq.w, g3, part);
+                        part1 = fmaf(wq.y, g1, part1);
+                        part2 = fmaf(wq.z, g2, part2);
+                        part3 = fmaf(wq.w, g3, part3);
                     }
                 }
+                part = (part + part1) + (part2 + part3);
                 tc::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(tempty_bar + a);
